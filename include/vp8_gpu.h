@@ -1,0 +1,122 @@
+/*
+ * vp8_gpu.h - C-ABI of libvp8gpu.so: the B200 pixel-reconstruction path of a VP8 key-frame
+ * (lossy WebP) decoder. Plain pointers and sizes only; no CUDA or torch types in any signature.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) The seven symbols the reference's main.c / main_ultra.c bind from its m06..m09 modules.
+ *      Linking the reference's unmodified main.c + m01..m05 objects against this library instead of
+ *      its m06..m09 objects yields a decoder whose -yuv / -yuvf / -ppm / -png output is byte-identical
+ *      (INTEGRATION.md). They are batch-of-one wrappers over group (2).
+ *
+ *  (2) Batch entry points (vp8_gpu_*): many frames per launch, device-resident intermediates.
+ *
+ * Error convention (same as the reference, vp8_recon.c:361-364,425-428; vp8_loopfilter.c:202-209):
+ * 0 on success, -1 with errno = EINVAL (bad arguments), ENOMEM (host or device allocation),
+ * EIO (CUDA runtime failure; vp8_gpu_last_error() has the text). There is NO CPU fallback: without a
+ * usable CUDA device every pixel entry point fails with EIO.
+ */
+#ifndef VP8_GPU_H
+#define VP8_GPU_H
+
+#include "vp8_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- (1) reference module interfaces */
+
+/* replaces reference src/m06_recon/vp8_recon.h:20-21 (vp8_recon.c:360-393) - host planes, malloc'ed */
+int yuv420_alloc(Yuv420Image* img, uint32_t width, uint32_t height);
+void yuv420_free(Yuv420Image* img);
+
+/* replaces reference src/m06_recon/vp8_recon.h:25 (vp8_recon.c:714-716): m06 only, cropped */
+int vp8_reconstruct_keyframe_yuv(const Vp8KeyFrameHeader* kf, const Vp8DecodedFrame* decoded, Yuv420Image* out);
+
+/* replaces reference src/m06_recon/vp8_recon.h:28 (vp8_recon.c:718-720): m06 + m07, cropped */
+int vp8_reconstruct_keyframe_yuv_filtered(const Vp8KeyFrameHeader* kf, const Vp8DecodedFrame* decoded, Yuv420Image* out);
+
+/* replaces reference src/m07_loopfilter/vp8_loopfilter.h:14 (vp8_loopfilter.c:201-283): in place on a
+ * macroblock-aligned host image */
+int vp8_loopfilter_apply_keyframe(Yuv420Image* padded_img, const Vp8DecodedFrame* decoded);
+
+/* replaces reference src/m08_yuv2rgb_ppm/yuv2rgb_ppm.h:10 (yuv2rgb_ppm.c:123-206) */
+int yuv420_write_ppm_fd(int fd, const Yuv420Image* img);
+
+/* replaces reference src/m09_png/yuv2rgb_png.h:10 (yuv2rgb_png.c:208-364) */
+int yuv420_write_png_fd(int fd, const Yuv420Image* img);
+
+/* ---------------------------------------------------------------- (2) batch interface */
+
+typedef struct vp8_gpu_ctx vp8_gpu_ctx;     /* one per GPU per host thread */
+typedef struct vp8_gpu_batch vp8_gpu_batch; /* n frames resident on the device */
+
+/* stream: a cudaStream_t passed as void* (e.g. torch.cuda.current_stream().cuda_stream), or NULL for a
+ * private stream. All work of the context is issued on that stream. */
+int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out);
+void vp8_gpu_destroy(vp8_gpu_ctx* ctx);
+int vp8_gpu_sync(vp8_gpu_ctx* ctx);
+const char* vp8_gpu_last_error(void);
+
+/* Tuning: warps cooperating on one image (4, 8, 16 or 32; 0 = pick from the batch size) and resident
+ * images per SM (0 = as many as fit). */
+int vp8_gpu_set_tuning(vp8_gpu_ctx* ctx, int warps_per_image, int images_per_sm);
+
+/* Pinned host memory: frames whose arrays live here are copied to the device without staging. */
+void* vp8_gpu_host_alloc(size_t bytes);
+void vp8_gpu_host_free(void* p);
+
+/* Stage the ten per-frame arrays of n decoded frames (vp8_tokens.h:52-99) into device memory.
+ * kf[i] supplies the visible width/height (vp8_header.h:7-18). Inputs are borrowed for the duration
+ * of the call only. */
+int vp8_gpu_upload(vp8_gpu_ctx* ctx, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,
+                   vp8_gpu_batch** out);
+void vp8_gpu_batch_free(vp8_gpu_ctx* ctx, vp8_gpu_batch* b);
+
+/* m06 on the device: upload + reconstruction (no loop filter) into macroblock-aligned planes.
+ * = vp8_gpu_upload + vp8_gpu_run(b, 0, VP8_GPU_PADDED). */
+int vp8_gpu_recon(vp8_gpu_ctx* ctx, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,
+                  vp8_gpu_batch** out);
+
+/* m07 on the device: in-place loop filter over the batch's macroblock-aligned planes
+ * (requires a batch produced with VP8_GPU_PADDED and not yet filtered). */
+int vp8_gpu_filter(vp8_gpu_ctx* ctx, vp8_gpu_batch* b);
+
+/* m08 on the device: fancy-upsampled RGB24 of the visible frame from the batch's current planes. */
+int vp8_gpu_rgb(vp8_gpu_ctx* ctx, vp8_gpu_batch* b);
+
+enum { VP8_GPU_TIGHT = 0, VP8_GPU_PADDED = 1 };
+
+/* One pass over an uploaded batch: reconstruction, fused with the loop filter when filtered != 0.
+ * VP8_GPU_TIGHT writes cropped I420 (stride = width) directly, which is what -yuv / -yuvf emit. */
+int vp8_gpu_run(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, int filtered, int layout);
+
+/* Results. "packed" = one host buffer, frame i at offsets[i]; its bytes are exactly the -yuv/-yuvf file
+ * (Y, U, V tight) resp. the -ppm file ("P6\n<w> <h>\n255\n" + RGB). dst may be pinned or pageable. */
+size_t vp8_gpu_i420_bytes(const vp8_gpu_batch* b);
+size_t vp8_gpu_ppm_bytes(const vp8_gpu_batch* b);
+int vp8_gpu_download_i420(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes);
+int vp8_gpu_download_ppm(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes);
+/* Callee-allocated images as the reference returns them (three malloc planes each; yuv420_free). */
+int vp8_gpu_download_images(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, Yuv420Image* out);
+/* Macroblock-aligned planes of frame i (VP8_GPU_PADDED batches), for inspection. */
+int vp8_gpu_download_padded(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, int i, uint8_t* y, uint8_t* u, uint8_t* v);
+
+/* Introspection for the benchmark. */
+int vp8_gpu_batch_size(const vp8_gpu_batch* b);
+uint64_t vp8_gpu_launch_count(const vp8_gpu_ctx* ctx); /* kernels launched by this context so far */
+uint64_t vp8_gpu_h2d_bytes(const vp8_gpu_ctx* ctx);
+uint64_t vp8_gpu_d2h_bytes(const vp8_gpu_ctx* ctx);
+int vp8_gpu_last_launch_config(const vp8_gpu_ctx* ctx, int* warps_per_image, int* grid, int* smem_bytes);
+
+/* Host-side per-frame parameter derivation, exported so tests can pin it against the oracle:
+ * dq[4][6] = {y1dc,y1ac,uvdc,uvac,y2dc,y2ac} per segment (vp8_recon.c:57-76);
+ * lf[4][2][4] = {level, interior limit, hev threshold, 0} per segment and per (ymode==B_PRED)
+ * (vp8_loopfilter.c:166-199). */
+void vp8_gpu_frame_params(const Vp8DecodedFrame* f, int16_t dq[4][6], uint8_t lf[4][2][4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VP8_GPU_H */

@@ -1,0 +1,67 @@
+// vp8_dev.h - descriptors shared between the host library and the kernels.
+#pragma once
+#include <stdint.h>
+
+// One decoded key frame as the kernels see it. All pointers are device pointers.
+// Built on the host by vp8_gpu.cu from a Vp8DecodedFrame (reference vp8_tokens.h:52-99).
+struct Vp8ImgDesc {
+	uint32_t mb_cols, mb_rows;
+
+	// Output planes. Pixels with x < out_w and y < out_h are stored, so the reference's crop
+	// (vp8_recon.c:693-707) is a store predicate, not a pass.
+	uint32_t out_w, out_h;
+	uint32_t out_stride_y, out_stride_uv;
+	uint8_t* out_y;
+	uint8_t* out_u;
+	uint8_t* out_v;
+
+	// Source planes of the stand-alone loop-filter stage (padded, unfiltered); unused when reconstructing.
+	const uint8_t* src_y;
+	const uint8_t* src_u;
+	const uint8_t* src_v;
+	uint32_t src_stride_y, src_stride_uv;
+
+	// Dense coefficients and per-macroblock syntax, in the reference's own array layout.
+	const int16_t* coeff_y;  // [mb*256]
+	const int16_t* coeff_u;  // [mb*64]
+	const int16_t* coeff_v;  // [mb*64]
+	const int16_t* coeff_y2; // [mb*16]
+	const uint8_t* ymode;
+	const uint8_t* uv_mode;
+	const uint8_t* bmode;
+	const uint8_t* segment_id; // null unless segmentation is enabled
+	const uint8_t* has_coeff;  // may be null (treated as 0, vp8_loopfilter.c:226)
+
+	// Per-segment dequantisation factors {y1dc,y1ac,uvdc,uvac,y2dc,y2ac} (vp8_recon.c:57-76).
+	int16_t dq[4][6];
+	// Per-segment, per-(ymode==B_PRED) loop filter {level, interior limit, hev threshold, 0}
+	// (vp8_loopfilter.c:166-199).
+	uint8_t lf[4][2][4];
+	uint8_t lf_simple;
+	uint8_t pad_[7];
+};
+
+// Work item of the RGB kernel: one image, tight I420 in, tight RGB24 out.
+struct Vp8RgbDesc {
+	const uint8_t* y;
+	const uint8_t* u;
+	const uint8_t* v;
+	uint8_t* rgb;
+	uint32_t width, height;
+	uint32_t stride_y, stride_uv;
+	uint32_t first_block; // prefix sum of blocks over the batch
+	uint32_t pad_;
+};
+
+enum Vp8KernelMode {
+	VP8_K_RECON = 0,        // m06 only: unfiltered pixels out
+	VP8_K_RECON_FILTER = 1, // m06+m07 fused: filtered pixels out, single pass
+	VP8_K_FILTER = 2,       // m07 only: padded unfiltered planes in, filtered planes out (in place allowed)
+};
+
+// Launchers (vp8_kernels.cu). warps_per_image in {4, 8, 16, 32}. Return cudaError_t as int.
+int vp8_launch_wavefront(int mode, int warps_per_image, const Vp8ImgDesc* descs_dev, int n_images, int max_mb_cols,
+                         int grid_ctas, void* stream);
+int vp8_wavefront_smem_bytes(int mode, int warps_per_image, int max_mb_cols);
+int vp8_wavefront_max_ctas_per_sm(int mode, int warps_per_image, int max_mb_cols);
+int vp8_launch_rgb(const Vp8RgbDesc* descs_dev, int n_images, uint32_t total_blocks, void* stream);

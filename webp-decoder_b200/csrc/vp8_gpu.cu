@@ -1,0 +1,1125 @@
+// vp8_gpu.cu - host side of libvp8gpu.so: contexts, batches, staging, and the C-ABI of include/vp8_gpu.h.
+//
+// The only compute done on the host is per-frame header arithmetic (a few dozen integers: dequantisation
+// factors and loop-filter levels per segment) and file framing (PPM header, PNG container). Every pixel is
+// produced by the kernels in vp8_kernels.cu; there is no CPU fallback.
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vp8_gpu.h"
+#include "vp8_dev.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int err, const char* what, cudaError_t ce = cudaSuccess) {
+	g_err = what;
+	if (ce != cudaSuccess) {
+		g_err += ": ";
+		g_err += cudaGetErrorString(ce);
+	}
+	errno = err;
+	return -1;
+}
+
+#define CU(call)                                                   \
+	do {                                                           \
+		cudaError_t e__ = (call);                                  \
+		if (e__ != cudaSuccess) return fail(EIO, #call, e__);      \
+	} while (0)
+
+constexpr size_t kAlign = 256;
+constexpr size_t kBounceBytes = 32u << 20;
+constexpr int kPpmSlot = 32; // header slot in front of each RGB image; RGB starts 32 bytes into the slot
+
+inline size_t align_up(size_t v, size_t a = kAlign) { return (v + a - 1) / a * a; }
+
+bool is_pinned(const void* p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeHost;
+}
+
+struct FreeBlock {
+	void* p;
+	size_t bytes;
+};
+
+} // namespace
+
+struct vp8_gpu_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	int sm_count = 0;
+	int tune_warps = 0, tune_imgs_per_sm = 0;
+	uint8_t* bounce[2] = {nullptr, nullptr};
+	cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+	bool bounce_busy[2] = {false, false};
+	std::vector<FreeBlock> cache; // device blocks kept for reuse
+	uint64_t launches = 0, h2d = 0, d2h = 0;
+	int last_warps = 0, last_grid = 0, last_smem = 0;
+};
+
+namespace {
+
+struct FrameMeta {
+	uint32_t width, height, mb_cols, mb_rows;
+	size_t in_off[9];   // coeff_y, coeff_u, coeff_v, coeff_y2, bmode, ymode, uv_mode, segment_id, has_coeff
+	bool has_seg, has_hc;
+	size_t tight_off;   // tight I420 (Y|U|V) within d_tight
+	size_t pad_off[3];  // padded planes within d_pad
+	size_t rgb_off;     // slot within d_rgb (RGB at +kPpmSlot)
+	int16_t dq[4][6];
+	uint8_t lf[4][2][4];
+	uint8_t lf_simple;
+	bool any_filter;
+};
+
+enum PlaneState { PLANES_NONE = 0, PLANES_TIGHT, PLANES_PADDED };
+
+} // namespace
+
+struct vp8_gpu_batch {
+	int n = 0;
+	std::vector<FrameMeta> meta;
+	uint8_t* d_in = nullptr;
+	size_t in_bytes = 0;
+	uint8_t* d_tight = nullptr;
+	size_t tight_bytes = 0;
+	uint8_t* d_pad = nullptr;
+	size_t pad_bytes = 0;
+	uint8_t* d_rgb = nullptr;
+	size_t rgb_bytes = 0;
+	Vp8ImgDesc* d_desc = nullptr;
+	Vp8RgbDesc* d_rgbdesc = nullptr;
+	int max_mb_cols = 0;
+	PlaneState state = PLANES_NONE;
+	bool filtered = false, have_rgb = false, have_coeffs = true;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ device memory
+int dev_alloc(vp8_gpu_ctx* c, size_t bytes, void** out) {
+	bytes = align_up(bytes ? bytes : 1, 1u << 20);
+	int best = -1;
+	for (int i = 0; i < (int)c->cache.size(); i++)
+		if (c->cache[i].bytes >= bytes && c->cache[i].bytes <= 2 * bytes &&
+		    (best < 0 || c->cache[i].bytes < c->cache[best].bytes))
+			best = i;
+	if (best >= 0) {
+		*out = c->cache[best].p;
+		c->cache.erase(c->cache.begin() + best);
+		return 0;
+	}
+	cudaError_t e = cudaMalloc(out, bytes);
+	if (e != cudaSuccess) {
+		// drop the cache and retry once
+		for (auto& b : c->cache) cudaFree(b.p);
+		c->cache.clear();
+		e = cudaMalloc(out, bytes);
+	}
+	if (e != cudaSuccess) return fail(ENOMEM, "cudaMalloc", e);
+	return 0;
+}
+
+size_t dev_block_bytes(size_t bytes) { return align_up(bytes ? bytes : 1, 1u << 20); }
+
+void dev_release(vp8_gpu_ctx* c, void* p, size_t bytes) {
+	if (!p) return;
+	c->cache.push_back({p, dev_block_bytes(bytes)});
+	size_t total = 0;
+	for (auto& b : c->cache) total += b.bytes;
+	while (c->cache.size() > 16 || total > (64ull << 30)) { // bound what we hold on to
+		total -= c->cache.front().bytes;
+		cudaFree(c->cache.front().p);
+		c->cache.erase(c->cache.begin());
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ staging
+int ensure_bounce(vp8_gpu_ctx* c) {
+	for (int i = 0; i < 2; i++) {
+		if (!c->bounce[i]) {
+			CU(cudaHostAlloc((void**)&c->bounce[i], kBounceBytes, cudaHostAllocDefault));
+			CU(cudaEventCreateWithFlags(&c->bounce_ev[i], cudaEventDisableTiming));
+		}
+	}
+	return 0;
+}
+
+// Host -> device. Pinned sources go straight to the copy engine; pageable ones are double-buffered through
+// pinned bounce buffers so the memcpy of chunk k+1 overlaps the DMA of chunk k.
+struct Uploader {
+	vp8_gpu_ctx* c;
+	int cur = 0;
+	size_t fill = 0;          // bytes staged in bounce[cur]
+	uint8_t* dev_at = nullptr; // device address matching bounce[cur][0]
+
+	int flush() {
+		if (fill) {
+			CU(cudaMemcpyAsync(dev_at, c->bounce[cur], fill, cudaMemcpyHostToDevice, c->stream));
+			CU(cudaEventRecord(c->bounce_ev[cur], c->stream));
+			c->bounce_busy[cur] = true;
+			cur ^= 1;
+			fill = 0;
+			dev_at = nullptr;
+		}
+		return 0;
+	}
+	int acquire() {
+		if (c->bounce_busy[cur]) {
+			CU(cudaEventSynchronize(c->bounce_ev[cur]));
+			c->bounce_busy[cur] = false;
+		}
+		return 0;
+	}
+	int put(uint8_t* dev, const void* src, size_t bytes) {
+		if (!bytes) return 0;
+		c->h2d += bytes;
+		if (is_pinned(src)) {
+			CU(cudaMemcpyAsync(dev, src, bytes, cudaMemcpyHostToDevice, c->stream));
+			return 0;
+		}
+		if (ensure_bounce(c)) return -1;
+		const uint8_t* s = (const uint8_t*)src;
+		while (bytes) {
+			// continue the current chunk only if this piece lands right behind (or within alignment slack of) it
+			if (fill && (dev < dev_at + fill || dev > dev_at + fill + kAlign || (size_t)(dev - dev_at) >= kBounceBytes)) {
+				if (flush()) return -1;
+			}
+			if (!fill) {
+				if (acquire()) return -1;
+				dev_at = dev;
+			}
+			const size_t at = (size_t)(dev - dev_at);
+			const size_t take = std::min(bytes, kBounceBytes - at);
+			memcpy(c->bounce[cur] + at, s, take);
+			fill = at + take;
+			dev += take;
+			s += take;
+			bytes -= take;
+			if (fill == kBounceBytes && flush()) return -1;
+		}
+		return 0;
+	}
+};
+
+// Device -> host for one contiguous range.
+int download(vp8_gpu_ctx* c, void* dst, const uint8_t* dev, size_t bytes) {
+	if (!bytes) return 0;
+	c->d2h += bytes;
+	if (is_pinned(dst)) {
+		CU(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		return 0;
+	}
+	if (ensure_bounce(c)) return -1;
+	for (int i = 0; i < 2; i++)
+		if (c->bounce_busy[i]) {
+			CU(cudaEventSynchronize(c->bounce_ev[i]));
+			c->bounce_busy[i] = false;
+		}
+	uint8_t* d = (uint8_t*)dst;
+	size_t off = 0, pend_off[2] = {0, 0}, pend_len[2] = {0, 0};
+	auto drain = [&](int k) -> int {
+		CU(cudaEventSynchronize(c->bounce_ev[k]));
+		memcpy(d + pend_off[k], c->bounce[k], pend_len[k]);
+		pend_len[k] = 0;
+		return 0;
+	};
+	// keep one chunk in flight while the previous one is copied out
+	for (int k = 0;; k ^= 1) {
+		bool issued = false;
+		if (off < bytes) {
+			const size_t len = std::min(kBounceBytes, bytes - off);
+			CU(cudaMemcpyAsync(c->bounce[k], dev + off, len, cudaMemcpyDeviceToHost, c->stream));
+			CU(cudaEventRecord(c->bounce_ev[k], c->stream));
+			pend_off[k] = off;
+			pend_len[k] = len;
+			off += len;
+			issued = true;
+		}
+		if (pend_len[k ^ 1] && drain(k ^ 1)) return -1;
+		if (!issued) {
+			if (pend_len[k] && drain(k)) return -1;
+			break;
+		}
+	}
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ frame parameters
+// RFC 6386 14.1 quantiser tables.
+const uint16_t kDcQ[128] = {
+    4,   5,   6,   7,   8,   9,   10,  10,  11,  12,  13,  14,  15,  16,  17,  17,  18,  19,  20,  20,  21,  21,
+    22,  22,  23,  23,  24,  25,  25,  26,  27,  28,  29,  30,  31,  32,  33,  34,  35,  36,  37,  37,  38,  39,
+    40,  41,  42,  43,  44,  45,  46,  46,  47,  48,  49,  50,  51,  52,  53,  54,  55,  56,  57,  58,  59,  60,
+    61,  62,  63,  64,  65,  66,  67,  68,  69,  70,  71,  72,  73,  74,  75,  76,  76,  77,  78,  79,  80,  81,
+    82,  83,  84,  85,  86,  87,  88,  89,  91,  93,  95,  96,  98,  100, 101, 102, 104, 106, 108, 110, 112, 114,
+    116, 118, 122, 124, 126, 128, 130, 132, 134, 136, 138, 140, 143, 145, 148, 151, 154, 157};
+const uint16_t kAcQ[128] = {
+    4,   5,   6,   7,   8,   9,   10,  11,  12,  13,  14,  15,  16,  17,  18,  19,  20,  21,  22,  23,  24,  25,
+    26,  27,  28,  29,  30,  31,  32,  33,  34,  35,  36,  37,  38,  39,  40,  41,  42,  43,  44,  45,  46,  47,
+    48,  49,  50,  51,  52,  53,  54,  55,  56,  57,  58,  60,  62,  64,  66,  68,  70,  72,  74,  76,  78,  80,
+    82,  84,  86,  88,  90,  92,  94,  96,  98,  100, 102, 104, 106, 108, 110, 112, 114, 116, 119, 122, 125, 128,
+    131, 134, 137, 140, 143, 146, 149, 152, 155, 158, 161, 164, 167, 170, 173, 177, 181, 185, 189, 193, 197, 201,
+    205, 209, 213, 217, 221, 225, 229, 234, 239, 245, 249, 254, 259, 264, 269, 274, 279, 284};
+
+inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+void frame_params(const Vp8DecodedFrame* f, int16_t dq[4][6], uint8_t lf[4][2][4]) {
+	for (int s = 0; s < 4; s++) {
+		// dequantisation factors (reference dequant_init, vp8_recon.c:57-76)
+		int q = f->q_index;
+		if (f->segmentation_enabled) q = f->segmentation_abs ? f->seg_quant_idx[s] : q + f->seg_quant_idx[s];
+		dq[s][0] = (int16_t)kDcQ[clampi(q + f->y1_dc_delta_q, 0, 127)];
+		dq[s][1] = (int16_t)kAcQ[clampi(q, 0, 127)];
+		dq[s][2] = (int16_t)std::min<int>(kDcQ[clampi(q + f->uv_dc_delta_q, 0, 127)], 132);
+		dq[s][3] = (int16_t)kAcQ[clampi(q + f->uv_ac_delta_q, 0, 127)];
+		dq[s][4] = (int16_t)(2 * kDcQ[clampi(q + f->y2_dc_delta_q, 0, 127)]);
+		dq[s][5] = (int16_t)std::max(kAcQ[clampi(q + f->y2_ac_delta_q, 0, 127)] * 155 / 100, 8);
+
+		// loop-filter strength (reference calc_params_keyframe, vp8_loopfilter.c:166-199)
+		for (int b = 0; b < 2; b++) {
+			int lvl = f->lf_level;
+			if (f->segmentation_enabled) lvl = f->segmentation_abs ? f->seg_lf_level[s] : lvl + f->seg_lf_level[s];
+			lvl = clampi(lvl, 0, 63);
+			if (f->lf_delta_enabled) {
+				lvl += f->lf_ref_delta[0];
+				if (b) lvl += f->lf_mode_delta[0];
+				lvl = clampi(lvl, 0, 63);
+			}
+			int in = lvl;
+			if (f->lf_sharpness) {
+				in >>= (f->lf_sharpness > 4) ? 2 : 1;
+				in = std::min(in, 9 - (int)f->lf_sharpness);
+			}
+			in = std::max(in, 1);
+			lf[s][b][0] = (uint8_t)lvl;
+			lf[s][b][1] = (uint8_t)in;
+			lf[s][b][2] = (uint8_t)((lvl >= 15) + (lvl >= 40));
+			lf[s][b][3] = 0;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ batches
+void batch_destroy(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
+	if (!b) return;
+	// work queued on the stream may still reference these blocks
+	cudaStreamSynchronize(c->stream);
+	dev_release(c, b->d_in, b->in_bytes);
+	dev_release(c, b->d_tight, b->tight_bytes);
+	dev_release(c, b->d_pad, b->pad_bytes);
+	dev_release(c, b->d_rgb, b->rgb_bytes);
+	dev_release(c, b->d_desc, sizeof(Vp8ImgDesc) * b->n);
+	dev_release(c, b->d_rgbdesc, sizeof(Vp8RgbDesc) * b->n);
+	delete b;
+}
+
+int validate_frame(const Vp8KeyFrameHeader* kf, const Vp8DecodedFrame* f, bool need_coeffs) {
+	if (!kf || !f) return fail(EINVAL, "null frame");
+	if (kf->width == 0 || kf->height == 0) return fail(EINVAL, "zero frame size");
+	if (f->mb_cols != (kf->width + 15u) / 16u || f->mb_rows != (kf->height + 15u) / 16u || f->mb_cols > 1024 ||
+	    f->mb_rows > 1024)
+		return fail(EINVAL, "macroblock grid does not match the frame size");
+	if (!f->ymode) return fail(EINVAL, "missing ymode");
+	if (f->segmentation_enabled && !f->segment_id) return fail(EINVAL, "missing segment_id");
+	if (need_coeffs && (!f->uv_mode || !f->bmode || !f->coeff_y || !f->coeff_u || !f->coeff_v || !f->coeff_y2))
+		return fail(EINVAL, "missing mode/coefficient arrays");
+	return 0;
+}
+
+// Lay out and upload the per-frame arrays. With need_coeffs == false only what the loop filter reads is staged.
+int batch_create(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* fr, int n, bool need_coeffs,
+                 vp8_gpu_batch** out) {
+	if (!c || !kf || !fr || !out || n <= 0) return fail(EINVAL, "bad arguments");
+	for (int i = 0; i < n; i++)
+		if (validate_frame(kf[i], fr[i], need_coeffs)) return -1;
+	CU(cudaSetDevice(c->device));
+
+	vp8_gpu_batch* b = new (std::nothrow) vp8_gpu_batch;
+	if (!b) return fail(ENOMEM, "batch");
+	b->n = n;
+	b->have_coeffs = need_coeffs;
+	b->meta.resize(n);
+	size_t in = 0, tight = 0, pad = 0, rgb = 0;
+	for (int i = 0; i < n; i++) {
+		FrameMeta& m = b->meta[i];
+		const Vp8DecodedFrame* f = fr[i];
+		m.width = kf[i]->width;
+		m.height = kf[i]->height;
+		m.mb_cols = f->mb_cols;
+		m.mb_rows = f->mb_rows;
+		const size_t mb = (size_t)m.mb_cols * m.mb_rows;
+		m.has_seg = f->segmentation_enabled && f->segment_id;
+		m.has_hc = f->has_coeff != nullptr;
+		const size_t sz[9] = {need_coeffs ? mb * 512 : 0, need_coeffs ? mb * 128 : 0, need_coeffs ? mb * 128 : 0,
+		                      need_coeffs ? mb * 32 : 0,  need_coeffs ? mb * 16 : 0,  mb,
+		                      need_coeffs ? mb : 0,       m.has_seg ? mb : 0,         m.has_hc ? mb : 0};
+		for (int k = 0; k < 9; k++) {
+			m.in_off[k] = in;
+			in += align_up(sz[k]);
+		}
+		const size_t cw = (m.width + 1) / 2, ch = (m.height + 1) / 2;
+		m.tight_off = tight;
+		tight += align_up((size_t)m.width * m.height + 2 * cw * ch);
+		const size_t pw = (size_t)m.mb_cols * 16, ph = (size_t)m.mb_rows * 16;
+		m.pad_off[0] = pad;
+		pad += align_up(pw * ph);
+		m.pad_off[1] = pad;
+		pad += align_up(pw * ph / 4);
+		m.pad_off[2] = pad;
+		pad += align_up(pw * ph / 4);
+		m.rgb_off = rgb;
+		rgb += align_up(kPpmSlot + (size_t)m.width * m.height * 3);
+		frame_params(f, m.dq, m.lf);
+		m.lf_simple = f->lf_use_simple;
+		m.any_filter = false;
+		for (int s = 0; s < (m.has_seg ? 4 : 1); s++)
+			for (int k = 0; k < 2; k++) m.any_filter |= m.lf[s][k][0] != 0;
+		b->max_mb_cols = std::max<int>(b->max_mb_cols, m.mb_cols);
+	}
+	b->in_bytes = in;
+	b->tight_bytes = tight;
+	b->pad_bytes = pad;
+	b->rgb_bytes = rgb;
+
+	if (dev_alloc(c, in, (void**)&b->d_in) || dev_alloc(c, sizeof(Vp8ImgDesc) * n, (void**)&b->d_desc)) {
+		batch_destroy(c, b);
+		return -1;
+	}
+	Uploader up{c};
+	for (int i = 0; i < n; i++) {
+		const FrameMeta& m = b->meta[i];
+		const Vp8DecodedFrame* f = fr[i];
+		const size_t mb = (size_t)m.mb_cols * m.mb_rows;
+		const void* src[9] = {f->coeff_y, f->coeff_u, f->coeff_v, f->coeff_y2, f->bmode, f->ymode, f->uv_mode, f->segment_id, f->has_coeff};
+		const size_t sz[9] = {need_coeffs ? mb * 512 : 0, need_coeffs ? mb * 128 : 0, need_coeffs ? mb * 128 : 0,
+		                      need_coeffs ? mb * 32 : 0,  need_coeffs ? mb * 16 : 0,  mb,
+		                      need_coeffs ? mb : 0,       m.has_seg ? mb : 0,         m.has_hc ? mb : 0};
+		for (int k = 0; k < 9; k++)
+			if (sz[k] && up.put(b->d_in + m.in_off[k], src[k], sz[k])) {
+				batch_destroy(c, b);
+				return -1;
+			}
+	}
+	if (up.flush()) {
+		batch_destroy(c, b);
+		return -1;
+	}
+	*out = b;
+	return 0;
+}
+
+int ensure_planes(vp8_gpu_ctx* c, vp8_gpu_batch* b, int layout) {
+	if (layout == VP8_GPU_TIGHT && !b->d_tight) return dev_alloc(c, b->tight_bytes, (void**)&b->d_tight);
+	if (layout == VP8_GPU_PADDED && !b->d_pad) return dev_alloc(c, b->pad_bytes, (void**)&b->d_pad);
+	return 0;
+}
+
+// Descriptors for one launch. kernel_mode: Vp8KernelMode; layout: where the pixels go.
+int push_descs(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layout) {
+	std::vector<Vp8ImgDesc> h(b->n);
+	for (int i = 0; i < b->n; i++) {
+		const FrameMeta& m = b->meta[i];
+		Vp8ImgDesc& d = h[i];
+		memset(&d, 0, sizeof(d));
+		d.mb_cols = m.mb_cols;
+		d.mb_rows = m.mb_rows;
+		const uint32_t pw = m.mb_cols * 16, ph = m.mb_rows * 16;
+		if (layout == VP8_GPU_TIGHT) {
+			const size_t cw = (m.width + 1) / 2, ch = (m.height + 1) / 2;
+			d.out_w = m.width;
+			d.out_h = m.height;
+			d.out_stride_y = m.width;
+			d.out_stride_uv = (uint32_t)cw;
+			d.out_y = b->d_tight + m.tight_off;
+			d.out_u = d.out_y + (size_t)m.width * m.height;
+			d.out_v = d.out_u + cw * ch;
+		} else {
+			d.out_w = pw;
+			d.out_h = ph;
+			d.out_stride_y = pw;
+			d.out_stride_uv = pw / 2;
+			d.out_y = b->d_pad + m.pad_off[0];
+			d.out_u = b->d_pad + m.pad_off[1];
+			d.out_v = b->d_pad + m.pad_off[2];
+		}
+		if (kernel_mode == VP8_K_FILTER) {
+			d.src_y = b->d_pad + m.pad_off[0];
+			d.src_u = b->d_pad + m.pad_off[1];
+			d.src_v = b->d_pad + m.pad_off[2];
+			d.src_stride_y = pw;
+			d.src_stride_uv = pw / 2;
+		}
+		const uint8_t* in = b->d_in;
+		d.coeff_y = (const int16_t*)(in + m.in_off[0]);
+		d.coeff_u = (const int16_t*)(in + m.in_off[1]);
+		d.coeff_v = (const int16_t*)(in + m.in_off[2]);
+		d.coeff_y2 = (const int16_t*)(in + m.in_off[3]);
+		d.bmode = in + m.in_off[4];
+		d.ymode = in + m.in_off[5];
+		d.uv_mode = in + m.in_off[6];
+		d.segment_id = m.has_seg ? in + m.in_off[7] : nullptr;
+		d.has_coeff = m.has_hc ? in + m.in_off[8] : nullptr;
+		memcpy(d.dq, m.dq, sizeof(d.dq));
+		memcpy(d.lf, m.lf, sizeof(d.lf));
+		d.lf_simple = m.lf_simple;
+	}
+	// pageable source: the runtime stages it before returning, so the vector may die right after
+	CU(cudaMemcpyAsync(b->d_desc, h.data(), sizeof(Vp8ImgDesc) * b->n, cudaMemcpyHostToDevice, c->stream));
+	return 0;
+}
+
+int pick_warps(const vp8_gpu_ctx* c, int n_images) {
+	if (c->tune_warps) return c->tune_warps;
+	const int per_sm = (n_images + c->sm_count - 1) / c->sm_count;
+	int w = 32 / std::max(per_sm, 1);
+	if (w >= 32) return 32;
+	if (w >= 16) return 16;
+	if (w >= 8) return 8;
+	return 4;
+}
+
+int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layout) {
+	if (push_descs(c, b, kernel_mode, layout)) return -1;
+	int warps = pick_warps(c, b->n);
+	int per_sm = 0;
+	for (;; warps /= 2) {
+		per_sm = vp8_wavefront_max_ctas_per_sm(kernel_mode, warps, b->max_mb_cols);
+		if (per_sm > 0 || warps == 4) break;
+	}
+	if (per_sm <= 0) return fail(EIO, "wavefront kernel does not fit on an SM (frame too wide?)", cudaGetLastError());
+	if (c->tune_imgs_per_sm > 0) per_sm = std::min(per_sm, c->tune_imgs_per_sm);
+	const int grid = std::min(b->n, per_sm * c->sm_count);
+	const int rc = vp8_launch_wavefront(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, c->stream);
+	if (rc != 0) return fail(EIO, "wavefront launch", (cudaError_t)rc);
+	c->launches++;
+	c->last_warps = warps;
+	c->last_grid = grid;
+	c->last_smem = vp8_wavefront_smem_bytes(kernel_mode, warps, b->max_mb_cols);
+	return 0;
+}
+
+int ppm_header(char* buf, uint32_t w, uint32_t h) { return snprintf(buf, 32, "P6\n%u %u\n255\n", w, h); }
+
+// ------------------------------------------------------------------------------------------------ default context
+std::mutex g_default_mu;
+vp8_gpu_ctx* g_default = nullptr;
+
+vp8_gpu_ctx* default_ctx() {
+	if (!g_default) {
+		int dev = 0;
+		if (const char* e = getenv("VP8_GPU_DEVICE")) dev = atoi(e);
+		if (vp8_gpu_init(dev, nullptr, &g_default) != 0) g_default = nullptr;
+	}
+	return g_default;
+}
+
+int write_all(int fd, const void* p, size_t n) {
+	const uint8_t* s = (const uint8_t*)p;
+	while (n) {
+		ssize_t k = write(fd, s, n);
+		if (k < 0) {
+			if (errno == EINTR) continue;
+			return -1;
+		}
+		s += k;
+		n -= (size_t)k;
+	}
+	return 0;
+}
+
+// RGB24 of a host I420 image through the device (K3 only).
+int rgb_of_host_image(vp8_gpu_ctx* c, const Yuv420Image* img, std::vector<uint8_t>& rgb) {
+	const uint32_t w = img->width, h = img->height, cw = (w + 1) / 2, ch = (h + 1) / 2;
+	const size_t ysz = (size_t)w * h, csz = (size_t)cw * ch, total = align_up(ysz) + 2 * align_up(csz);
+	const size_t rgb_bytes = ysz * 3;
+	uint8_t *d_in = nullptr, *d_rgb = nullptr;
+	Vp8RgbDesc* d_desc = nullptr;
+	if (dev_alloc(c, total, (void**)&d_in)) return -1;
+	if (dev_alloc(c, rgb_bytes, (void**)&d_rgb) || dev_alloc(c, sizeof(Vp8RgbDesc), (void**)&d_desc)) {
+		dev_release(c, d_in, total);
+		dev_release(c, d_rgb, rgb_bytes);
+		return -1;
+	}
+	int rc = 0;
+	Uploader up{c};
+	uint8_t* dy = d_in;
+	uint8_t* du = d_in + align_up(ysz);
+	uint8_t* dv = du + align_up(csz);
+	// tighten strides on the way in
+	for (uint32_t r = 0; r < h && !rc; r++) rc = up.put(dy + (size_t)r * w, img->y + (size_t)r * img->stride_y, w);
+	for (uint32_t r = 0; r < ch && !rc; r++) rc = up.put(du + (size_t)r * cw, img->u + (size_t)r * img->stride_uv, cw);
+	for (uint32_t r = 0; r < ch && !rc; r++) rc = up.put(dv + (size_t)r * cw, img->v + (size_t)r * img->stride_uv, cw);
+	if (!rc) rc = up.flush();
+	if (!rc) {
+		Vp8RgbDesc d{dy, du, dv, d_rgb, w, h, w, cw, 0, 0};
+		cudaError_t e = cudaMemcpyAsync(d_desc, &d, sizeof(d), cudaMemcpyHostToDevice, c->stream);
+		if (e != cudaSuccess) rc = fail(EIO, "descriptor upload", e);
+	}
+	if (!rc) {
+		const uint32_t groups = ((w + 3) / 4) * h;
+		const int lrc = vp8_launch_rgb(d_desc, 1, (groups + 255) / 256, c->stream);
+		if (lrc) rc = fail(EIO, "rgb launch", (cudaError_t)lrc);
+		else c->launches++;
+	}
+	if (!rc) {
+		rgb.resize(rgb_bytes);
+		rc = download(c, rgb.data(), d_rgb, rgb_bytes);
+	}
+	cudaStreamSynchronize(c->stream);
+	dev_release(c, d_in, total);
+	dev_release(c, d_rgb, rgb_bytes);
+	dev_release(c, d_desc, sizeof(Vp8RgbDesc));
+	return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ PNG framing
+// Stored-deflate PNG as the reference frames it (yuv2rgb_png.c:208-364): signature, IHDR, a single IDAT holding
+// a zlib stream of stored blocks of at most 65535 bytes over filter-0 scanlines, Adler-32, IEND.
+uint32_t g_crc_tab[8][256];
+std::once_flag g_crc_once;
+void crc_build() {
+	for (uint32_t i = 0; i < 256; i++) {
+		uint32_t v = i;
+		for (int k = 0; k < 8; k++) v = (v & 1) ? 0xEDB88320u ^ (v >> 1) : v >> 1;
+		g_crc_tab[0][i] = v;
+	}
+	for (uint32_t i = 0; i < 256; i++)
+		for (int t = 1; t < 8; t++) g_crc_tab[t][i] = g_crc_tab[0][g_crc_tab[t - 1][i] & 255] ^ (g_crc_tab[t - 1][i] >> 8);
+}
+uint32_t crc_update(uint32_t crc, const uint8_t* p, size_t n) { // slice-by-8
+	while (n && ((uintptr_t)p & 7)) {
+		crc = g_crc_tab[0][(crc ^ *p++) & 255] ^ (crc >> 8);
+		n--;
+	}
+	while (n >= 8) {
+		uint64_t v;
+		memcpy(&v, p, 8);
+		v ^= crc;
+		crc = g_crc_tab[7][v & 255] ^ g_crc_tab[6][(v >> 8) & 255] ^ g_crc_tab[5][(v >> 16) & 255] ^ g_crc_tab[4][(v >> 24) & 255] ^
+		      g_crc_tab[3][(v >> 32) & 255] ^ g_crc_tab[2][(v >> 40) & 255] ^ g_crc_tab[1][(v >> 48) & 255] ^ g_crc_tab[0][v >> 56];
+		p += 8;
+		n -= 8;
+	}
+	while (n--) crc = g_crc_tab[0][(crc ^ *p++) & 255] ^ (crc >> 8);
+	return crc;
+}
+void adler_update(uint32_t& a, uint32_t& b, const uint8_t* p, size_t n) {
+	while (n) {
+		size_t k = std::min<size_t>(n, 5552); // largest run that cannot overflow 32 bits
+		n -= k;
+		while (k--) {
+			a += *p++;
+			b += a;
+		}
+		a %= 65521;
+		b %= 65521;
+	}
+}
+void be32(uint8_t* p, uint32_t v) {
+	p[0] = (uint8_t)(v >> 24);
+	p[1] = (uint8_t)(v >> 16);
+	p[2] = (uint8_t)(v >> 8);
+	p[3] = (uint8_t)v;
+}
+
+int png_frame(const uint8_t* rgb, uint32_t w, uint32_t h, std::vector<uint8_t>& out) {
+	std::call_once(g_crc_once, crc_build);
+	const size_t row = (size_t)w * 3, line = row + 1, raw = line * h;
+	if (raw > 0x7FFFFFFFu) return fail(EFBIG, "image too large for a single IDAT");
+	const size_t blocks = (raw + 65534) / 65535, zsize = 2 + raw + 5 * blocks + 4;
+	out.resize(8 + 25 + 12 + zsize + 12);
+	uint8_t* o = out.data();
+	static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+	memcpy(o, sig, 8);
+	o += 8;
+	auto chunk_end = [](uint8_t* start, uint32_t len) { // start -> length field; data already in place
+		be32(start, len);
+		be32(start + 8 + len, crc_update(0xFFFFFFFFu, start + 4, 4 + (size_t)len) ^ 0xFFFFFFFFu);
+		return start + 12 + len;
+	};
+	memcpy(o + 4, "IHDR", 4);
+	be32(o + 8, w);
+	be32(o + 12, h);
+	o[16] = 8;
+	o[17] = 2;
+	o[18] = o[19] = o[20] = 0;
+	o = chunk_end(o, 13);
+
+	memcpy(o + 4, "IDAT", 4);
+	uint8_t* z = o + 8;
+	size_t zp = 0;
+	z[zp++] = 0x78;
+	z[zp++] = 0x01;
+	uint32_t a = 1, b = 0;
+	size_t pos = 0; // position in the scanline stream
+	while (pos < raw) {
+		const size_t len = std::min<size_t>(raw - pos, 65535);
+		z[zp++] = (pos + len == raw) ? 1 : 0;
+		z[zp++] = (uint8_t)(len & 255);
+		z[zp++] = (uint8_t)(len >> 8);
+		z[zp++] = (uint8_t)(~len & 255);
+		z[zp++] = (uint8_t)((~len >> 8) & 255);
+		size_t left = len;
+		while (left) { // copy scanline pieces: filter byte, then RGB
+			const size_t r = pos / line, col = pos % line;
+			size_t take;
+			if (col == 0) {
+				z[zp] = 0;
+				take = 1;
+			} else {
+				take = std::min(left, line - col);
+				memcpy(z + zp, rgb + r * row + (col - 1), take);
+			}
+			adler_update(a, b, z + zp, take);
+			zp += take;
+			pos += take;
+			left -= take;
+		}
+	}
+	be32(z + zp, (b << 16) | a);
+	zp += 4;
+	o = chunk_end(o, (uint32_t)zp);
+	memcpy(o + 4, "IEND", 4);
+	o = chunk_end(o, 0);
+	out.resize((size_t)(o - out.data()));
+	return 0;
+}
+
+} // namespace
+
+// ================================================================================================ C-ABI: batch interface
+extern "C" {
+
+const char* vp8_gpu_last_error(void) { return g_err.c_str(); }
+
+int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out) {
+	if (!out) return fail(EINVAL, "null out");
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) return fail(EIO, "no CUDA device (this library has no CPU fallback)", e);
+	if (device < 0 || device >= count) return fail(EINVAL, "bad device index");
+	CU(cudaSetDevice(device));
+	vp8_gpu_ctx* c = new (std::nothrow) vp8_gpu_ctx;
+	if (!c) return fail(ENOMEM, "context");
+	c->device = device;
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, device));
+	c->sm_count = prop.multiProcessorCount;
+	if (stream) {
+		c->stream = (cudaStream_t)stream;
+	} else {
+		cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+		if (se != cudaSuccess) {
+			delete c;
+			return fail(EIO, "cudaStreamCreate", se);
+		}
+		c->own_stream = true;
+	}
+	if (const char* w = getenv("VP8_GPU_WARPS")) c->tune_warps = atoi(w);
+	if (const char* w = getenv("VP8_GPU_IMAGES_PER_SM")) c->tune_imgs_per_sm = atoi(w);
+	*out = c;
+	return 0;
+}
+
+void vp8_gpu_destroy(vp8_gpu_ctx* c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	for (auto& b : c->cache) cudaFree(b.p);
+	for (int i = 0; i < 2; i++) {
+		if (c->bounce[i]) cudaFreeHost(c->bounce[i]);
+		if (c->bounce_ev[i]) cudaEventDestroy(c->bounce_ev[i]);
+	}
+	if (c->own_stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int vp8_gpu_sync(vp8_gpu_ctx* c) {
+	if (!c) return fail(EINVAL, "null context");
+	CU(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int vp8_gpu_set_tuning(vp8_gpu_ctx* c, int warps_per_image, int images_per_sm) {
+	if (!c || (warps_per_image != 0 && warps_per_image != 4 && warps_per_image != 8 && warps_per_image != 16 && warps_per_image != 32) ||
+	    images_per_sm < 0)
+		return fail(EINVAL, "bad tuning");
+	c->tune_warps = warps_per_image;
+	c->tune_imgs_per_sm = images_per_sm;
+	return 0;
+}
+
+void* vp8_gpu_host_alloc(size_t bytes) {
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+		cudaGetLastError();
+		errno = ENOMEM;
+		return nullptr;
+	}
+	return p;
+}
+
+void vp8_gpu_host_free(void* p) {
+	if (p) cudaFreeHost(p);
+}
+
+int vp8_gpu_upload(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,
+                   vp8_gpu_batch** out) {
+	return batch_create(c, kf, frames, n, true, out);
+}
+
+void vp8_gpu_batch_free(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
+	if (c && b) batch_destroy(c, b);
+}
+
+int vp8_gpu_run(vp8_gpu_ctx* c, vp8_gpu_batch* b, int filtered, int layout) {
+	if (!c || !b || (layout != VP8_GPU_TIGHT && layout != VP8_GPU_PADDED)) return fail(EINVAL, "bad arguments");
+	if (!b->have_coeffs) return fail(EINVAL, "batch holds no coefficients");
+	CU(cudaSetDevice(c->device));
+	if (ensure_planes(c, b, layout)) return -1;
+	// frames whose every macroblock has filter level 0 come out of m07 unchanged (vp8_loopfilter.c:220), so a
+	// batch made only of such frames takes the reconstruction-only kernel
+	bool any = false;
+	for (auto& m : b->meta) any |= m.any_filter;
+	const int mode = (filtered && any) ? VP8_K_RECON_FILTER : VP8_K_RECON;
+	if (launch_wavefront(c, b, mode, layout)) return -1;
+	b->state = layout == VP8_GPU_TIGHT ? PLANES_TIGHT : PLANES_PADDED;
+	b->filtered = filtered != 0;
+	b->have_rgb = false;
+	return 0;
+}
+
+int vp8_gpu_recon(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,
+                  vp8_gpu_batch** out) {
+	vp8_gpu_batch* b = nullptr;
+	if (batch_create(c, kf, frames, n, true, &b)) return -1;
+	if (vp8_gpu_run(c, b, 0, VP8_GPU_PADDED)) {
+		batch_destroy(c, b);
+		return -1;
+	}
+	*out = b;
+	return 0;
+}
+
+int vp8_gpu_filter(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
+	if (!c || !b) return fail(EINVAL, "bad arguments");
+	if (b->state != PLANES_PADDED || b->filtered) return fail(EINVAL, "vp8_gpu_filter needs unfiltered macroblock-aligned planes");
+	CU(cudaSetDevice(c->device));
+	bool any = false;
+	for (auto& m : b->meta) any |= m.any_filter;
+	if (any && launch_wavefront(c, b, VP8_K_FILTER, VP8_GPU_PADDED)) return -1;
+	b->filtered = true;
+	b->have_rgb = false;
+	return 0;
+}
+
+int vp8_gpu_rgb(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
+	if (!c || !b) return fail(EINVAL, "bad arguments");
+	if (b->state == PLANES_NONE) return fail(EINVAL, "no planes to convert; run reconstruction first");
+	CU(cudaSetDevice(c->device));
+	if (!b->d_rgb && dev_alloc(c, b->rgb_bytes, (void**)&b->d_rgb)) return -1;
+	if (!b->d_rgbdesc && dev_alloc(c, sizeof(Vp8RgbDesc) * b->n, (void**)&b->d_rgbdesc)) return -1;
+	std::vector<Vp8RgbDesc> h(b->n);
+	uint32_t max_blocks = 0;
+	for (int i = 0; i < b->n; i++) {
+		const FrameMeta& m = b->meta[i];
+		Vp8RgbDesc& d = h[i];
+		memset(&d, 0, sizeof(d));
+		d.width = m.width;
+		d.height = m.height;
+		if (b->state == PLANES_TIGHT) {
+			const size_t cw = (m.width + 1) / 2, ch = (m.height + 1) / 2;
+			d.y = b->d_tight + m.tight_off;
+			d.u = d.y + (size_t)m.width * m.height;
+			d.v = d.u + cw * ch;
+			d.stride_y = m.width;
+			d.stride_uv = (uint32_t)cw;
+		} else {
+			d.y = b->d_pad + m.pad_off[0];
+			d.u = b->d_pad + m.pad_off[1];
+			d.v = b->d_pad + m.pad_off[2];
+			d.stride_y = m.mb_cols * 16;
+			d.stride_uv = m.mb_cols * 8;
+		}
+		d.rgb = b->d_rgb + m.rgb_off + kPpmSlot;
+		const uint32_t groups = ((m.width + 3) / 4) * m.height;
+		max_blocks = std::max(max_blocks, (groups + 255) / 256);
+	}
+	CU(cudaMemcpyAsync(b->d_rgbdesc, h.data(), sizeof(Vp8RgbDesc) * b->n, cudaMemcpyHostToDevice, c->stream));
+	const int rc = vp8_launch_rgb(b->d_rgbdesc, b->n, max_blocks, c->stream);
+	if (rc) return fail(EIO, "rgb launch", (cudaError_t)rc);
+	c->launches++;
+	b->have_rgb = true;
+	return 0;
+}
+
+size_t vp8_gpu_i420_bytes(const vp8_gpu_batch* b) { return b ? b->tight_bytes : 0; }
+size_t vp8_gpu_ppm_bytes(const vp8_gpu_batch* b) { return b ? b->rgb_bytes : 0; }
+int vp8_gpu_batch_size(const vp8_gpu_batch* b) { return b ? b->n : 0; }
+
+int vp8_gpu_download_i420(vp8_gpu_ctx* c, vp8_gpu_batch* b, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes) {
+	if (!c || !b || !dst) return fail(EINVAL, "bad arguments");
+	if (b->state != PLANES_TIGHT) return fail(EINVAL, "tight planes required (vp8_gpu_run with VP8_GPU_TIGHT)");
+	if (cap < b->tight_bytes) return fail(EINVAL, "destination too small");
+	CU(cudaSetDevice(c->device));
+	const FrameMeta& last = b->meta.back();
+	const size_t used = last.tight_off + (size_t)last.width * last.height + 2 * (size_t)((last.width + 1) / 2) * ((last.height + 1) / 2);
+	if (download(c, dst, b->d_tight, used)) return -1;
+	for (int i = 0; i < b->n; i++) {
+		const FrameMeta& m = b->meta[i];
+		if (offsets) offsets[i] = m.tight_off;
+		if (sizes) sizes[i] = (size_t)m.width * m.height + 2 * (size_t)((m.width + 1) / 2) * ((m.height + 1) / 2);
+	}
+	return 0;
+}
+
+int vp8_gpu_download_ppm(vp8_gpu_ctx* c, vp8_gpu_batch* b, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes) {
+	if (!c || !b || !dst) return fail(EINVAL, "bad arguments");
+	if (!b->have_rgb) return fail(EINVAL, "run vp8_gpu_rgb first");
+	if (cap < b->rgb_bytes) return fail(EINVAL, "destination too small");
+	CU(cudaSetDevice(c->device));
+	const FrameMeta& last = b->meta.back();
+	const size_t used = last.rgb_off + kPpmSlot + (size_t)last.width * last.height * 3;
+	if (download(c, dst, b->d_rgb, used)) return -1;
+	for (int i = 0; i < b->n; i++) {
+		const FrameMeta& m = b->meta[i];
+		char hdr[32];
+		const int hl = ppm_header(hdr, m.width, m.height);
+		memcpy(dst + m.rgb_off + kPpmSlot - hl, hdr, hl);
+		if (offsets) offsets[i] = m.rgb_off + kPpmSlot - hl;
+		if (sizes) sizes[i] = hl + (size_t)m.width * m.height * 3;
+	}
+	return 0;
+}
+
+int vp8_gpu_download_padded(vp8_gpu_ctx* c, vp8_gpu_batch* b, int i, uint8_t* y, uint8_t* u, uint8_t* v) {
+	if (!c || !b || i < 0 || i >= b->n || !y || !u || !v) return fail(EINVAL, "bad arguments");
+	if (b->state != PLANES_PADDED) return fail(EINVAL, "macroblock-aligned planes required");
+	CU(cudaSetDevice(c->device));
+	const FrameMeta& m = b->meta[i];
+	const size_t px = (size_t)m.mb_cols * 16 * m.mb_rows * 16;
+	if (download(c, y, b->d_pad + m.pad_off[0], px) || download(c, u, b->d_pad + m.pad_off[1], px / 4) ||
+	    download(c, v, b->d_pad + m.pad_off[2], px / 4))
+		return -1;
+	return 0;
+}
+
+int vp8_gpu_download_images(vp8_gpu_ctx* c, vp8_gpu_batch* b, Yuv420Image* out) {
+	if (!c || !b || !out) return fail(EINVAL, "bad arguments");
+	if (b->state == PLANES_NONE) return fail(EINVAL, "nothing reconstructed yet");
+	CU(cudaSetDevice(c->device));
+	int done = 0, rc = 0;
+	for (; done < b->n && !rc; done++) {
+		const FrameMeta& m = b->meta[done];
+		Yuv420Image* img = &out[done];
+		if (yuv420_alloc(img, m.width, m.height)) {
+			rc = -1;
+			break;
+		}
+		const size_t cw = (m.width + 1) / 2, ch = (m.height + 1) / 2;
+		if (b->state == PLANES_TIGHT) {
+			const uint8_t* s = b->d_tight + m.tight_off;
+			rc = download(c, img->y, s, (size_t)m.width * m.height) || download(c, img->u, s + (size_t)m.width * m.height, cw * ch) ||
+			     download(c, img->v, s + (size_t)m.width * m.height + cw * ch, cw * ch);
+		} else {
+			// crop while copying (reference vp8_recon.c:693-707)
+			const size_t pw = (size_t)m.mb_cols * 16;
+			cudaError_t e = cudaMemcpy2DAsync(img->y, m.width, b->d_pad + m.pad_off[0], pw, m.width, m.height, cudaMemcpyDeviceToHost, c->stream);
+			if (e == cudaSuccess) e = cudaMemcpy2DAsync(img->u, cw, b->d_pad + m.pad_off[1], pw / 2, cw, ch, cudaMemcpyDeviceToHost, c->stream);
+			if (e == cudaSuccess) e = cudaMemcpy2DAsync(img->v, cw, b->d_pad + m.pad_off[2], pw / 2, cw, ch, cudaMemcpyDeviceToHost, c->stream);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+			if (e != cudaSuccess) rc = fail(EIO, "cropping download", e);
+			c->d2h += (size_t)m.width * m.height + 2 * cw * ch;
+		}
+		if (rc) yuv420_free(img);
+	}
+	if (rc) {
+		const int saved = errno;
+		for (int i = 0; i < done; i++) yuv420_free(&out[i]);
+		errno = saved;
+		return -1;
+	}
+	return 0;
+}
+
+uint64_t vp8_gpu_launch_count(const vp8_gpu_ctx* c) { return c ? c->launches : 0; }
+uint64_t vp8_gpu_h2d_bytes(const vp8_gpu_ctx* c) { return c ? c->h2d : 0; }
+uint64_t vp8_gpu_d2h_bytes(const vp8_gpu_ctx* c) { return c ? c->d2h : 0; }
+
+int vp8_gpu_last_launch_config(const vp8_gpu_ctx* c, int* warps, int* grid, int* smem) {
+	if (!c) return fail(EINVAL, "null context");
+	if (warps) *warps = c->last_warps;
+	if (grid) *grid = c->last_grid;
+	if (smem) *smem = c->last_smem;
+	return 0;
+}
+
+void vp8_gpu_frame_params(const Vp8DecodedFrame* f, int16_t dq[4][6], uint8_t lf[4][2][4]) { frame_params(f, dq, lf); }
+
+// ================================================================================================ C-ABI: reference module interfaces
+
+int yuv420_alloc(Yuv420Image* img, uint32_t width, uint32_t height) {
+	if (!img || width == 0 || height == 0) {
+		errno = EINVAL;
+		return -1;
+	}
+	memset(img, 0, sizeof(*img));
+	img->width = width;
+	img->height = height;
+	img->stride_y = width;
+	img->stride_uv = (width + 1) / 2;
+	const size_t ysz = (size_t)width * height, csz = (size_t)img->stride_uv * ((height + 1) / 2);
+	img->y = (uint8_t*)malloc(ysz);
+	img->u = (uint8_t*)malloc(csz);
+	img->v = (uint8_t*)malloc(csz);
+	if (!img->y || !img->u || !img->v) {
+		yuv420_free(img);
+		errno = ENOMEM;
+		return -1;
+	}
+	memset(img->y, 0, ysz);
+	memset(img->u, 128, csz);
+	memset(img->v, 128, csz);
+	return 0;
+}
+
+void yuv420_free(Yuv420Image* img) {
+	if (!img) return;
+	free(img->y);
+	free(img->u);
+	free(img->v);
+	memset(img, 0, sizeof(*img));
+}
+
+static int reconstruct_one(const Vp8KeyFrameHeader* kf, const Vp8DecodedFrame* decoded, Yuv420Image* out, int filtered) {
+	if (!kf || !decoded || !out) {
+		errno = EINVAL;
+		return -1;
+	}
+	std::lock_guard<std::mutex> lock(g_default_mu);
+	vp8_gpu_ctx* c = default_ctx();
+	if (!c) return -1;
+	vp8_gpu_batch* b = nullptr;
+	if (vp8_gpu_upload(c, &kf, &decoded, 1, &b)) return -1;
+	Yuv420Image img;
+	int rc = vp8_gpu_run(c, b, filtered, VP8_GPU_TIGHT);
+	if (!rc) rc = vp8_gpu_download_images(c, b, &img);
+	const int saved = errno;
+	batch_destroy(c, b);
+	if (rc) {
+		errno = saved;
+		return -1;
+	}
+	*out = img;
+	return 0;
+}
+
+int vp8_reconstruct_keyframe_yuv(const Vp8KeyFrameHeader* kf, const Vp8DecodedFrame* decoded, Yuv420Image* out) {
+	return reconstruct_one(kf, decoded, out, 0);
+}
+
+int vp8_reconstruct_keyframe_yuv_filtered(const Vp8KeyFrameHeader* kf, const Vp8DecodedFrame* decoded, Yuv420Image* out) {
+	return reconstruct_one(kf, decoded, out, 1);
+}
+
+int vp8_loopfilter_apply_keyframe(Yuv420Image* img, const Vp8DecodedFrame* decoded) {
+	if (!img || !decoded || !img->y || !img->u || !img->v) {
+		errno = EINVAL;
+		return -1;
+	}
+	if (img->width != decoded->mb_cols * 16u || img->height != decoded->mb_rows * 16u) {
+		errno = EINVAL;
+		return -1;
+	}
+	std::lock_guard<std::mutex> lock(g_default_mu);
+	vp8_gpu_ctx* c = default_ctx();
+	if (!c) return -1;
+	Vp8KeyFrameHeader kf;
+	memset(&kf, 0, sizeof(kf));
+	kf.width = (uint16_t)img->width;
+	kf.height = (uint16_t)img->height;
+	const Vp8KeyFrameHeader* kfp = &kf;
+	vp8_gpu_batch* b = nullptr;
+	if (batch_create(c, &kfp, &decoded, 1, false, &b)) return -1;
+	int rc = ensure_planes(c, b, VP8_GPU_PADDED);
+	const FrameMeta& m = b->meta[0];
+	const uint32_t pw = img->width, ph = img->height;
+	if (!rc) {
+		Uploader up{c};
+		for (uint32_t r = 0; r < ph && !rc; r++) rc = up.put(b->d_pad + m.pad_off[0] + (size_t)r * pw, img->y + (size_t)r * img->stride_y, pw);
+		for (uint32_t r = 0; r < ph / 2 && !rc; r++) rc = up.put(b->d_pad + m.pad_off[1] + (size_t)r * (pw / 2), img->u + (size_t)r * img->stride_uv, pw / 2);
+		for (uint32_t r = 0; r < ph / 2 && !rc; r++) rc = up.put(b->d_pad + m.pad_off[2] + (size_t)r * (pw / 2), img->v + (size_t)r * img->stride_uv, pw / 2);
+		if (!rc) rc = up.flush();
+	}
+	if (!rc) {
+		b->state = PLANES_PADDED;
+		b->filtered = false;
+		rc = vp8_gpu_filter(c, b);
+	}
+	if (!rc) {
+		std::vector<uint8_t> tmp((size_t)pw * ph * 3 / 2);
+		uint8_t *ty = tmp.data(), *tu = ty + (size_t)pw * ph, *tv = tu + (size_t)pw * ph / 4;
+		rc = vp8_gpu_download_padded(c, b, 0, ty, tu, tv);
+		for (uint32_t r = 0; r < ph && !rc; r++) memcpy(img->y + (size_t)r * img->stride_y, ty + (size_t)r * pw, pw);
+		for (uint32_t r = 0; r < ph / 2 && !rc; r++) {
+			memcpy(img->u + (size_t)r * img->stride_uv, tu + (size_t)r * (pw / 2), pw / 2);
+			memcpy(img->v + (size_t)r * img->stride_uv, tv + (size_t)r * (pw / 2), pw / 2);
+		}
+	}
+	const int saved = errno;
+	batch_destroy(c, b);
+	if (rc) {
+		errno = saved;
+		return -1;
+	}
+	return 0;
+}
+
+static int rgb_for_writer(int fd, const Yuv420Image* img, std::vector<uint8_t>& rgb) {
+	if (fd < 0 || !img || !img->y || !img->u || !img->v || img->width == 0 || img->height == 0) {
+		errno = EINVAL;
+		return -1;
+	}
+	std::lock_guard<std::mutex> lock(g_default_mu);
+	vp8_gpu_ctx* c = default_ctx();
+	if (!c) return -1;
+	return rgb_of_host_image(c, img, rgb);
+}
+
+int yuv420_write_ppm_fd(int fd, const Yuv420Image* img) {
+	std::vector<uint8_t> rgb;
+	if (rgb_for_writer(fd, img, rgb)) return -1;
+	char hdr[32];
+	const int hl = ppm_header(hdr, img->width, img->height);
+	if (write_all(fd, hdr, (size_t)hl) || write_all(fd, rgb.data(), rgb.size())) return -1;
+	return 0;
+}
+
+int yuv420_write_png_fd(int fd, const Yuv420Image* img) {
+	std::vector<uint8_t> rgb, png;
+	if (rgb_for_writer(fd, img, rgb)) return -1;
+	if (png_frame(rgb.data(), img->width, img->height, png)) return -1;
+	return write_all(fd, png.data(), png.size());
+}
+
+} // extern "C"

@@ -1,0 +1,897 @@
+// vp8_kernels.cu - sm_100a kernels for the VP8 key-frame pixel path.
+//
+//   vp8_mb_wavefront<NW, RECON, FILTER>
+//       dequantisation + inverse WHT/DCT + intra prediction + residual add   (reference m06, vp8_recon.c:423-684)
+//       fused with the in-loop deblocking filter                             (reference m07, vp8_loopfilter.c:201-283)
+//       and the crop to the visible frame                                    (vp8_recon.c:693-707).
+//   vp8_i420_to_rgb
+//       libwebp-exact fixed-point YUV->RGB with fancy upsampling              (reference m08, yuv2rgb_ppm.c:30-121,164-201).
+//
+// Execution model of the wavefront kernel
+// ---------------------------------------
+// One CTA owns one image at a time; many images are in flight per launch (grid-stride over the batch).
+// Inside the CTA, warp w owns macroblock rows w, w+NW, ... and walks each row left to right, one macroblock
+// per iteration, all 32 lanes cooperating on that macroblock. MB(x,y) needs MB(x-1,y) (same warp, previous
+// iteration) and MB(x,y-1), MB(x+1,y-1) (the warp one row up), so the only synchronisation is a per-row progress
+// stamp in shared memory that the row below spins on: the rows of an image form a diagonal wavefront without any
+// CTA-wide barrier and without any inter-CTA dependency (nothing to deadlock on, nothing to co-schedule).
+//
+// Nothing but coefficients/modes is read from HBM and nothing but final pixels is written:
+//   * the unfiltered bottom pixel row of every macroblock (what the row below predicts from) lives in a
+//     shared-memory line buffer (tu_*), the unfiltered right column stays in the warp's own tile;
+//   * the loop filter runs on a 20x20 (+2x 12x12) tile whose 4-pixel top/left aprons are the already filtered
+//     neighbours: the left apron is the warp's previous tile, the top apron comes from a second shared-memory
+//     line buffer (tf_*) holding the last four filtered rows of the macroblock row above;
+//   * a macroblock's pixels are stored to HBM only once they can no longer change: the block of rows -4..11 /
+//     columns -4..11 relative to the macroblock (the right 4 columns and bottom 4 rows wait for the neighbours'
+//     edge filters). The 4-pixel shift keeps every store 32-bit aligned.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vp8_dev.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ constants
+// (mode, pixel) -> first tap | 0x10 for 2-tap, over the edge vector
+//   E[0..2]=L3 E[3]=L2 E[4]=L1 E[5]=L0 E[6]=P E[7..14]=A0..A7 E[15]=A7
+// Rows 0 (B_DC) and 1 (B_TM) are placeholders; those two modes are computed arithmetically.
+// Equivalent to the ten unrolled cases of reference subblock_predict (vp8_recon.c:218-358).
+#define T3(i) (i)
+#define T2(i) (0x10 | (i))
+__constant__ uint8_t c_bpred_taps[10 * 16] = {
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    /* VE */ T3(6), T3(7), T3(8), T3(9), T3(6), T3(7), T3(8), T3(9), T3(6), T3(7), T3(8), T3(9), T3(6), T3(7), T3(8), T3(9),
+    /* HE */ T3(4), T3(4), T3(4), T3(4), T3(3), T3(3), T3(3), T3(3), T3(2), T3(2), T3(2), T3(2), T3(1), T3(1), T3(1), T3(1),
+    /* LD */ T3(7), T3(8), T3(9), T3(10), T3(8), T3(9), T3(10), T3(11), T3(9), T3(10), T3(11), T3(12), T3(10), T3(11), T3(12), T3(13),
+    /* RD */ T3(5), T3(6), T3(7), T3(8), T3(4), T3(5), T3(6), T3(7), T3(3), T3(4), T3(5), T3(6), T3(2), T3(3), T3(4), T3(5),
+    /* VR */ T2(6), T2(7), T2(8), T2(9), T3(5), T3(6), T3(7), T3(8), T3(4), T2(6), T2(7), T2(8), T3(3), T3(5), T3(6), T3(7),
+    /* VL */ T2(7), T2(8), T2(9), T2(10), T3(7), T3(8), T3(9), T3(10), T2(8), T2(9), T2(10), T3(11), T3(8), T3(9), T3(10), T3(12),
+    /* HD */ T2(5), T3(5), T3(6), T3(7), T2(4), T3(4), T2(5), T3(5), T2(3), T3(3), T2(4), T3(4), T2(2), T3(2), T2(3), T3(3),
+    /* HU */ T2(4), T3(3), T2(3), T3(2), T2(3), T3(2), T2(2), T3(1), T2(2), T3(1), T3(0), T3(0), T3(0), T3(0), T3(0), T3(0),
+};
+#undef T3
+#undef T2
+
+constexpr int kProgRing = 64;      // progress stamps, ring over macroblock rows (>= 2*NW)
+constexpr int kStampRow = 4096;    // stamp = (row+1)*kStampRow + macroblocks done in that row
+constexpr int kSmemFixed = 768;    // progress ring (256) + tap table (256) + image descriptor (256)
+
+// Per-warp shared-memory workspace.
+//   rt_*: reconstruction tile with a 1-pixel top/left border (what intra prediction reads).
+//         luma row r in [-1,15] at (r+1)*24, column c in [-1,19] at 4+c (columns 16..19 = above-right);
+//         chroma row r in [-1,7] at (r+1)*12, column c in [-1,7] at 4+c.
+//   ft_*: filter tile with 4-pixel top/left aprons. luma row r in [-4,15] at (r+4)*20, column c at 4+c;
+//         chroma row r in [-4,7] at (r+4)*12, column c at 4+c.
+struct __align__(16) WarpWs {
+	uint8_t rt_y[17 * 24];
+	uint8_t rt_u[9 * 12];
+	uint8_t rt_v[9 * 12];
+	uint8_t lcol[32];     // unfiltered left neighbours packed: y[16] u[8] v[8]
+	int16_t res[16][16];  // luma residuals of a B_PRED macroblock; res[0] doubles as the WHT output
+	uint8_t ft_y[20 * 20];
+	uint8_t ft_u[12 * 12];
+	uint8_t ft_v[12 * 12];
+	uint8_t pad_[64];
+};
+static_assert(sizeof(WarpWs) % 16 == 0, "WarpWs alignment");
+
+struct OutPlane {
+	uint8_t* p;
+	uint32_t stride, w, h;
+	bool word_ok;
+};
+
+// ------------------------------------------------------------------------------------------------ small helpers
+__device__ __forceinline__ int s16(int v) { return (int)(short)v; }
+__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int sclamp(int v) { return min(max(v, -128), 127); }
+__device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
+__device__ __forceinline__ void st32(uint8_t* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
+__device__ __forceinline__ uint32_t sum4(uint32_t w) { return __dp4a(w, 0x01010101u, 0u); }
+
+__device__ __forceinline__ uint4 ldg_stream(const int16_t* p) {
+	// coefficients are read exactly once: keep them out of L1
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+	             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+	             : "l"(p));
+	return r;
+}
+
+// Store 4 pixels at (ox, oy) of an output plane, honouring the crop.
+__device__ __forceinline__ void put_word(const OutPlane& o, int ox, int oy, uint32_t v) {
+	if ((uint32_t)oy >= o.h || (uint32_t)ox >= o.w) return;
+	uint8_t* d = o.p + (size_t)oy * o.stride + ox;
+	if (o.word_ok && (uint32_t)ox + 4 <= o.w) {
+		st32(d, v);
+	} else {
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			if ((uint32_t)ox + k < o.w) d[k] = (uint8_t)(v >> (8 * k));
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ transforms
+// RFC 6386 14.4 butterfly. Reference inv_dct4x4 (vp8_recon.c:107-148): vertical pass, int16 truncation, horizontal
+// pass with (x+4)>>3.
+__device__ __forceinline__ void idct_1d(int x0, int x1, int x2, int x3, int& o0, int& o1, int& o2, int& o3) {
+	int e = x0 + x2, g = x0 - x2;
+	int s1 = (x1 * 35468) >> 16, s3 = (x3 * 35468) >> 16;
+	int c1 = x1 + ((x1 * 20091) >> 16), c3 = x3 + ((x3 * 20091) >> 16);
+	int lo = s1 - c3, hi = c1 + s3;
+	o0 = e + hi;
+	o1 = g + lo;
+	o2 = g - lo;
+	o3 = e - hi;
+}
+
+__device__ __forceinline__ void idct4x4(const int (&v)[16], int (&r)[16]) {
+	int t[16];
+#pragma unroll
+	for (int c = 0; c < 4; c++) {
+		int o0, o1, o2, o3;
+		idct_1d(v[c], v[4 + c], v[8 + c], v[12 + c], o0, o1, o2, o3);
+		t[c] = s16(o0);
+		t[4 + c] = s16(o1);
+		t[8 + c] = s16(o2);
+		t[12 + c] = s16(o3);
+	}
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		int o0, o1, o2, o3;
+		idct_1d(t[4 * k], t[4 * k + 1], t[4 * k + 2], t[4 * k + 3], o0, o1, o2, o3);
+		r[4 * k] = s16((o0 + 4) >> 3);
+		r[4 * k + 1] = s16((o1 + 4) >> 3);
+		r[4 * k + 2] = s16((o2 + 4) >> 3);
+		r[4 * k + 3] = s16((o3 + 4) >> 3);
+	}
+}
+
+// Reference inv_wht4x4 (vp8_recon.c:80-105).
+__device__ __forceinline__ void iwht4x4(const int (&v)[16], int (&r)[16]) {
+	int t[16];
+#pragma unroll
+	for (int c = 0; c < 4; c++) {
+		int s03 = v[c] + v[12 + c], s12 = v[4 + c] + v[8 + c];
+		int d12 = v[4 + c] - v[8 + c], d03 = v[c] - v[12 + c];
+		t[c] = s16(s03 + s12);
+		t[4 + c] = s16(d12 + d03);
+		t[8 + c] = s16(s03 - s12);
+		t[12 + c] = s16(d03 - d12);
+	}
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		int s03 = t[4 * k] + t[4 * k + 3], s12 = t[4 * k + 1] + t[4 * k + 2];
+		int d12 = t[4 * k + 1] - t[4 * k + 2], d03 = t[4 * k] - t[4 * k + 3];
+		r[4 * k] = s16((s03 + s12 + 3) >> 3);
+		r[4 * k + 1] = s16((d12 + d03 + 3) >> 3);
+		r[4 * k + 2] = s16((s03 - s12 + 3) >> 3);
+		r[4 * k + 3] = s16((d03 - d12 + 3) >> 3);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ loop filter
+enum { EDGE_MB = 0, EDGE_INNER = 1, EDGE_SIMPLE = 2 };
+
+// One position across an edge, in registers. Returns true when pixels changed.
+// Thresholds: reference vp8_loopfilter.c:24-56; kernels :58-104; dispatch :106-164.
+template <int KIND>
+__device__ __forceinline__ bool lf_position(int p3, int& p2, int& p1, int& p0, int& q0, int& q1, int& q2, int q3, int lim,
+                                            int interior, int hev_thr) {
+	if (2 * abs(p0 - q0) + (abs(p1 - q1) >> 1) > lim) return false;
+	bool hev = false;
+	if (KIND != EDGE_SIMPLE) {
+		int m = max(max(abs(p3 - p2), abs(p2 - p1)), max(abs(p1 - p0), abs(q3 - q2)));
+		m = max(m, max(abs(q2 - q1), abs(q1 - q0)));
+		if (m > interior) return false;
+		hev = abs(p1 - p0) > hev_thr || abs(q1 - q0) > hev_thr;
+		if (KIND == EDGE_MB && !hev) {
+			int w = sclamp(sclamp(p1 - q1) + 3 * (q0 - p0));
+			int a = (27 * w + 63) >> 7, b = (18 * w + 63) >> 7, c = (9 * w + 63) >> 7;
+			p0 = clip255(p0 + a);
+			q0 = clip255(q0 - a);
+			p1 = clip255(p1 + b);
+			q1 = clip255(q1 - b);
+			p2 = clip255(p2 + c);
+			q2 = clip255(q2 - c);
+			return true;
+		}
+	}
+	const bool outer = (KIND != EDGE_INNER) || hev;
+	int a = 3 * (q0 - p0);
+	if (outer) a += sclamp(p1 - q1);
+	a = sclamp(a);
+	int f1 = sclamp(a + 4) >> 3, f2 = sclamp(a + 3) >> 3;
+	q0 = clip255(q0 - f1);
+	p0 = clip255(p0 + f2);
+	if (!outer) {
+		int h = (f1 + 1) >> 1;
+		q1 = clip255(q1 - h);
+		p1 = clip255(p1 + h);
+	}
+	return true;
+}
+
+// Filter across a vertical edge: q points at the word holding q0..q3 of this lane's pixel row (4-byte aligned).
+template <int KIND>
+__device__ __forceinline__ void lf_across_columns(uint8_t* q, int lim, int interior, int hev_thr) {
+	uint32_t wp = ld32(q - 4), wq = ld32(q);
+	int p3 = wp & 255, p2 = (wp >> 8) & 255, p1 = (wp >> 16) & 255, p0 = wp >> 24;
+	int q0 = wq & 255, q1 = (wq >> 8) & 255, q2 = (wq >> 16) & 255, q3 = wq >> 24;
+	if (lf_position<KIND>(p3, p2, p1, p0, q0, q1, q2, q3, lim, interior, hev_thr)) {
+		st32(q - 4, (uint32_t)p3 | (p2 << 8) | (p1 << 16) | ((uint32_t)p0 << 24));
+		st32(q, (uint32_t)q0 | (q1 << 8) | (q2 << 16) | ((uint32_t)q3 << 24));
+	}
+}
+
+// Filter across a horizontal edge: q points at q0 of this lane's pixel column, s = row stride.
+template <int KIND>
+__device__ __forceinline__ void lf_across_rows(uint8_t* q, int s, int lim, int interior, int hev_thr) {
+	int p3 = 0, q3 = 0;
+	int p2 = q[-3 * s], p1 = q[-2 * s], p0 = q[-s], q0 = q[0], q1 = q[s], q2 = q[2 * s];
+	if (KIND != EDGE_SIMPLE) {
+		p3 = q[-4 * s];
+		q3 = q[3 * s];
+	}
+	if (lf_position<KIND>(p3, p2, p1, p0, q0, q1, q2, q3, lim, interior, hev_thr)) {
+		q[-s] = (uint8_t)p0;
+		q[0] = (uint8_t)q0;
+		if (KIND != EDGE_SIMPLE) {
+			q[-3 * s] = (uint8_t)p2;
+			q[-2 * s] = (uint8_t)p1;
+			q[s] = (uint8_t)q1;
+			q[2 * s] = (uint8_t)q2;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int NW, bool RECON, bool FILTER>
+__global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px) {
+	extern __shared__ __align__(16) uint8_t smem[];
+	volatile int* prog = reinterpret_cast<volatile int*>(smem);
+	uint8_t* taps = smem + 256;
+	Vp8ImgDesc* sd = reinterpret_cast<Vp8ImgDesc*>(smem + 512);
+	// line buffers: unfiltered bottom rows (tu), last four filtered rows (tf)
+	uint8_t* tu_y = smem + kSmemFixed;
+	uint8_t* tu_u = tu_y + line_px;
+	uint8_t* tu_v = tu_u + line_px / 2;
+	uint8_t* tf_y = tu_v + line_px / 2;
+	uint8_t* tf_u = tf_y + 4 * line_px;
+	uint8_t* tf_v = tf_u + 2 * line_px;
+	const int line_c = line_px / 2;
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	WarpWs& ws = reinterpret_cast<WarpWs*>(smem + kSmemFixed + 10 * line_px)[warp];
+
+	static_assert(sizeof(Vp8ImgDesc) <= 256, "descriptor must fit its shared-memory slot");
+	static_assert(2 * NW <= kProgRing, "progress ring too small");
+
+	for (int i = tid; i < 160; i += NW * 32) taps[i] = c_bpred_taps[i];
+
+	// lane roles that never change
+	//   transform / block-per-lane prediction: lanes 0..15 luma block, 16..19 U block, 20..23 V block, 24 Y2
+	const bool is_luma_lane = lane < 16, is_chroma_lane = lane >= 16 && lane < 24;
+	const int cb = lane & 3;                                   // chroma block index within its plane
+	const int blk_bx = is_luma_lane ? (lane & 3) * 4 : (cb & 1) * 4;
+	const int blk_by = is_luma_lane ? (lane >> 2) * 4 : (cb >> 1) * 4;
+	//   B_PRED pixel-per-lane: two sub-blocks in flight, 16 lanes each
+	const int half = lane >> 4, px_i = lane & 15, px_r = px_i >> 2, px_c = px_i & 3;
+	const int e_dy = px_i <= 2 ? 3 : (px_i <= 5 ? 5 - px_i : -1);
+	const int e_dx = px_i <= 6 ? -1 : (px_i == 15 ? 7 : px_i - 7);
+	const int e_off = e_dy * 24 + e_dx;
+	const bool dc_tap = (px_i >= 2 && px_i <= 5) || (px_i >= 7 && px_i <= 10);
+
+	for (int img = blockIdx.x; img < n_images; img += gridDim.x) {
+		__syncthreads(); // previous image fully retired before its line buffers and descriptor are reused
+		{
+			const uint32_t* src = reinterpret_cast<const uint32_t*>(descs + img);
+			uint32_t* dst = reinterpret_cast<uint32_t*>(sd);
+			for (int i = tid; i < (int)(sizeof(Vp8ImgDesc) / 4); i += NW * 32) dst[i] = src[i];
+			if (tid < kProgRing) prog[tid] = 0;
+		}
+		__syncthreads();
+
+		const int cols = sd->mb_cols, rows = sd->mb_rows;
+		OutPlane oy{sd->out_y, sd->out_stride_y, sd->out_w, sd->out_h,
+		            ((reinterpret_cast<uintptr_t>(sd->out_y) | sd->out_stride_y) & 3) == 0};
+		const uint32_t ocw = (sd->out_w + 1) >> 1, och = (sd->out_h + 1) >> 1;
+		OutPlane ou{sd->out_u, sd->out_stride_uv, ocw, och,
+		            ((reinterpret_cast<uintptr_t>(sd->out_u) | sd->out_stride_uv) & 3) == 0};
+		OutPlane ov{sd->out_v, sd->out_stride_uv, ocw, och,
+		            ((reinterpret_cast<uintptr_t>(sd->out_v) | sd->out_stride_uv) & 3) == 0};
+		const bool lf_simple = sd->lf_simple != 0;
+
+		for (int y = warp; y < rows; y += NW) {
+			const bool last_row = (y == rows - 1);
+
+			// ---- row start: out-of-frame left neighbours (129) and corner (127 on the top row, else 129)
+			if (RECON) {
+				ws.lcol[lane] = 129;
+				if (lane < 16) ws.rt_y[(lane + 1) * 24 + 3] = 129;
+				else if (lane < 24) ws.rt_u[(lane - 16 + 1) * 12 + 3] = 129;
+				else ws.rt_v[(lane - 24 + 1) * 12 + 3] = 129;
+				const uint8_t corner = (y == 0) ? 127 : 129;
+				if (lane == 0) ws.rt_y[3] = corner;
+				if (lane == 1) ws.rt_u[3] = corner;
+				if (lane == 2) ws.rt_v[3] = corner;
+			}
+
+			// ---- software prefetch of the first macroblock's coefficients
+			uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+			const int16_t* cptr = nullptr;
+			size_t cstep = 0; // elements per macroblock for this lane's coefficient stream
+			if (RECON) {
+				const size_t mb0 = (size_t)y * cols;
+				if (is_luma_lane) { cptr = sd->coeff_y + (mb0 * 16 + lane) * 16; cstep = 256; }
+				else if (lane < 20) { cptr = sd->coeff_u + (mb0 * 4 + cb) * 16; cstep = 64; }
+				else if (lane < 24) { cptr = sd->coeff_v + (mb0 * 4 + cb) * 16; cstep = 64; }
+				else if (lane == 24) { cptr = sd->coeff_y2 + mb0 * 16; cstep = 16; }
+				if (cptr) {
+					c0 = ldg_stream(cptr);
+					c1 = ldg_stream(cptr + 8);
+				}
+			}
+
+			for (int x = 0; x < cols; x++) {
+				const size_t mb = (size_t)y * cols + x;
+				const bool last_col = (x == cols - 1);
+
+				// ---- per-macroblock syntax
+				const int ymode = sd->ymode[mb];
+				const bool bpred = (ymode == 4);
+				const int seg = sd->segment_id ? (sd->segment_id[mb] & 3) : 0;
+				int uvmode = 0, bmode = 0;
+				if (RECON) {
+					uvmode = sd->uv_mode[mb];
+					if (bpred && lane < 16) bmode = sd->bmode[mb * 16 + lane];
+				}
+
+				// ---- issue the next macroblock's coefficient loads before doing anything that can stall
+				uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+				if (RECON && cptr && !last_col) {
+					n0 = ldg_stream(cptr + (size_t)(x + 1) * cstep);
+					n1 = ldg_stream(cptr + (size_t)(x + 1) * cstep + 8);
+				}
+
+				// ---- wait for MB(x+1, y-1) (or the end of the row above)
+				if (y > 0) {
+					if (lane == 0) {
+						const int target = y * kStampRow + min(x + 2, cols);
+						while (prog[(y - 1) & (kProgRing - 1)] < target) __nanosleep(40);
+						__threadfence_block();
+					}
+					__syncwarp();
+				}
+
+				if (RECON) {
+					// ================================================================== m06: reconstruction
+					// ---- top border (row -1) from the unfiltered line buffer, 127 above the frame
+					if (lane < 9) {
+						uint32_t w = 0x7f7f7f7fu;
+						if (y > 0) {
+							if (lane < 5) {
+								if (lane == 4 && last_col) w = 0x01010101u * tu_y[16 * x + 15];
+								else w = ld32(tu_y + 16 * x + 4 * lane);
+							} else if (lane < 7) {
+								w = ld32(tu_u + 8 * x + 4 * (lane - 5));
+							} else {
+								w = ld32(tu_v + 8 * x + 4 * (lane - 7));
+							}
+						}
+						if (lane < 5) {
+							st32(ws.rt_y + 4 + 4 * lane, w);
+							if (lane == 4) { // above-right of sub-block column 3 always comes from the MB row above
+								st32(ws.rt_y + 4 * 24 + 20, w);
+								st32(ws.rt_y + 8 * 24 + 20, w);
+								st32(ws.rt_y + 12 * 24 + 20, w);
+							}
+						} else if (lane < 7) {
+							st32(ws.rt_u + 4 + 4 * (lane - 5), w);
+						} else {
+							st32(ws.rt_v + 4 + 4 * (lane - 7), w);
+						}
+					}
+
+					// ---- dequantise + inverse transforms, one 4x4 block per lane (lanes 0..24)
+					int r[16];
+					bool any = false;
+					{
+						int v[16];
+						const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+						const int16_t* dq = sd->dq[seg];
+						const int dcq = is_luma_lane ? dq[0] : (lane < 24 ? dq[2] : dq[4]);
+						const int acq = is_luma_lane ? dq[1] : (lane < 24 ? dq[3] : dq[5]);
+#pragma unroll
+						for (int i = 0; i < 8; i++) {
+							v[2 * i] = s16(s16(cw[i]) * (i == 0 ? dcq : acq));
+							v[2 * i + 1] = s16(((int)cw[i] >> 16) * acq);
+						}
+						if (!bpred) {
+							// Y2: lane 24 runs the WHT, luma lanes take their DC from it (vp8_recon.c:563-586)
+							if (lane == 24) {
+								int d[16];
+								iwht4x4(v, d);
+#pragma unroll
+								for (int i = 0; i < 16; i++) ws.res[0][i] = (int16_t)d[i];
+							}
+							__syncwarp();
+							if (is_luma_lane) v[0] = ws.res[0][lane];
+						}
+						uint32_t ac_or = 0;
+#pragma unroll
+						for (int i = 1; i < 16; i++) ac_or |= (uint32_t)v[i];
+						any = (lane < 24) && ((ac_or | (uint32_t)v[0]) != 0);
+						if (any) {
+							if (ac_or == 0) {
+								const int dc = s16((v[0] + 4) >> 3); // DC-only block: flat residual
+#pragma unroll
+								for (int i = 0; i < 16; i++) r[i] = dc;
+							} else {
+								idct4x4(v, r);
+							}
+						} else {
+#pragma unroll
+							for (int i = 0; i < 16; i++) r[i] = 0;
+						}
+					}
+					__syncwarp(); // borders visible; res[0] consumed
+
+					// ---- block-per-lane prediction: i16 luma (lanes 0..15) and chroma (lanes 16..23)
+					if (bpred && is_luma_lane) {
+						// park the residuals for the pixel-per-lane pass
+						uint32_t pk[8];
+#pragma unroll
+						for (int i = 0; i < 8; i++) pk[i] = (uint32_t)(r[2 * i] & 0xffff) | ((uint32_t)r[2 * i + 1] << 16);
+						uint4* dst = reinterpret_cast<uint4*>(ws.res[lane]);
+						dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+						dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+					} else if (lane < 24) {
+						uint8_t* tile;
+						const uint8_t* lc;
+						int stride, nwords, mode;
+						if (is_luma_lane) { tile = ws.rt_y; lc = ws.lcol; stride = 24; nwords = 4; mode = ymode; }
+						else if (lane < 20) { tile = ws.rt_u; lc = ws.lcol + 16; stride = 12; nwords = 2; mode = uvmode; }
+						else { tile = ws.rt_v; lc = ws.lcol + 24; stride = 12; nwords = 2; mode = uvmode; }
+						uint32_t pw[4];
+						if (mode == 1) { // V: above row
+							const uint32_t a = ld32(tile + 4 + blk_bx);
+							pw[0] = pw[1] = pw[2] = pw[3] = a;
+						} else if (mode == 2) { // H: left column
+							const uint32_t l = ld32(lc + blk_by);
+#pragma unroll
+							for (int k = 0; k < 4; k++) pw[k] = ((l >> (8 * k)) & 255u) * 0x01010101u;
+						} else if (mode == 3) { // TM: clip(L + A - P)
+							const uint32_t a = ld32(tile + 4 + blk_bx), l = ld32(lc + blk_by);
+							const int p = tile[3];
+#pragma unroll
+							for (int k = 0; k < 4; k++) {
+								const int base = (int)((l >> (8 * k)) & 255u) - p;
+								uint32_t w = 0;
+#pragma unroll
+								for (int j = 0; j < 4; j++) w |= (uint32_t)clip255(base + (int)((a >> (8 * j)) & 255u)) << (8 * j);
+								pw[k] = w;
+							}
+						} else { // DC (also any out-of-range mode): vp8_recon.c:152-176
+							uint32_t sum = 0;
+							const bool have_a = y > 0, have_l = x > 0;
+							for (int k = 0; k < nwords; k++) {
+								if (have_a) sum += sum4(ld32(tile + 4 + 4 * k));
+								if (have_l) sum += sum4(ld32(lc + 4 * k));
+							}
+							const int lg = (nwords == 4) ? 4 : 3; // log2(n)
+							uint32_t dcv;
+							if (have_a && have_l) dcv = (sum + (1u << lg)) >> (lg + 1);
+							else if (have_a || have_l) dcv = (sum + (1u << (lg - 1))) >> lg;
+							else dcv = 128;
+							pw[0] = pw[1] = pw[2] = pw[3] = dcv * 0x01010101u;
+						}
+						uint8_t* dst = tile + (blk_by + 1) * stride + 4 + blk_bx;
+#pragma unroll
+						for (int k = 0; k < 4; k++) {
+							uint32_t w = pw[k];
+							if (any) {
+								uint32_t o = 0;
+#pragma unroll
+								for (int j = 0; j < 4; j++) o |= (uint32_t)clip255((int)((w >> (8 * j)) & 255u) + r[4 * k + j]) << (8 * j);
+								w = o;
+							}
+							st32(dst + k * stride, w);
+						}
+					}
+					__syncwarp();
+
+					// ---- B_PRED luma: sub-block wavefront, step s handles sub-blocks with col + 2*row == s
+					if (bpred) {
+#pragma unroll 1
+						for (int s = 0; s < 10; s++) {
+							const int rb = (s >> 1) - half, cbk = (s & 1) + 2 * half;
+							const bool active = rb >= 0 && rb <= 3;
+							const int blk = (rb * 4 + cbk) & 15;
+							const int mode = __shfl_sync(0xffffffffu, bmode, blk);
+							uint8_t* base = ws.rt_y + (rb * 4 + 1) * 24 + 4 + cbk * 4;
+							int e = 0, tap = 0, rs = 0;
+							if (active) {
+								e = base[e_off];
+								tap = taps[min(mode, 9) * 16 + px_i];
+								rs = ws.res[blk][px_i];
+							}
+							const int ti = tap & 15;
+							const bool tm = (mode == 1);
+							const int i0 = tm ? 5 - px_r : ti, i1 = tm ? 7 + px_c : ti + 1, i2 = tm ? 6 : ((ti + 2) & 15);
+							const int a = __shfl_sync(0xffffffffu, e, (lane & 16) | i0);
+							const int b = __shfl_sync(0xffffffffu, e, (lane & 16) | i1);
+							const int c = __shfl_sync(0xffffffffu, e, (lane & 16) | i2);
+							int v = (tap & 16) ? (a + b + 1) >> 1 : (a + 2 * b + c + 2) >> 2;
+							if (tm) v = clip255(a + b - c);
+							if (__any_sync(0xffffffffu, active && mode == 0)) {
+								int sum = dc_tap ? e : 0;
+								sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+								sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+								sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+								sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+								if (mode == 0) v = (sum + 4) >> 3;
+							}
+							if (mode > 9) v = 128;
+							if (active) base[px_r * 24 + px_c] = (uint8_t)clip255(v + rs);
+							__syncwarp();
+						}
+					}
+				} else {
+					// ================================================================== stand-alone m07: load the MB
+					const uint8_t* sy = sd->src_y + (size_t)(16 * y) * sd->src_stride_y + 16 * x;
+#pragma unroll
+					for (int k = 0; k < 2; k++) {
+						const int i = lane + 32 * k, row = i >> 2, wc = i & 3;
+						st32(ws.rt_y + (row + 1) * 24 + 4 + 4 * wc, ld32(sy + (size_t)row * sd->src_stride_y + 4 * wc));
+					}
+					{
+						const int j = lane & 15, row = j >> 1, wc = j & 1;
+						const uint8_t* sp = (lane < 16 ? sd->src_u : sd->src_v) + (size_t)(8 * y + row) * sd->src_stride_uv + 8 * x + 4 * wc;
+						st32((lane < 16 ? ws.rt_u : ws.rt_v) + (row + 1) * 12 + 4 + 4 * wc, ld32(sp));
+					}
+					__syncwarp();
+				}
+
+				// ---- snapshot of the unfiltered tile that the neighbours will need (read phase)
+				uint32_t edge_b = 0, bot_w = 0, corner_b = 0;
+				if (RECON) {
+					if (lane < 16) edge_b = ws.rt_y[(lane + 1) * 24 + 4 + 15];
+					else if (lane < 24) edge_b = ws.rt_u[(lane - 16 + 1) * 12 + 4 + 7];
+					else edge_b = ws.rt_v[(lane - 24 + 1) * 12 + 4 + 7];
+					if (lane < 4) bot_w = ld32(ws.rt_y + 16 * 24 + 4 + 4 * lane);
+					else if (lane < 6) bot_w = ld32(ws.rt_u + 8 * 12 + 4 + 4 * (lane - 4));
+					else if (lane < 8) bot_w = ld32(ws.rt_v + 8 * 12 + 4 + 4 * (lane - 6));
+					if (lane == 8) corner_b = ws.rt_y[4 + 15];
+					if (lane == 9) corner_b = ws.rt_u[4 + 7];
+					if (lane == 10) corner_b = ws.rt_v[4 + 7];
+				}
+
+				if (!FILTER) {
+					// ================================================================== unfiltered output (-yuv)
+#pragma unroll
+					for (int k = 0; k < 2; k++) {
+						const int i = lane + 32 * k, row = i >> 2, wc = i & 3;
+						put_word(oy, 16 * x + 4 * wc, 16 * y + row, ld32(ws.rt_y + (row + 1) * 24 + 4 + 4 * wc));
+					}
+					{
+						const int j = lane & 15, row = j >> 1, wc = j & 1;
+						put_word(lane < 16 ? ou : ov, 8 * x + 4 * wc, 8 * y + row,
+						         ld32((lane < 16 ? ws.rt_u : ws.rt_v) + (row + 1) * 12 + 4 + 4 * wc));
+					}
+				} else {
+					// ================================================================== m07: loop filter
+					// ---- assemble the filter tile: left apron = previous tile's right 4 columns, top apron = tf lines
+					uint32_t la = 0, ta = 0, in0, in1, inc;
+					if (lane < 16) la = ld32(ws.ft_y + (lane + 4) * 20 + 16);
+					else if (lane < 24) la = ld32(ws.ft_u + (lane - 16 + 4) * 12 + 8);
+					else la = ld32(ws.ft_v + (lane - 24 + 4) * 12 + 8);
+					if (y > 0) {
+						if (lane < 16) ta = ld32(tf_y + (lane >> 2) * line_px + 16 * x + 4 * (lane & 3));
+						else {
+							const int j = lane & 7; // 4 rows x 2 words
+							ta = ld32((lane < 24 ? tf_u : tf_v) + (j >> 1) * line_c + 8 * x + 4 * (j & 1));
+						}
+					}
+					in0 = ld32(ws.rt_y + ((lane >> 2) + 1) * 24 + 4 + 4 * (lane & 3));
+					in1 = ld32(ws.rt_y + ((lane >> 2) + 9) * 24 + 4 + 4 * (lane & 3));
+					{
+						const int j = lane & 15;
+						inc = ld32((lane < 16 ? ws.rt_u : ws.rt_v) + ((j >> 1) + 1) * 12 + 4 + 4 * (j & 1));
+					}
+					__syncwarp();
+					if (lane < 16) st32(ws.ft_y + (lane + 4) * 20, la);
+					else if (lane < 24) st32(ws.ft_u + (lane - 16 + 4) * 12, la);
+					else st32(ws.ft_v + (lane - 24 + 4) * 12, la);
+					if (lane < 16) st32(ws.ft_y + (lane >> 2) * 20 + 4 + 4 * (lane & 3), ta);
+					else {
+						const int j = lane & 7;
+						st32((lane < 24 ? ws.ft_u : ws.ft_v) + (j >> 1) * 12 + 4 + 4 * (j & 1), ta);
+					}
+					st32(ws.ft_y + ((lane >> 2) + 4) * 20 + 4 + 4 * (lane & 3), in0);
+					st32(ws.ft_y + ((lane >> 2) + 12) * 20 + 4 + 4 * (lane & 3), in1);
+					{
+						const int j = lane & 15;
+						st32((lane < 16 ? ws.ft_u : ws.ft_v) + ((j >> 1) + 4) * 12 + 4 + 4 * (j & 1), inc);
+					}
+					__syncwarp();
+
+					// ---- edge filters in the reference's order (vp8_loopfilter.c:226-277)
+					const uint8_t* lfp = sd->lf[seg][bpred ? 1 : 0];
+					const int level = lfp[0], interior = lfp[1], hev_thr = lfp[2];
+					if (level > 0) {
+						const bool inner = bpred || (sd->has_coeff && sd->has_coeff[mb]);
+						const int lim_mb = 2 * (level + 2) + interior, lim_in = 2 * level + interior;
+						// this lane's line (row for column edges, column for row edges) in luma or chroma
+						uint8_t* t;
+						int stride, n;
+						if (lane < 16) { t = ws.ft_y + 4 * 20 + 4; stride = 20; n = lane; }
+						else if (lane < 24) { t = ws.ft_u + 4 * 12 + 4; stride = 12; n = lane - 16; }
+						else { t = ws.ft_v + 4 * 12 + 4; stride = 12; n = lane - 24; }
+						if (!lf_simple) {
+							if (x > 0) lf_across_columns<EDGE_MB>(t + n * stride, lim_mb, interior, hev_thr);
+							__syncwarp();
+							if (inner) {
+								lf_across_columns<EDGE_INNER>(t + n * stride + 4, lim_in, interior, hev_thr);
+								__syncwarp();
+								if (lane < 16) lf_across_columns<EDGE_INNER>(t + n * stride + 8, lim_in, interior, hev_thr);
+								__syncwarp();
+								if (lane < 16) lf_across_columns<EDGE_INNER>(t + n * stride + 12, lim_in, interior, hev_thr);
+								__syncwarp();
+							}
+							if (y > 0) lf_across_rows<EDGE_MB>(t + n, stride, lim_mb, interior, hev_thr);
+							__syncwarp();
+							if (inner) {
+								lf_across_rows<EDGE_INNER>(t + 4 * stride + n, stride, lim_in, interior, hev_thr);
+								__syncwarp();
+								if (lane < 16) lf_across_rows<EDGE_INNER>(t + 8 * stride + n, stride, lim_in, interior, hev_thr);
+								__syncwarp();
+								if (lane < 16) lf_across_rows<EDGE_INNER>(t + 12 * stride + n, stride, lim_in, interior, hev_thr);
+								__syncwarp();
+							}
+						} else if (lane < 16) {
+							// simple filter: luma only (vp8_loopfilter.c:228-244)
+							if (x > 0) lf_across_columns<EDGE_SIMPLE>(t + n * stride, lim_mb, 0, 0);
+							__syncwarp(0xffffu);
+							if (inner) {
+								for (int e = 4; e < 16; e += 4) {
+									lf_across_columns<EDGE_SIMPLE>(t + n * stride + e, lim_in, 0, 0);
+									__syncwarp(0xffffu);
+								}
+							}
+							if (y > 0) lf_across_rows<EDGE_SIMPLE>(t + n, stride, lim_mb, 0, 0);
+							__syncwarp(0xffffu);
+							if (inner) {
+								for (int e = 4; e < 16; e += 4) {
+									lf_across_rows<EDGE_SIMPLE>(t + e * stride + n, stride, lim_in, 0, 0);
+									__syncwarp(0xffffu);
+								}
+							}
+						}
+						__syncwarp();
+					}
+
+					// ---- store what can no longer change
+					const int wc_lo = (x > 0) ? -1 : 0;
+					{ // luma body: rows 0..11 (0..15 on the last MB row), word columns wc_lo..2 (..3 on the last MB column)
+						const int wc_hi = last_col ? 4 : 3, r_hi = last_row ? 16 : 12;
+						for (int i = lane; i < 16 * 5; i += 32) {
+							const int row = i / 5, wc = i % 5 - 1;
+							if (row < r_hi && wc >= wc_lo && wc < wc_hi)
+								put_word(oy, 16 * x + 4 * wc, 16 * y + row, ld32(ws.ft_y + (row + 4) * 20 + 4 + 4 * wc));
+						}
+					}
+					{ // chroma body: rows 0..3 (0..7), word columns wc_lo..0 (..1)
+						const int wc_hi = last_col ? 2 : 1, r_hi = last_row ? 8 : 4;
+						for (int i = lane; i < 2 * 8 * 3; i += 32) {
+							const int pl = i / 24, j = i % 24, row = j / 3, wc = j % 3 - 1;
+							if (row < r_hi && wc >= wc_lo && wc < wc_hi)
+								put_word(pl ? ov : ou, 8 * x + 4 * wc, 8 * y + row,
+								         ld32((pl ? ws.ft_v : ws.ft_u) + (row + 4) * 12 + 4 + 4 * wc));
+						}
+					}
+					if (y > 0) { // bottom 4 rows of the macroblock above are final now
+						if (lane < 16)
+							put_word(oy, 16 * x + 4 * (lane & 3), 16 * y - 4 + (lane >> 2), ld32(ws.ft_y + (lane >> 2) * 20 + 4 + 4 * (lane & 3)));
+						else {
+							const int j = lane & 7;
+							put_word(lane < 24 ? ou : ov, 8 * x + 4 * (j & 1), 8 * y - 4 + (j >> 1),
+							         ld32((lane < 24 ? ws.ft_u : ws.ft_v) + (j >> 1) * 12 + 4 + 4 * (j & 1)));
+						}
+					}
+					if (!last_row) { // hand the bottom 4 filtered rows to the row below
+						const int wc_hi = last_col ? 4 : 3;
+						if (lane < 20) {
+							const int row = lane / 5, wc = lane % 5 - 1;
+							if (wc >= wc_lo && wc < wc_hi)
+								st32(tf_y + row * line_px + 16 * x + 4 * wc, ld32(ws.ft_y + (row + 16) * 20 + 4 + 4 * wc));
+						}
+						const int cwc_hi = last_col ? 2 : 1;
+						if (lane < 24) {
+							const int pl = lane / 12, j = lane % 12, row = j / 3, wc = j % 3 - 1;
+							if (wc >= wc_lo && wc < cwc_hi)
+								st32((pl ? tf_v : tf_u) + row * line_c + 8 * x + 4 * wc,
+								     ld32((pl ? ws.ft_v : ws.ft_u) + (row + 8) * 12 + 4 + 4 * wc));
+						}
+					}
+				}
+
+				// ---- hand the unfiltered borders on (write phase) and publish progress
+				if (RECON) {
+					__syncwarp();
+					ws.lcol[lane] = (uint8_t)edge_b;
+					if (lane < 16) ws.rt_y[(lane + 1) * 24 + 3] = (uint8_t)edge_b;
+					else if (lane < 24) ws.rt_u[(lane - 16 + 1) * 12 + 3] = (uint8_t)edge_b;
+					else ws.rt_v[(lane - 24 + 1) * 12 + 3] = (uint8_t)edge_b;
+					if (lane == 8) ws.rt_y[3] = (uint8_t)corner_b;
+					if (lane == 9) ws.rt_u[3] = (uint8_t)corner_b;
+					if (lane == 10) ws.rt_v[3] = (uint8_t)corner_b;
+					if (!last_row) {
+						if (lane < 4) st32(tu_y + 16 * x + 4 * lane, bot_w);
+						else if (lane < 6) st32(tu_u + 8 * x + 4 * (lane - 4), bot_w);
+						else if (lane < 8) st32(tu_v + 8 * x + 4 * (lane - 6), bot_w);
+					}
+				}
+				__syncwarp();
+				if (lane == 0) {
+					__threadfence_block();
+					prog[y & (kProgRing - 1)] = (y + 1) * kStampRow + x + 1;
+				}
+				c0 = n0;
+				c1 = n1;
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ m08: YUV -> RGB
+// Reference mult_hi / vp8_clip8 / vp8_yuv_to_rgb (yuv2rgb_ppm.c:19-41).
+__device__ __forceinline__ uint32_t fix_clip(int v) { return (v & ~16383) == 0 ? (uint32_t)(v >> 6) : (v < 0 ? 0u : 255u); }
+
+__device__ __forceinline__ void yuv_to_rgb(int Y, int U, int V, uint32_t& R, uint32_t& G, uint32_t& B) {
+	const int yy = (Y * 19077) >> 8;
+	R = fix_clip(yy + ((V * 26149) >> 8) - 14234);
+	G = fix_clip(yy - ((U * 6419) >> 8) - ((V * 13320) >> 8) + 8708);
+	B = fix_clip(yy + ((U * 33050) >> 8) - 17685);
+}
+
+// Interior sample of the fancy upsampler: near/far rows N,F; near/far columns nc,fc.
+__device__ __forceinline__ int fancy(int Nn, int Nf, int Fn, int Ff) {
+	const int sum = Nn + Nf + Fn + Ff + 8;
+	const int diag = (sum + 2 * (Nf + Fn)) >> 3;
+	return (diag + Nn) >> 1;
+}
+
+constexpr int kRgbThreads = 256;
+constexpr int kRgbPxPerThread = 4;
+
+// One thread = 4 horizontally adjacent pixels of one image. grid = (blocks per image, images).
+__global__ void __launch_bounds__(kRgbThreads) vp8_i420_to_rgb(const Vp8RgbDesc* __restrict__ descs) {
+	const Vp8RgbDesc d = descs[blockIdx.y];
+	const uint32_t w = d.width, h = d.height, cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+	const uint32_t groups_per_row = (w + kRgbPxPerThread - 1) / kRgbPxPerThread;
+	const uint32_t g = blockIdx.x * kRgbThreads + threadIdx.x;
+	if (g >= groups_per_row * h) return;
+	const uint32_t py = g / groups_per_row, px0 = (g % groups_per_row) * kRgbPxPerThread;
+
+	// near / far chroma rows (reference yuv420_write_ppm_fd row pairing, yuv2rgb_ppm.c:164-201)
+	const uint32_t nrow = py >> 1;
+	uint32_t frow;
+	if (py == 0) frow = 0;
+	else if (py & 1) frow = min(nrow + 1, ch - 1);
+	else frow = nrow - 1;
+	const uint8_t* un = d.u + (size_t)nrow * d.stride_uv;
+	const uint8_t* uf = d.u + (size_t)frow * d.stride_uv;
+	const uint8_t* vn = d.v + (size_t)nrow * d.stride_uv;
+	const uint8_t* vf = d.v + (size_t)frow * d.stride_uv;
+	const uint8_t* yrow = d.y + (size_t)py * d.stride_y;
+
+	// chroma columns j-1 .. j+2 with j = px0/2 cover all four pixels; clamp indices (clamped taps are unused)
+	const int j = (int)(px0 >> 1);
+	int un4[4], uf4[4], vn4[4], vf4[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int c = min(max(j - 1 + k, 0), (int)cw - 1);
+		un4[k] = un[c];
+		uf4[k] = uf[c];
+		vn4[k] = vn[c];
+		vf4[k] = vf[c];
+	}
+	uint8_t out[12];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const uint32_t px = px0 + k;
+		if (px >= w) break;
+		int U, V;
+		if (px == 0) {
+			U = (3 * un[0] + uf[0] + 2) >> 2;
+			V = (3 * vn[0] + vf[0] + 2) >> 2;
+		} else if (px == w - 1 && (w & 1) == 0) {
+			U = (3 * un[cw - 1] + uf[cw - 1] + 2) >> 2;
+			V = (3 * vn[cw - 1] + vf[cw - 1] + 2) >> 2;
+		} else {
+			// k=0: near j, far j-1; k=1: near j, far j+1; k=2: near j+1, far j; k=3: near j+1, far j+2  (array index = col-j+1)
+			const int ni = (k < 2) ? 1 : 2, fi = (k == 0) ? 0 : (k == 1 ? 2 : (k == 2 ? 1 : 3));
+			U = fancy(un4[ni], un4[fi], uf4[ni], uf4[fi]);
+			V = fancy(vn4[ni], vn4[fi], vf4[ni], vf4[fi]);
+		}
+		uint32_t R, G, B;
+		yuv_to_rgb(yrow[px], U, V, R, G, B);
+		out[3 * k] = (uint8_t)R;
+		out[3 * k + 1] = (uint8_t)G;
+		out[3 * k + 2] = (uint8_t)B;
+	}
+	uint8_t* dst = d.rgb + ((size_t)py * w + px0) * 3;
+	if (px0 + 4 <= w && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+		uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+		d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+		d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
+		d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
+	} else {
+		for (uint32_t k = 0; k < 12 && px0 * 3 + k < w * 3; k++) dst[k] = out[k];
+	}
+}
+
+template <int NW, bool RECON, bool FILTER>
+int launch_t(const Vp8ImgDesc* descs, int n, int line_px, int grid, size_t smem, cudaStream_t st) {
+	auto k = vp8_mb_wavefront<NW, RECON, FILTER>;
+	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return (int)e;
+	k<<<grid, NW * 32, smem, st>>>(descs, n, line_px);
+	return (int)cudaGetLastError();
+}
+
+template <int NW, bool RECON, bool FILTER>
+int occupancy_t(size_t smem) {
+	auto k = vp8_mb_wavefront<NW, RECON, FILTER>;
+	if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+	int nb = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, NW * 32, smem) != cudaSuccess) return 0;
+	return nb;
+}
+
+} // namespace
+
+int vp8_wavefront_smem_bytes(int mode, int warps_per_image, int max_mb_cols) {
+	(void)mode;
+	return kSmemFixed + 10 * 16 * max_mb_cols + warps_per_image * (int)sizeof(WarpWs);
+}
+
+#define VP8_DISPATCH(FN, ...)                                                            \
+	switch (mode * 100 + warps_per_image) {                                              \
+		case 4: return FN<4, true, false>(__VA_ARGS__);                                   \
+		case 8: return FN<8, true, false>(__VA_ARGS__);                                   \
+		case 16: return FN<16, true, false>(__VA_ARGS__);                                 \
+		case 32: return FN<32, true, false>(__VA_ARGS__);                                 \
+		case 104: return FN<4, true, true>(__VA_ARGS__);                                  \
+		case 108: return FN<8, true, true>(__VA_ARGS__);                                  \
+		case 116: return FN<16, true, true>(__VA_ARGS__);                                 \
+		case 132: return FN<32, true, true>(__VA_ARGS__);                                 \
+		case 204: return FN<4, false, true>(__VA_ARGS__);                                 \
+		case 208: return FN<8, false, true>(__VA_ARGS__);                                 \
+		case 216: return FN<16, false, true>(__VA_ARGS__);                                \
+		case 232: return FN<32, false, true>(__VA_ARGS__);                                \
+		default: return -1;                                                               \
+	}
+
+int vp8_launch_wavefront(int mode, int warps_per_image, const Vp8ImgDesc* descs_dev, int n_images, int max_mb_cols,
+                         int grid_ctas, void* stream) {
+	const size_t smem = (size_t)vp8_wavefront_smem_bytes(mode, warps_per_image, max_mb_cols);
+	const int line_px = 16 * max_mb_cols;
+	cudaStream_t st = (cudaStream_t)stream;
+	VP8_DISPATCH(launch_t, descs_dev, n_images, line_px, grid_ctas, smem, st)
+}
+
+int vp8_wavefront_max_ctas_per_sm(int mode, int warps_per_image, int max_mb_cols) {
+	const size_t smem = (size_t)vp8_wavefront_smem_bytes(mode, warps_per_image, max_mb_cols);
+	VP8_DISPATCH(occupancy_t, smem)
+}
+
+int vp8_launch_rgb(const Vp8RgbDesc* descs_dev, int n_images, uint32_t max_blocks_per_image, void* stream) {
+	if (n_images <= 0) return 0;
+	dim3 grid(max_blocks_per_image, (unsigned)n_images);
+	vp8_i420_to_rgb<<<grid, kRgbThreads, 0, (cudaStream_t)stream>>>(descs_dev);
+	return (int)cudaGetLastError();
+}
