@@ -109,6 +109,9 @@ uint64_t vp8_gpu_launch_count(const vp8_gpu_ctx* ctx); /* kernels launched by th
 uint64_t vp8_gpu_h2d_bytes(const vp8_gpu_ctx* ctx);
 uint64_t vp8_gpu_d2h_bytes(const vp8_gpu_ctx* ctx);
 int vp8_gpu_last_launch_config(const vp8_gpu_ctx* ctx, int* warps_per_image, int* grid, int* smem_bytes);
+/* Sum of the device-side durations (CUDA events on the context's stream) of the wavefront launches issued since
+ * the previous call, and how many there were. Waits for them to finish. */
+int vp8_gpu_kernel_time(vp8_gpu_ctx* ctx, double* total_ms, int* launches);
 
 /* Host-side per-frame parameter derivation, exported so tests can pin it against the oracle:
  * dq[4][6] = {y1dc,y1ac,uvdc,uvac,y2dc,y2ac} per segment (vp8_recon.c:57-76);

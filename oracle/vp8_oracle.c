@@ -280,18 +280,18 @@ typedef struct {
 	int level, interior, hev_thr;
 } MbFilter;
 
-/* Reference calc_params_keyframe (vp8_loopfilter.c:166-199). */
-static MbFilter mb_filter_params(const Vp8DecodedFrame* f, size_t mb) {
+/* Reference calc_params_keyframe (vp8_loopfilter.c:166-199), as a function of (segment, ymode==B_PRED). */
+static MbFilter seg_filter_params(const Vp8DecodedFrame* f, int seg, int is_bpred) {
 	MbFilter m;
 	int lvl = f->lf_level;
 	if (f->segmentation_enabled) {
-		int adj = f->seg_lf_level[f->segment_id[mb] & 3];
+		int adj = f->seg_lf_level[seg & 3];
 		lvl = f->segmentation_abs ? adj : lvl + adj;
 	}
 	lvl = lvl < 0 ? 0 : (lvl > 63 ? 63 : lvl);
 	if (f->lf_delta_enabled) {
 		lvl += f->lf_ref_delta[0];
-		if (f->ymode[mb] == 4) lvl += f->lf_mode_delta[0];
+		if (is_bpred) lvl += f->lf_mode_delta[0];
 		lvl = lvl < 0 ? 0 : (lvl > 63 ? 63 : lvl);
 	}
 	int in = lvl;
@@ -304,6 +304,31 @@ static MbFilter mb_filter_params(const Vp8DecodedFrame* f, size_t mb) {
 	m.interior = in;
 	m.hev_thr = (lvl >= 15) + (lvl >= 40);
 	return m;
+}
+
+static MbFilter mb_filter_params(const Vp8DecodedFrame* f, size_t mb) {
+	return seg_filter_params(f, f->segmentation_enabled ? (f->segment_id[mb] & 3) : 0, f->ymode[mb] == 4);
+}
+
+/* The per-frame tables the GPU library derives on the host, restated from the two functions above. */
+void orc_frame_params(const Vp8DecodedFrame* f, int16_t dq[4][6], uint8_t lf[4][2][4]) {
+	for (int s = 0; s < 4; s++) {
+		SegQuant q;
+		seg_quant(f, s, &q);
+		dq[s][0] = (int16_t)q.y1dc;
+		dq[s][1] = (int16_t)q.y1ac;
+		dq[s][2] = (int16_t)q.uvdc;
+		dq[s][3] = (int16_t)q.uvac;
+		dq[s][4] = (int16_t)q.y2dc;
+		dq[s][5] = (int16_t)q.y2ac;
+		for (int b = 0; b < 2; b++) {
+			MbFilter m = seg_filter_params(f, s, b);
+			lf[s][b][0] = (uint8_t)m.level;
+			lf[s][b][1] = (uint8_t)m.interior;
+			lf[s][b][2] = (uint8_t)m.hev_thr;
+			lf[s][b][3] = 0;
+		}
+	}
 }
 
 enum { EDGE_MB = 0, EDGE_INNER = 1, EDGE_SIMPLE = 2 };

@@ -23,6 +23,9 @@ extern "C" {
 int orc_recon_padded(const Vp8DecodedFrame* f, uint8_t* y, uint8_t* u, uint8_t* v);
 int orc_loopfilter_padded(const Vp8DecodedFrame* f, uint8_t* y, uint8_t* u, uint8_t* v);
 
+/* {y1dc,y1ac,uvdc,uvac,y2dc,y2ac} per segment and {level,interior,hev,0} per segment x (ymode==B_PRED). */
+void orc_frame_params(const Vp8DecodedFrame* f, int16_t dq[4][6], uint8_t lf[4][2][4]);
+
 /* Full path to a tight I420 buffer: Y[w*h] U[cw*ch] V[cw*ch], cw=(w+1)/2, ch=(h+1)/2. */
 int orc_decode_i420(const Vp8DecodedFrame* f, uint32_t width, uint32_t height, int filtered, uint8_t* out);
 

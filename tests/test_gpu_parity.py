@@ -1,0 +1,220 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI of libvp8gpu.so, against
+   (1) digests of the unmodified reference decoder's -yuv/-yuvf/-ppm/-png bytes (tests/golden, bench_data),
+   (2) the CPU oracle on seeded fuzz frames, and (3) size-independent properties at the benchmark sizes.
+Bit-exact is the bar: every comparison is equality of bytes."""
+import ctypes as C
+import errno
+import json
+
+import numpy as np
+import pytest
+
+from vp8fix import GOLDEN, ROOT, fuzz_frame, sha
+
+pytestmark = pytest.mark.gpu
+
+
+def _slices(buf, offs, sizes):
+    return [buf[int(o):int(o) + int(s)] for o, s in zip(offs, sizes)]
+
+
+def test_golden_webp_batch_yuv_yuvf_ppm(gpu_ctx, golden, parsed_golden):
+    """All 254 golden inputs (1x1 .. 960x1162, segmentation, i16/B_PRED mixes) as ONE mixed-size batch."""
+    names = sorted(golden)
+    kfs = [parsed_golden[n][0] for n in names]
+    frs = [parsed_golden[n][1] for n in names]
+    for filtered, key in ((False, "yuv"), (True, "yuvf")):
+        outs = gpu_ctx.decode_i420(kfs, frs, filtered=filtered)
+        bad = [n for n, o in zip(names, outs) if sha(o) != golden[n][key]]
+        assert not bad, f"-{key}: {len(bad)} differ, e.g. {bad[:5]}"
+    ppms = gpu_ctx.decode_ppm(kfs, frs)
+    bad = [n for n, p in zip(names, ppms) if sha(p) != golden[n]["ppm"]]
+    assert not bad, f"-ppm: {len(bad)} differ, e.g. {bad[:5]}"
+    # the reference's dwebp-derived golden PNG pixels (libwebp itself)
+    for n, p in zip(names, ppms):
+        if "dwebp_rgb" in golden[n]:
+            w, h = golden[n]["width"], golden[n]["height"]
+            assert sha(p[len(p) - w * h * 3:]) == golden[n]["dwebp_rgb"], n
+
+
+def test_reference_fuzz_digests(gpu_ctx):
+    """120 struct-level fuzz frames whose digests came from the real reference hot path: simple filter,
+    sharpness, lf deltas, absolute segment levels, int16 wrap of dequant/IDCT."""
+    fz = json.loads((GOLDEN / "fuzz.json").read_text())
+    seeds = sorted(fz, key=int)
+    frames = [fuzz_frame(int(s), fz[s]["width"], fz[s]["height"], **fz[s]["kw"]) for s in seeds]
+    kfs, ds = [f.header() for f in frames], [f.cstruct() for f in frames]
+    for filtered, key in ((False, "yuv"), (True, "yuvf")):
+        outs = gpu_ctx.decode_i420(kfs, ds, filtered=filtered)
+        bad = [s for s, o in zip(seeds, outs) if sha(o) != fz[s][key]]
+        assert not bad, f"{key}: seeds {bad[:8]}"
+    ppms = gpu_ctx.decode_ppm(kfs, ds)
+    assert not [s for s, p in zip(seeds, ppms) if sha(p) != fz[s]["ppm"]]
+
+
+@pytest.mark.parametrize("warps", [4, 8, 16, 32])
+def test_fuzz_vs_oracle_all_warp_shapes(gpu_ctx, oracle, warps):
+    gpu_ctx.set_tuning(warps, 0)
+    try:
+        frames = []
+        for s in range(48):
+            rng = np.random.default_rng(s * 31 + warps)
+            frames.append(fuzz_frame(9000 + s + 100 * warps, int(rng.integers(1, 400)), int(rng.integers(1, 400)),
+                                     amp=[5, 40, 400, 2500][s % 4], density=[0.02, 0.2, 0.7][s % 3], raw=bool(s & 1)))
+        kfs, ds = [f.header() for f in frames], [f.cstruct() for f in frames]
+        for filtered in (False, True):
+            outs = gpu_ctx.decode_i420(kfs, ds, filtered=filtered)
+            for f, o in zip(frames, outs):
+                assert np.array_equal(o, oracle.decode_i420(f, filtered)), (f.width, f.height, filtered)
+    finally:
+        gpu_ctx.set_tuning(0, 0)
+
+
+def test_edge_geometries(gpu_ctx, oracle):
+    """1-pixel frames, single rows/columns of macroblocks, widths that break 4-byte store alignment."""
+    dims = [(1, 1), (1, 40), (40, 1), (2, 2), (15, 15), (16, 16), (17, 17), (33, 16), (16, 33), (129, 129), (131, 67),
+            (1000, 24), (24, 1000), (258, 30), (255, 255)]
+    frames = [fuzz_frame(70 + i, w, h, density=0.3) for i, (w, h) in enumerate(dims)]
+    kfs, ds = [f.header() for f in frames], [f.cstruct() for f in frames]
+    for filtered in (False, True):
+        for f, o in zip(frames, gpu_ctx.decode_i420(kfs, ds, filtered=filtered)):
+            assert np.array_equal(o, oracle.decode_i420(f, filtered)), (f.width, f.height, filtered)
+    for f, p in zip(frames, gpu_ctx.decode_ppm(kfs, ds)):
+        yuvf = oracle.decode_i420(f, True)
+        assert p == oracle.ppm(oracle.rgb(yuvf, f.width, f.height), f.width, f.height), (f.width, f.height)
+
+
+def test_all_zero_and_saturated_inputs(gpu_ctx, oracle):
+    a = fuzz_frame(1, 96, 80, density=0.0)                          # prediction only, every IDCT short-circuits
+    b = fuzz_frame(2, 96, 80, density=1.0, amp=2047, q_index=127)   # every coefficient set, maximal quantiser
+    c = fuzz_frame(3, 96, 80, density=1.0, amp=32767)               # beyond any bitstream: pure int16 wrap behaviour
+    for f in (a, b, c):
+        for filtered in (False, True):
+            got = gpu_ctx.decode_i420([f.header()], [f.cstruct()], filtered=filtered)[0]
+            assert np.array_equal(got, oracle.decode_i420(f, filtered))
+
+
+def test_has_coeff_may_be_null(gpu_ctx, oracle):
+    f = fuzz_frame(11, 120, 90, lf_level=30, lf_use_simple=0)
+    got = gpu_ctx.decode_i420([f.header()], [f.cstruct(drop_has_coeff=True)], filtered=True)[0]
+    assert np.array_equal(got, oracle.decode_i420(f, True, drop_has_coeff=True))
+
+
+def test_staged_entry_points_recon_filter_rgb(gpu_ctx, oracle):
+    """vp8_gpu_recon -> vp8_gpu_filter -> vp8_gpu_rgb on macroblock-aligned planes, checked after every stage."""
+    frames = [fuzz_frame(300 + s, 40 + 23 * s, 200 - 17 * s, density=0.25) for s in range(8)]
+    b = gpu_ctx.recon([f.header() for f in frames], [f.cstruct() for f in frames])
+    want = [oracle.recon_padded(f) for f in frames]
+    for i, f in enumerate(frames):
+        for got, w in zip(gpu_ctx.download_padded(b, i), want[i]):
+            assert np.array_equal(got, w), ("recon", i)
+    gpu_ctx.filter(b)
+    for i, f in enumerate(frames):
+        oracle.loopfilter_padded(f, *want[i])
+        for got, w in zip(gpu_ctx.download_padded(b, i), want[i]):
+            assert np.array_equal(got, w), ("filter", i)
+    with pytest.raises(OSError):  # filtering twice is a caller error
+        gpu_ctx.filter(b)
+    gpu_ctx.rgb(b)
+    buf, offs, sizes = gpu_ctx.download_ppm(b)
+    for f, p in zip(frames, _slices(buf, offs, sizes)):
+        yuvf = oracle.decode_i420(f, True)
+        assert p.tobytes() == oracle.ppm(oracle.rgb(yuvf, f.width, f.height), f.width, f.height)
+    b.free()
+
+
+def test_reference_module_interfaces(lib, gpu_ctx, oracle):
+    """The seven symbols main.c binds, used the way main.c uses them (main.c:591,665,742,758,811,827)."""
+    f = fuzz_frame(21, 150, 70, density=0.3, lf_level=25, lf_use_simple=0)
+    kf, d = f.header(), f.cstruct()
+    yuv = lib.vp8_reconstruct_keyframe_yuv(kf, d)
+    yuvf = lib.vp8_reconstruct_keyframe_yuv_filtered(kf, d)
+    assert np.array_equal(yuv, oracle.decode_i420(f, False))
+    assert np.array_equal(yuvf, oracle.decode_i420(f, True))
+    rgb = oracle.rgb(yuvf, f.width, f.height)
+    assert lib.yuv420_write_ppm(yuvf, f.width, f.height) == oracle.ppm(rgb, f.width, f.height)
+    assert lib.yuv420_write_png(yuvf, f.width, f.height) == oracle.png(rgb, f.width, f.height)
+    # in-place loop filter on a host image with padded dims (vp8_loopfilter.h:10-14)
+    y, u, v = oracle.recon_padded(f)
+    wy, wu, wv = y.copy(), u.copy(), v.copy()
+    oracle.loopfilter_padded(f, wy, wu, wv)
+    lib.vp8_loopfilter_apply_keyframe(y, u, v, d)
+    assert np.array_equal(y, wy) and np.array_equal(u, wu) and np.array_equal(v, wv)
+    # dims that are not the macroblock grid are rejected like the reference does (vp8_loopfilter.c:206-209)
+    with pytest.raises(OSError) as e:
+        lib.vp8_loopfilter_apply_keyframe(y[:-16], u[:-8], v[:-8], d)
+    assert e.value.errno == errno.EINVAL
+
+
+def test_simple_filter_and_level_zero_paths(gpu_ctx, oracle):
+    frames = [fuzz_frame(400, 100, 60, lf_use_simple=1, lf_level=40, segmentation_enabled=0, lf_delta_enabled=0),
+              fuzz_frame(401, 100, 60, lf_use_simple=1),
+              fuzz_frame(402, 100, 60, lf_level=0, segmentation_enabled=0, lf_delta_enabled=0),          # no filtering at all
+              fuzz_frame(403, 100, 60, lf_level=0, segmentation_enabled=1, segmentation_abs=0,
+                         seg_lf_level=[0, 20, 0, 63], lf_delta_enabled=0)]                                # level 0 in some segments only
+    outs = gpu_ctx.decode_i420([f.header() for f in frames], [f.cstruct() for f in frames], filtered=True)
+    for f, o in zip(frames, outs):
+        assert np.array_equal(o, oracle.decode_i420(f, True))
+
+
+def test_pinned_and_pageable_inputs_agree(lib, gpu_ctx, golden):
+    from webp_decoder_b200 import parse as P
+    names = [n for n in sorted(golden) if golden[n]["width"] >= 100][:24]
+    datas = [(GOLDEN / "webp" / n).read_bytes() for n in names]
+    h2d0 = gpu_ctx.h2d_bytes
+    for pinned in (False, True):
+        pf = P.parse_batch(datas, pinned=pinned)
+        outs = gpu_ctx.decode_i420(pf.kf_list(), pf.frame_list(), filtered=True)
+        assert [sha(o) for o in outs] == [golden[n]["yuvf"] for n in names], pinned
+        pf.free()
+    assert gpu_ctx.h2d_bytes > h2d0
+
+
+def test_bench_inputs_full_size_parity_and_replication(lib, gpu_ctx):
+    """BASELINE.json sizes: 1080p / 512x512 / 4K inputs against the reference decoder's digests, then the
+    size-independent properties a big batch offers: replicas of one frame decode identically wherever they sit
+    in the batch, and a batch result equals the frame-at-a-time result."""
+    from webp_decoder_b200 import parse as P
+    dg = json.loads((ROOT / "bench_data" / "digests.json").read_text())
+    names = sorted(dg)
+    pf = P.parse_batch([(ROOT / "bench_data" / n).read_bytes() for n in names], pinned=True)
+    kfs, frs = pf.kf_list(), pf.frame_list()
+    for filtered, key in ((False, "yuv"), (True, "yuvf")):
+        outs = gpu_ctx.decode_i420(kfs, frs, filtered=filtered)
+        assert [sha(o) for o in outs] == [dg[n][key] for n in names], key
+    ppms = gpu_ctx.decode_ppm(kfs, frs)
+    assert [sha(p) for p in ppms] == [dg[n]["ppm"] for n in names]
+    # 96 replicas of the four 1080p frames, interleaved
+    idx = [i for i, n in enumerate(names) if "1920x1080" in n]
+    order = [idx[k % len(idx)] for k in range(96)]
+    outs = gpu_ctx.decode_i420([kfs[i] for i in order], [frs[i] for i in order], filtered=True)
+    for k, o in zip(order, outs):
+        assert sha(o) == dg[names[k]]["yuvf"]
+    single = gpu_ctx.decode_i420([kfs[idx[0]]], [frs[idx[0]]], filtered=True)[0]
+    assert sha(single) == dg[names[idx[0]]]["yuvf"]
+    pf.free()
+
+
+def test_argument_errors(lib, gpu_ctx):
+    f = fuzz_frame(5, 64, 64)
+    kf, d = f.header(), f.cstruct()
+    kf.width = 100  # macroblock grid no longer matches the frame size
+    with pytest.raises(OSError) as e:
+        gpu_ctx.decode_i420([kf], [d])
+    assert e.value.errno == errno.EINVAL
+    d2 = f.cstruct()
+    d2.coeff_y = C.POINTER(C.c_int16)()
+    with pytest.raises(OSError) as e:
+        gpu_ctx.decode_i420([f.header()], [d2])
+    assert e.value.errno == errno.EINVAL
+    with pytest.raises(OSError):
+        gpu_ctx.set_tuning(5, 0)
+
+
+def test_kernels_really_launch(gpu_ctx, oracle):
+    f = fuzz_frame(8, 64, 64, lf_level=20)
+    n0 = gpu_ctx.launches
+    gpu_ctx.decode_ppm([f.header()], [f.cstruct()])
+    assert gpu_ctx.launches - n0 == 2  # fused recon+filter wavefront, RGB
+    cfg = gpu_ctx.last_launch_config()
+    assert cfg["warps_per_image"] in (4, 8, 16, 32) and cfg["grid"] >= 1 and cfg["smem_bytes"] > 0

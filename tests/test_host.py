@@ -1,0 +1,130 @@
+"""Host-side logic and the C-ABI surface, no GPU needed: the library loads and exports every declared symbol,
+derives per-frame parameters like the oracle, parses .webp files like the reference's m01/m02/m05, and fails
+loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import errno
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from vp8fix import GOLDEN, I16_ARRAYS, SCALARS, U8_ARRAYS, VEC4, fuzz_frame
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols(header: Path):
+    text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b((?:vp8_gpu|vp8_parse|yuv420|vp8_reconstruct|vp8_loopfilter)\w*)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    L = lib.load_library()
+    syms = declared_symbols(ROOT / "include" / "vp8_gpu.h") + declared_symbols(ROOT / "include" / "vp8_parse.h")
+    assert len(syms) >= 38
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(lib.EXPORTS) <= set(syms)
+    # the seven symbols the reference's main.c / main_ultra.c bind from m06..m09
+    for s in ("yuv420_alloc", "yuv420_free", "vp8_reconstruct_keyframe_yuv", "vp8_reconstruct_keyframe_yuv_filtered",
+              "vp8_loopfilter_apply_keyframe", "yuv420_write_ppm_fd", "yuv420_write_png_fd"):
+        assert s in syms
+
+
+def test_struct_layouts_match_the_reference_abi(lib):
+    from webp_decoder_b200.abi import DecodedFrame, KeyFrameHeader, Yuv420Image
+    assert (C.sizeof(KeyFrameHeader), C.sizeof(DecodedFrame), C.sizeof(Yuv420Image)) == (28, 320, 40)
+    assert KeyFrameHeader.width.offset == 20 and KeyFrameHeader.height.offset == 22
+    assert DecodedFrame.segment_id.offset == 40 and DecodedFrame.coeff_v.offset == 112 and DecodedFrame.stats_opaque.offset == 120
+    assert Yuv420Image.y.offset == 16 and Yuv420Image.v.offset == 32
+
+
+def test_yuv420_alloc_free_contract(lib):
+    from webp_decoder_b200.abi import Yuv420Image
+    L = lib.load_library()
+    img = Yuv420Image()
+    assert L.yuv420_alloc(C.addressof(img), 5, 3) == 0
+    assert (img.width, img.height, img.stride_y, img.stride_uv) == (5, 3, 5, 3)
+    assert bytes(np.ctypeslib.as_array(img.y, (15,))) == b"\0" * 15           # vp8_recon.c:381
+    assert bytes(np.ctypeslib.as_array(img.u, (6,))) == b"\x80" * 6            # vp8_recon.c:382
+    L.yuv420_free(C.addressof(img))
+    assert not img.y and img.width == 0
+    C.set_errno(0)
+    assert L.yuv420_alloc(C.addressof(img), 0, 3) == -1 and C.get_errno() == errno.EINVAL
+    L.yuv420_free(None)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_frame_params_match_oracle(lib, oracle, seed):
+    fr = fuzz_frame(seed, 32, 32)
+    dq, lf = lib.frame_params(fr.cstruct())
+    odq, olf = oracle.frame_params(fr)
+    assert np.array_equal(dq, odq) and np.array_equal(lf, olf)
+
+
+def test_no_device_means_error_not_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(lib.Vp8GpuError) as e:
+        lib.Context(0)
+    assert e.value.errno == errno.EIO
+    fr = fuzz_frame(1, 16, 16)
+    with pytest.raises(lib.Vp8GpuError):
+        lib.vp8_reconstruct_keyframe_yuv_filtered(fr.header(), fr.cstruct())
+
+
+def test_legacy_entry_points_reject_bad_arguments(lib):
+    L = lib.load_library()
+    C.set_errno(0)
+    assert L.vp8_reconstruct_keyframe_yuv(None, None, None) == -1 and C.get_errno() == errno.EINVAL
+    assert L.vp8_loopfilter_apply_keyframe(None, None) == -1 and C.get_errno() == errno.EINVAL
+    assert L.yuv420_write_ppm_fd(-1, None) == -1 and C.get_errno() == errno.EINVAL
+    assert L.yuv420_write_png_fd(-1, None) == -1 and C.get_errno() == errno.EINVAL
+
+
+# ---------------------------------------------------------------------------------------------- host front end
+def test_parser_matches_reference_m05_on_golden_inputs(lib, reference, golden, parsed_golden):
+    for name in sorted(golden):
+        kf, d, pf = parsed_golden[name]
+        ref = reference.parse_webp((GOLDEN / "webp" / name).read_bytes())
+        assert (kf.width, kf.height) == (ref.width, ref.height), name
+        for k in SCALARS:
+            assert int(getattr(d, k)) == ref.params[k], (name, k)
+        for k in VEC4:
+            assert [int(getattr(d, k)[j]) for j in range(4)] == ref.params[k], (name, k)
+        i = list(sorted(golden)).index(name)
+        for k in U8_ARRAYS + I16_ARRAYS:
+            assert np.array_equal(pf.array(i, k), ref.arrays[k]), (name, k)
+
+
+def test_parser_is_reentrant_across_threads(lib, golden):
+    from webp_decoder_b200 import parse as P
+    names = sorted(golden)[:64]
+    datas = [(GOLDEN / "webp" / n).read_bytes() for n in names]
+    a = P.parse_batch(datas, threads=1)
+    b = P.parse_batch(datas * 3, threads=8)
+    for i in range(len(names)):
+        for k in ("coeff_y", "coeff_y2", "bmode", "ymode", "has_coeff"):
+            for rep in range(3):
+                assert np.array_equal(a.array(i, k), b.array(i + rep * len(names), k)), (names[i], k)
+
+
+def test_parser_rejects_what_the_reference_rejects(lib):
+    from webp_decoder_b200 import parse as P
+    good = (GOLDEN / "webp" / "enc_noise_16x16_q10_rdo_nolf.webp").read_bytes()
+    bad_cases = {
+        "truncated": good[:-3],
+        "not riff": b"RIFX" + good[4:],
+        "not webp": good[:8] + b"WEBX" + good[12:],
+        "vp8l chunk": good[:12] + b"VP8L" + good[16:],
+        "inter frame": good[:20] + bytes([good[20] | 1]) + good[21:],
+        "bad start code": good[:23] + b"\x00\x01\x2a" + good[26:],
+        "empty": b"",
+    }
+    for what, data in bad_cases.items():
+        with pytest.raises(OSError) as e:
+            P.parse_batch([data], threads=1)
+        assert e.value.errno == errno.EINVAL, what
+    assert P.webp_size(good) == (16, 16)

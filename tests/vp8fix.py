@@ -246,6 +246,8 @@ class Oracle(Checker):
         L.orc_png_bound.restype = C.c_size_t
         L.orc_png.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.orc_png.restype = C.c_size_t
+        L.orc_frame_params.argtypes = [C.POINTER(DecodedFrame), C.c_void_p, C.c_void_p]
+        L.orc_frame_params.restype = None
 
     def decode_i420(self, fr, filtered, drop_has_coeff=False):
         out = np.empty(fr.i420_size, np.uint8)
@@ -253,6 +255,12 @@ class Oracle(Checker):
         rc = self.lib.orc_decode_i420(C.byref(d), fr.width, fr.height, int(filtered), out.ctypes.data)
         assert rc == 0
         return out
+
+    def frame_params(self, fr):
+        dq, lf = np.zeros((4, 6), np.int16), np.zeros((4, 2, 4), np.uint8)
+        d = fr.cstruct()
+        self.lib.orc_frame_params(C.byref(d), dq.ctypes.data, lf.ctypes.data)
+        return dq, lf
 
     def recon_padded(self, fr):
         pw, ph = fr.mb_cols * 16, fr.mb_rows * 16

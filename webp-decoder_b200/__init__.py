@@ -40,7 +40,7 @@ EXPORTS = [
     "vp8_gpu_filter", "vp8_gpu_rgb", "vp8_gpu_run", "vp8_gpu_i420_bytes", "vp8_gpu_ppm_bytes",
     "vp8_gpu_download_i420", "vp8_gpu_download_ppm", "vp8_gpu_download_images", "vp8_gpu_download_padded",
     "vp8_gpu_batch_size", "vp8_gpu_launch_count", "vp8_gpu_h2d_bytes", "vp8_gpu_d2h_bytes",
-    "vp8_gpu_last_launch_config", "vp8_gpu_frame_params",
+    "vp8_gpu_last_launch_config", "vp8_gpu_frame_params", "vp8_gpu_kernel_time",
 ]
 
 _lib = None
@@ -90,6 +90,7 @@ def load_library() -> C.CDLL:
         getattr(L, fn).argtypes = [vp]
         getattr(L, fn).restype = C.c_uint64
     L.vp8_gpu_last_launch_config.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.vp8_gpu_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.vp8_gpu_frame_params.argtypes = [vp, vp, vp]
     L.vp8_gpu_frame_params.restype = None
     L.yuv420_alloc.argtypes = [vp, C.c_uint32, C.c_uint32]
@@ -293,6 +294,12 @@ class Context:
     @property
     def d2h_bytes(self) -> int:
         return int(self._L.vp8_gpu_d2h_bytes(self._h))
+
+    def kernel_time(self):
+        """(total_ms, launches) of the wavefront launches since the previous call, timed with CUDA events."""
+        ms, n = C.c_double(), C.c_int()
+        _check(self._L.vp8_gpu_kernel_time(self._h, C.byref(ms), C.byref(n)), "vp8_gpu_kernel_time")
+        return ms.value, n.value
 
     def last_launch_config(self):
         w, g, s = C.c_int(), C.c_int(), C.c_int()

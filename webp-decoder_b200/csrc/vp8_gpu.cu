@@ -73,6 +73,9 @@ struct vp8_gpu_ctx {
 	std::vector<FreeBlock> cache; // device blocks kept for reuse
 	uint64_t launches = 0, h2d = 0, d2h = 0;
 	int last_warps = 0, last_grid = 0, last_smem = 0;
+	// device-side duration of every wavefront launch since the last vp8_gpu_kernel_time() query
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed; // recorded, not yet read
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spare;
 };
 
 namespace {
@@ -110,6 +113,7 @@ struct vp8_gpu_batch {
 	int max_mb_cols = 0;
 	PlaneState state = PLANES_NONE;
 	bool filtered = false, have_rgb = false, have_coeffs = true;
+	int desc_key = -1; // kernel_mode*2 + layout of the descriptors currently on the device
 };
 
 namespace {
@@ -436,6 +440,7 @@ int ensure_planes(vp8_gpu_ctx* c, vp8_gpu_batch* b, int layout) {
 
 // Descriptors for one launch. kernel_mode: Vp8KernelMode; layout: where the pixels go.
 int push_descs(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layout) {
+	if (b->desc_key == kernel_mode * 2 + layout) return 0; // already resident
 	std::vector<Vp8ImgDesc> h(b->n);
 	for (int i = 0; i < b->n; i++) {
 		const FrameMeta& m = b->meta[i];
@@ -485,6 +490,7 @@ int push_descs(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layout) {
 	}
 	// pageable source: the runtime stages it before returning, so the vector may die right after
 	CU(cudaMemcpyAsync(b->d_desc, h.data(), sizeof(Vp8ImgDesc) * b->n, cudaMemcpyHostToDevice, c->stream));
+	b->desc_key = kernel_mode * 2 + layout;
 	return 0;
 }
 
@@ -509,7 +515,22 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 	if (per_sm <= 0) return fail(EIO, "wavefront kernel does not fit on an SM (frame too wide?)", cudaGetLastError());
 	if (c->tune_imgs_per_sm > 0) per_sm = std::min(per_sm, c->tune_imgs_per_sm);
 	const int grid = std::min(b->n, per_sm * c->sm_count);
+	std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+	if (!c->spare.empty()) {
+		ev = c->spare.back();
+		c->spare.pop_back();
+	} else {
+		CU(cudaEventCreate(&ev.first));
+		CU(cudaEventCreate(&ev.second));
+	}
+	CU(cudaEventRecord(ev.first, c->stream));
 	const int rc = vp8_launch_wavefront(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, c->stream);
+	CU(cudaEventRecord(ev.second, c->stream));
+	c->timed.push_back(ev);
+	if (c->timed.size() > 4096) { // nobody is asking: recycle the oldest
+		c->spare.push_back(c->timed.front());
+		c->timed.erase(c->timed.begin());
+	}
 	if (rc != 0) return fail(EIO, "wavefront launch", (cudaError_t)rc);
 	c->launches++;
 	c->last_warps = warps;
@@ -750,6 +771,11 @@ void vp8_gpu_destroy(vp8_gpu_ctx* c) {
 		if (c->bounce[i]) cudaFreeHost(c->bounce[i]);
 		if (c->bounce_ev[i]) cudaEventDestroy(c->bounce_ev[i]);
 	}
+	for (auto* v : {&c->timed, &c->spare})
+		for (auto& ev : *v) {
+			cudaEventDestroy(ev.first);
+			cudaEventDestroy(ev.second);
+		}
 	if (c->own_stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -975,6 +1001,24 @@ int vp8_gpu_last_launch_config(const vp8_gpu_ctx* c, int* warps, int* grid, int*
 }
 
 void vp8_gpu_frame_params(const Vp8DecodedFrame* f, int16_t dq[4][6], uint8_t lf[4][2][4]) { frame_params(f, dq, lf); }
+
+int vp8_gpu_kernel_time(vp8_gpu_ctx* c, double* total_ms, int* launches) {
+	if (!c) return fail(EINVAL, "null context");
+	double sum = 0;
+	int n = 0;
+	for (auto& ev : c->timed) {
+		CU(cudaEventSynchronize(ev.second));
+		float ms = 0;
+		CU(cudaEventElapsedTime(&ms, ev.first, ev.second));
+		sum += ms;
+		n++;
+		c->spare.push_back(ev);
+	}
+	c->timed.clear();
+	if (total_ms) *total_ms = sum;
+	if (launches) *launches = n;
+	return 0;
+}
 
 // ================================================================================================ C-ABI: reference module interfaces
 
