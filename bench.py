@@ -150,7 +150,10 @@ def gpu_arm(args):
     import webp_decoder_b200 as W
     from webp_decoder_b200 import parse as P
 
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream: its handle is what the library launches on, so torch.cuda.Event sees our kernels
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = W.Context(local, stream.cuda_stream)
     if args.warps or args.images_per_sm:
         ctx.set_tuning(args.warps, args.images_per_sm)
