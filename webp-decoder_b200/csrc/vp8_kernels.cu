@@ -56,7 +56,8 @@ __constant__ uint8_t c_bpred_taps[10 * 16] = {
 
 constexpr int kProgRing = 64;      // progress stamps, ring over macroblock rows (>= 2*NW)
 constexpr int kStampRow = 4096;    // stamp = (row+1)*kStampRow + macroblocks done in that row
-constexpr int kSmemFixed = 768;    // progress ring (256) + tap table (256) + image descriptor (256)
+constexpr int kBtabWords = 2 * 11 * 16;
+constexpr int kSmemFixed = 256 + 256 + kBtabWords * 4; // progress ring + image descriptor + B_PRED lane table
 
 // Per-warp shared-memory workspace.
 //   rt_*: reconstruction tile with a 1-pixel top/left border (what intra prediction reads).
@@ -64,6 +65,8 @@ constexpr int kSmemFixed = 768;    // progress ring (256) + tap table (256) + im
 //         chroma row r in [-1,7] at (r+1)*12, column c in [-1,7] at 4+c.
 //   ft_*: filter tile with 4-pixel top/left aprons. luma row r in [-4,15] at (r+4)*20, column c at 4+c;
 //         chroma row r in [-4,7] at (r+4)*12, column c at 4+c.
+//   coef: the macroblock's 25 coefficient blocks as landed by cp.async: 16-byte half h of block i at [h*25+i]
+//         (blocks 0..15 luma, 16..19 U, 20..23 V, 24 Y2), so that lane i reads both halves without bank conflicts.
 struct __align__(16) WarpWs {
 	uint8_t rt_y[17 * 24];
 	uint8_t rt_u[9 * 12];
@@ -73,9 +76,11 @@ struct __align__(16) WarpWs {
 	uint8_t ft_y[20 * 20];
 	uint8_t ft_u[12 * 12];
 	uint8_t ft_v[12 * 12];
-	uint8_t pad_[64];
+	uint4 coef[50];
+	uint8_t pad_[32];
 };
 static_assert(sizeof(WarpWs) % 16 == 0, "WarpWs alignment");
+static_assert(offsetof(WarpWs, res) % 16 == 0 && offsetof(WarpWs, coef) % 16 == 0, "vector slots must be 16-byte aligned");
 
 struct OutPlane {
 	uint8_t* p;
@@ -85,22 +90,22 @@ struct OutPlane {
 
 // ------------------------------------------------------------------------------------------------ small helpers
 __device__ __forceinline__ int s16(int v) { return (int)(short)v; }
-__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int clip255(int v) { return __vimin_s32_relu(v, 255); }                 // VIMNMX.RELU
+__device__ __forceinline__ int add_clip255(int a, int b) { return __viaddmin_s32_relu(a, b, 255); } // VIADDMNMX.RELU
 __device__ __forceinline__ int sclamp(int v) { return min(max(v, -128), 127); }
+__device__ __forceinline__ int absdiff(int a, int b) { return (int)__sad(a, b, 0u); }               // VABSDIFF
 __device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
 __device__ __forceinline__ void st32(uint8_t* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
 __device__ __forceinline__ uint32_t sum4(uint32_t w) { return __dp4a(w, 0x01010101u, 0u); }
 
-__device__ __forceinline__ uint4 ldg_stream(const int16_t* p) {
-	// coefficients are read exactly once: keep them out of L1
-	uint4 r;
-	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-	             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-	             : "l"(p));
-	return r;
+// 16-byte global -> shared copy that bypasses L1 (coefficients are read exactly once).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Store 4 pixels at (ox, oy) of an output plane, honouring the crop.
+// Store 4 pixels at (ox, oy) of an output plane, honouring the crop (negative coordinates are outside too).
 __device__ __forceinline__ void put_word(const OutPlane& o, int ox, int oy, uint32_t v) {
 	if ((uint32_t)oy >= o.h || (uint32_t)ox >= o.w) return;
 	uint8_t* d = o.p + (size_t)oy * o.stride + ox;
@@ -180,22 +185,23 @@ enum { EDGE_MB = 0, EDGE_INNER = 1, EDGE_SIMPLE = 2 };
 template <int KIND>
 __device__ __forceinline__ bool lf_position(int p3, int& p2, int& p1, int& p0, int& q0, int& q1, int& q2, int q3, int lim,
                                             int interior, int hev_thr) {
-	if (2 * abs(p0 - q0) + (abs(p1 - q1) >> 1) > lim) return false;
+	if (2 * absdiff(p0, q0) + (absdiff(p1, q1) >> 1) > lim) return false;
 	bool hev = false;
 	if (KIND != EDGE_SIMPLE) {
-		int m = max(max(abs(p3 - p2), abs(p2 - p1)), max(abs(p1 - p0), abs(q3 - q2)));
-		m = max(m, max(abs(q2 - q1), abs(q1 - q0)));
-		if (m > interior) return false;
-		hev = abs(p1 - p0) > hev_thr || abs(q1 - q0) > hev_thr;
+		const int dp = absdiff(p1, p0), dq = absdiff(q1, q0);
+		int m = __vimax3_s32(absdiff(p3, p2), absdiff(p2, p1), dp);
+		m = __vimax3_s32(m, absdiff(q3, q2), absdiff(q2, q1));
+		if (max(m, dq) > interior) return false;
+		hev = max(dp, dq) > hev_thr;
 		if (KIND == EDGE_MB && !hev) {
 			int w = sclamp(sclamp(p1 - q1) + 3 * (q0 - p0));
 			int a = (27 * w + 63) >> 7, b = (18 * w + 63) >> 7, c = (9 * w + 63) >> 7;
-			p0 = clip255(p0 + a);
-			q0 = clip255(q0 - a);
-			p1 = clip255(p1 + b);
-			q1 = clip255(q1 - b);
-			p2 = clip255(p2 + c);
-			q2 = clip255(q2 - c);
+			p0 = add_clip255(p0, a);
+			q0 = add_clip255(q0, -a);
+			p1 = add_clip255(p1, b);
+			q1 = add_clip255(q1, -b);
+			p2 = add_clip255(p2, c);
+			q2 = add_clip255(q2, -c);
 			return true;
 		}
 	}
@@ -203,13 +209,13 @@ __device__ __forceinline__ bool lf_position(int p3, int& p2, int& p1, int& p0, i
 	int a = 3 * (q0 - p0);
 	if (outer) a += sclamp(p1 - q1);
 	a = sclamp(a);
-	int f1 = sclamp(a + 4) >> 3, f2 = sclamp(a + 3) >> 3;
-	q0 = clip255(q0 - f1);
-	p0 = clip255(p0 + f2);
+	int f1 = min(a + 4, 127) >> 3, f2 = min(a + 3, 127) >> 3; // a >= -128 already
+	q0 = add_clip255(q0, -f1);
+	p0 = add_clip255(p0, f2);
 	if (!outer) {
 		int h = (f1 + 1) >> 1;
-		q1 = clip255(q1 - h);
-		p1 = clip255(p1 + h);
+		q1 = add_clip255(q1, -h);
+		p1 = add_clip255(p1, h);
 	}
 	return true;
 }
@@ -248,12 +254,16 @@ __device__ __forceinline__ void lf_across_rows(uint8_t* q, int s, int lim, int i
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+#ifndef VP8_MIN_CTAS
+#define VP8_MIN_CTAS(NW) ((NW) == 4 ? 7 : (NW) == 8 ? 3 : 1)
+#endif
+
 template <int NW, bool RECON, bool FILTER>
-__global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px) {
+__global__ void __launch_bounds__(NW * 32, VP8_MIN_CTAS(NW)) vp8_mb_wavefront(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	volatile int* prog = reinterpret_cast<volatile int*>(smem);
-	uint8_t* taps = smem + 256;
-	Vp8ImgDesc* sd = reinterpret_cast<Vp8ImgDesc*>(smem + 512);
+	Vp8ImgDesc* sd = reinterpret_cast<Vp8ImgDesc*>(smem + 256);
+	uint32_t* btab = reinterpret_cast<uint32_t*>(smem + 512);
 	// line buffers: unfiltered bottom rows (tu), last four filtered rows (tf)
 	uint8_t* tu_y = smem + kSmemFixed;
 	uint8_t* tu_u = tu_y + line_px;
@@ -269,20 +279,44 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 	static_assert(sizeof(Vp8ImgDesc) <= 256, "descriptor must fit its shared-memory slot");
 	static_assert(2 * NW <= kProgRing, "progress ring too small");
 
-	for (int i = tid; i < 160; i += NW * 32) taps[i] = c_bpred_taps[i];
+	// B_PRED lane table: btab[half][mode 0..10][pixel] = lane(a) | lane(b) << 8 | lane(c) << 16 | kind << 24, where the
+	// prediction is (a + 2b + c + 2) >> 2 over edge-vector entries held by lanes half*16 + index (a 2-tap average is
+	// the same formula with c = a), kind 1 = B_TM (clip(a + b - c) with a = L[r], b = A[c], c = P), kind 2 = B_DC,
+	// kind 3 = out-of-range mode (constant 128, reference vp8_recon.c:352-356).
+	if (RECON) {
+		for (int i = tid; i < kBtabWords; i += NW * 32) {
+			const int h = i / 176, m = (i % 176) / 16, p = i % 16, base = h * 16;
+			uint32_t a = 0, b = 0, c = 0, kind = 0;
+			if (m == 0) kind = 2;
+			else if (m == 1) { a = 5 - (p >> 2); b = 7 + (p & 3); c = 6; kind = 1; }
+			else if (m == 10) kind = 3;
+			else {
+				const int tap = c_bpred_taps[m * 16 + p], t0 = tap & 15;
+				a = t0; b = t0 + 1; c = (tap & 16) ? t0 : t0 + 2;
+			}
+			btab[i] = (base + a) | ((base + b) << 8) | ((base + c) << 16) | (kind << 24);
+		}
+	}
 
 	// lane roles that never change
 	//   transform / block-per-lane prediction: lanes 0..15 luma block, 16..19 U block, 20..23 V block, 24 Y2
-	const bool is_luma_lane = lane < 16, is_chroma_lane = lane >= 16 && lane < 24;
-	const int cb = lane & 3;                                   // chroma block index within its plane
+	const bool is_luma_lane = lane < 16;
+	const int cb = lane & 3; // chroma block index within its plane
 	const int blk_bx = is_luma_lane ? (lane & 3) * 4 : (cb & 1) * 4;
 	const int blk_by = is_luma_lane ? (lane >> 2) * 4 : (cb >> 1) * 4;
-	//   B_PRED pixel-per-lane: two sub-blocks in flight, 16 lanes each
+	//   B_PRED pixel-per-lane: two sub-blocks in flight, 16 lanes each. At step s half h works on sub-block
+	//   (row (s>>1)-h, column (s&1)+2h): every address is a per-lane base plus a per-step compile-time constant.
 	const int half = lane >> 4, px_i = lane & 15, px_r = px_i >> 2, px_c = px_i & 3;
 	const int e_dy = px_i <= 2 ? 3 : (px_i <= 5 ? 5 - px_i : -1);
 	const int e_dx = px_i <= 6 ? -1 : (px_i == 15 ? 7 : px_i - 7);
-	const int e_off = e_dy * 24 + e_dx;
+	uint8_t* const bp_edge = ws.rt_y + half * (8 - 96) + e_dy * 24 + e_dx;      // + step constant -> this lane's edge byte
+	uint8_t* const bp_out = ws.rt_y + half * (8 - 96) + px_r * 24 + px_c;        // + step constant -> this lane's pixel
+	const int16_t* const bp_res = &ws.res[0][0] + half * (-2 * 16) + px_i;       // + step constant -> this lane's residual
+	const uint32_t* const bp_tab = btab + half * 176 + px_i;                     // + mode*16 -> this lane's table word
+	const int bp_blk = -2 * half;                                                // + step constant -> sub-block index
 	const bool dc_tap = (px_i >= 2 && px_i <= 5) || (px_i >= 7 && px_i <= 10);
+	//   coefficient stream of this lane (lanes 0..24), in int16 units per macroblock
+	const int cstep = is_luma_lane ? 256 : (lane < 24 ? 64 : 16);
 
 	for (int img = blockIdx.x; img < n_images; img += gridDim.x) {
 		__syncthreads(); // previous image fully retired before its line buffers and descriptor are reused
@@ -302,12 +336,17 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 		            ((reinterpret_cast<uintptr_t>(sd->out_u) | sd->out_stride_uv) & 3) == 0};
 		OutPlane ov{sd->out_v, sd->out_stride_uv, ocw, och,
 		            ((reinterpret_cast<uintptr_t>(sd->out_v) | sd->out_stride_uv) & 3) == 0};
+		const bool words_ok = oy.word_ok && ou.word_ok && ov.word_ok;
 		const bool lf_simple = sd->lf_simple != 0;
+		const uint8_t* const g_ymode = sd->ymode;
+		const uint8_t* const g_seg = sd->segment_id;
 
 		for (int y = warp; y < rows; y += NW) {
 			const bool last_row = (y == rows - 1);
+			const size_t mb_row0 = (size_t)y * cols;
 
 			// ---- row start: out-of-frame left neighbours (129) and corner (127 on the top row, else 129)
+			const int16_t* cptr = nullptr;
 			if (RECON) {
 				ws.lcol[lane] = 129;
 				if (lane < 16) ws.rt_y[(lane + 1) * 24 + 3] = 129;
@@ -317,50 +356,43 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 				if (lane == 0) ws.rt_y[3] = corner;
 				if (lane == 1) ws.rt_u[3] = corner;
 				if (lane == 2) ws.rt_v[3] = corner;
-			}
-
-			// ---- software prefetch of the first macroblock's coefficients
-			uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
-			const int16_t* cptr = nullptr;
-			size_t cstep = 0; // elements per macroblock for this lane's coefficient stream
-			if (RECON) {
-				const size_t mb0 = (size_t)y * cols;
-				if (is_luma_lane) { cptr = sd->coeff_y + (mb0 * 16 + lane) * 16; cstep = 256; }
-				else if (lane < 20) { cptr = sd->coeff_u + (mb0 * 4 + cb) * 16; cstep = 64; }
-				else if (lane < 24) { cptr = sd->coeff_v + (mb0 * 4 + cb) * 16; cstep = 64; }
-				else if (lane == 24) { cptr = sd->coeff_y2 + mb0 * 16; cstep = 16; }
+				// coefficient stream of this lane, and the first macroblock's blocks on their way to shared memory
+				if (is_luma_lane) cptr = sd->coeff_y + (mb_row0 * 16 + lane) * 16;
+				else if (lane < 20) cptr = sd->coeff_u + (mb_row0 * 4 + cb) * 16;
+				else if (lane < 24) cptr = sd->coeff_v + (mb_row0 * 4 + cb) * 16;
+				else if (lane == 24) cptr = sd->coeff_y2 + mb_row0 * 16;
 				if (cptr) {
-					c0 = ldg_stream(cptr);
-					c1 = ldg_stream(cptr + 8);
+					cp_async16(&ws.coef[lane], cptr);
+					cp_async16(&ws.coef[25 + lane], cptr + 8);
 				}
+				cp_async_commit();
 			}
+			int ymode_next = g_ymode[mb_row0];
+			int seg_next = g_seg ? g_seg[mb_row0] : 0;
 
 			for (int x = 0; x < cols; x++) {
-				const size_t mb = (size_t)y * cols + x;
+				const size_t mb = mb_row0 + x;
 				const bool last_col = (x == cols - 1);
 
-				// ---- per-macroblock syntax
-				const int ymode = sd->ymode[mb];
+				// ---- per-macroblock syntax (this macroblock's was fetched one iteration ago)
+				const int ymode = ymode_next;
 				const bool bpred = (ymode == 4);
-				const int seg = sd->segment_id ? (sd->segment_id[mb] & 3) : 0;
+				const int seg = seg_next & 3;
+				if (!last_col) {
+					ymode_next = g_ymode[mb + 1];
+					if (g_seg) seg_next = g_seg[mb + 1];
+				}
 				int uvmode = 0, bmode = 0;
 				if (RECON) {
 					uvmode = sd->uv_mode[mb];
-					if (bpred && lane < 16) bmode = sd->bmode[mb * 16 + lane];
-				}
-
-				// ---- issue the next macroblock's coefficient loads before doing anything that can stall
-				uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-				if (RECON && cptr && !last_col) {
-					n0 = ldg_stream(cptr + (size_t)(x + 1) * cstep);
-					n1 = ldg_stream(cptr + (size_t)(x + 1) * cstep + 8);
+					if (bpred && lane < 16) bmode = min((int)sd->bmode[mb * 16 + lane], 10);
 				}
 
 				// ---- wait for MB(x+1, y-1) (or the end of the row above)
 				if (y > 0) {
 					if (lane == 0) {
 						const int target = y * kStampRow + min(x + 2, cols);
-						while (prog[(y - 1) & (kProgRing - 1)] < target) __nanosleep(40);
+						while (prog[(y - 1) & (kProgRing - 1)] < target) __nanosleep(32);
 						__threadfence_block();
 					}
 					__syncwarp();
@@ -395,6 +427,24 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 						}
 					}
 
+					// ---- coefficients: landed by cp.async, pick up this lane's block, then refill for MB x+1
+					cp_async_wait_all();
+					__syncwarp();
+					uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+					if (lane < 25) {
+						c0 = ws.coef[lane];
+						c1 = ws.coef[25 + lane];
+					}
+					__syncwarp();
+					if (!last_col) {
+						if (cptr) {
+							const int16_t* nx = cptr + (size_t)(x + 1) * cstep;
+							cp_async16(&ws.coef[lane], nx);
+							cp_async16(&ws.coef[25 + lane], nx + 8);
+						}
+						cp_async_commit();
+					}
+
 					// ---- dequantise + inverse transforms, one 4x4 block per lane (lanes 0..24)
 					int r[16];
 					bool any = false;
@@ -412,10 +462,16 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 						if (!bpred) {
 							// Y2: lane 24 runs the WHT, luma lanes take their DC from it (vp8_recon.c:563-586)
 							if (lane == 24) {
-								int d[16];
-								iwht4x4(v, d);
+								if ((c0.x | c0.y | c0.z | c0.w | c1.x | c1.y | c1.z | c1.w) == 0) {
+									uint4* z = reinterpret_cast<uint4*>(ws.res[0]);
+									z[0] = make_uint4(0, 0, 0, 0);
+									z[1] = make_uint4(0, 0, 0, 0);
+								} else {
+									int d[16];
+									iwht4x4(v, d);
 #pragma unroll
-								for (int i = 0; i < 16; i++) ws.res[0][i] = (int16_t)d[i];
+									for (int i = 0; i < 16; i++) ws.res[0][i] = (int16_t)d[i];
+								}
 							}
 							__syncwarp();
 							if (is_luma_lane) v[0] = ws.res[0][lane];
@@ -471,7 +527,7 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 								const int base = (int)((l >> (8 * k)) & 255u) - p;
 								uint32_t w = 0;
 #pragma unroll
-								for (int j = 0; j < 4; j++) w |= (uint32_t)clip255(base + (int)((a >> (8 * j)) & 255u)) << (8 * j);
+								for (int j = 0; j < 4; j++) w |= (uint32_t)add_clip255(base, (int)((a >> (8 * j)) & 255u)) << (8 * j);
 								pw[k] = w;
 							}
 						} else { // DC (also any out-of-range mode): vp8_recon.c:152-176
@@ -495,7 +551,7 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 							if (any) {
 								uint32_t o = 0;
 #pragma unroll
-								for (int j = 0; j < 4; j++) o |= (uint32_t)clip255((int)((w >> (8 * j)) & 255u) + r[4 * k + j]) << (8 * j);
+								for (int j = 0; j < 4; j++) o |= (uint32_t)add_clip255((int)((w >> (8 * j)) & 255u), r[4 * k + j]) << (8 * j);
 								w = o;
 							}
 							st32(dst + k * stride, w);
@@ -505,37 +561,37 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 
 					// ---- B_PRED luma: sub-block wavefront, step s handles sub-blocks with col + 2*row == s
 					if (bpred) {
-#pragma unroll 1
+						// which sub-blocks need the two non-tap predictors (bit = sub-block index)
+						const uint32_t special = __ballot_sync(0xffffffffu, lane < 16 && (bmode <= 1 || bmode == 10));
+#pragma unroll
 						for (int s = 0; s < 10; s++) {
-							const int rb = (s >> 1) - half, cbk = (s & 1) + 2 * half;
-							const bool active = rb >= 0 && rb <= 3;
-							const int blk = (rb * 4 + cbk) & 15;
-							const int mode = __shfl_sync(0xffffffffu, bmode, blk);
-							uint8_t* base = ws.rt_y + (rb * 4 + 1) * 24 + 4 + cbk * 4;
-							int e = 0, tap = 0, rs = 0;
+							const int blk0 = (s >> 1) * 4 + (s & 1);                   // half 0's sub-block; half 1 has blk0 - 2
+							const int tile_c = ((s >> 1) * 4 + 1) * 24 + 4 + (s & 1) * 4; // pixel (0,0) of half 0's sub-block
+							const bool active = (s < 2) ? (half == 0) : (s >= 8 ? (half == 1) : true);
+							const int mode = __shfl_sync(0xffffffffu, bmode, blk0 + bp_blk);
+							uint32_t t = 0;
+							int e = 0, rs = 0;
 							if (active) {
-								e = base[e_off];
-								tap = taps[min(mode, 9) * 16 + px_i];
-								rs = ws.res[blk][px_i];
+								t = bp_tab[mode * 16];
+								e = bp_edge[tile_c];
+								rs = bp_res[blk0 * 16];
 							}
-							const int ti = tap & 15;
-							const bool tm = (mode == 1);
-							const int i0 = tm ? 5 - px_r : ti, i1 = tm ? 7 + px_c : ti + 1, i2 = tm ? 6 : ((ti + 2) & 15);
-							const int a = __shfl_sync(0xffffffffu, e, (lane & 16) | i0);
-							const int b = __shfl_sync(0xffffffffu, e, (lane & 16) | i1);
-							const int c = __shfl_sync(0xffffffffu, e, (lane & 16) | i2);
-							int v = (tap & 16) ? (a + b + 1) >> 1 : (a + 2 * b + c + 2) >> 2;
-							if (tm) v = clip255(a + b - c);
-							if (__any_sync(0xffffffffu, active && mode == 0)) {
-								int sum = dc_tap ? e : 0;
-								sum += __shfl_xor_sync(0xffffffffu, sum, 8);
-								sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-								sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-								sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-								if (mode == 0) v = (sum + 4) >> 3;
+							const int a = __shfl_sync(0xffffffffu, e, t);
+							const int b = __shfl_sync(0xffffffffu, e, t >> 8);
+							const int c = __shfl_sync(0xffffffffu, e, t >> 16);
+							int v = (a + c + 2 + 2 * b) >> 2;
+							const uint32_t here = (s < 2 ? 0u : (1u << (blk0 - 2))) | (s >= 8 ? 0u : (1u << blk0));
+							if (special & here) {
+								const uint32_t kind = t >> 24;
+								if (kind == 1) v = clip255(a + b - c);
+								// B_DC: (sum of A0..A3 and L0..L3 + 4) >> 3, one warp-wide reduction per half
+								const int mine = dc_tap ? e : 0;
+								const int s_lo = __reduce_add_sync(0xffffffffu, half == 0 ? mine : 0);
+								const int s_hi = __reduce_add_sync(0xffffffffu, half == 1 ? mine : 0);
+								if (kind == 2) v = ((half ? s_hi : s_lo) + 4) >> 3;
+								if (kind == 3) v = 128;
 							}
-							if (mode > 9) v = 128;
-							if (active) base[px_r * 24 + px_c] = (uint8_t)clip255(v + rs);
+							if (active) bp_out[tile_c] = (uint8_t)add_clip255(v, rs);
 							__syncwarp();
 						}
 					}
@@ -571,23 +627,31 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 
 				if (!FILTER) {
 					// ================================================================== unfiltered output (-yuv)
-#pragma unroll
-					for (int k = 0; k < 2; k++) {
-						const int i = lane + 32 * k, row = i >> 2, wc = i & 3;
-						put_word(oy, 16 * x + 4 * wc, 16 * y + row, ld32(ws.rt_y + (row + 1) * 24 + 4 + 4 * wc));
-					}
-					{
-						const int j = lane & 15, row = j >> 1, wc = j & 1;
-						put_word(lane < 16 ? ou : ov, 8 * x + 4 * wc, 8 * y + row,
-						         ld32((lane < 16 ? ws.rt_u : ws.rt_v) + (row + 1) * 12 + 4 + 4 * wc));
+					const int row0 = lane >> 2, wc = lane & 3;
+					const int j = lane & 15, crow = j >> 1, cwc = j & 1;
+					const uint32_t w0 = ld32(ws.rt_y + (row0 + 1) * 24 + 4 + 4 * wc), w1 = ld32(ws.rt_y + (row0 + 9) * 24 + 4 + 4 * wc);
+					const uint32_t wcx = ld32((lane < 16 ? ws.rt_u : ws.rt_v) + (crow + 1) * 12 + 4 + 4 * cwc);
+					if (words_ok && !last_col && !last_row) {
+						uint8_t* d = oy.p + (size_t)(16 * y + row0) * oy.stride + 16 * x + 4 * wc;
+						st32(d, w0);
+						st32(d + (size_t)8 * oy.stride, w1);
+						st32((lane < 16 ? ou.p : ov.p) + (size_t)(8 * y + crow) * ou.stride + 8 * x + 4 * cwc, wcx);
+					} else {
+						put_word(oy, 16 * x + 4 * wc, 16 * y + row0, w0);
+						put_word(oy, 16 * x + 4 * wc, 16 * y + row0 + 8, w1);
+						put_word(lane < 16 ? ou : ov, 8 * x + 4 * cwc, 8 * y + crow, wcx);
 					}
 				} else {
 					// ================================================================== m07: loop filter
-					// ---- assemble the filter tile: left apron = previous tile's right 4 columns, top apron = tf lines
-					uint32_t la = 0, ta = 0, in0, in1, inc;
+					// ---- assemble the filter tile: left apron = previous tile's right 4 columns (all 20 / 12 rows, so the
+					//      corner above-left travels along), top apron = tf lines, interior = the fresh reconstruction
+					uint32_t la, la2 = 0, ta = 0, in0, in1, inc;
 					if (lane < 16) la = ld32(ws.ft_y + (lane + 4) * 20 + 16);
 					else if (lane < 24) la = ld32(ws.ft_u + (lane - 16 + 4) * 12 + 8);
 					else la = ld32(ws.ft_v + (lane - 24 + 4) * 12 + 8);
+					if (lane < 4) la2 = ld32(ws.ft_y + lane * 20 + 16);
+					else if (lane < 8) la2 = ld32(ws.ft_u + (lane - 4) * 12 + 8);
+					else if (lane < 12) la2 = ld32(ws.ft_v + (lane - 8) * 12 + 8);
 					if (y > 0) {
 						if (lane < 16) ta = ld32(tf_y + (lane >> 2) * line_px + 16 * x + 4 * (lane & 3));
 						else {
@@ -605,6 +669,9 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 					if (lane < 16) st32(ws.ft_y + (lane + 4) * 20, la);
 					else if (lane < 24) st32(ws.ft_u + (lane - 16 + 4) * 12, la);
 					else st32(ws.ft_v + (lane - 24 + 4) * 12, la);
+					if (lane < 4) st32(ws.ft_y + lane * 20, la2);
+					else if (lane < 8) st32(ws.ft_u + (lane - 4) * 12, la2);
+					else if (lane < 12) st32(ws.ft_v + (lane - 8) * 12, la2);
 					if (lane < 16) st32(ws.ft_y + (lane >> 2) * 20 + 4 + 4 * (lane & 3), ta);
 					else {
 						const int j = lane & 7;
@@ -631,8 +698,10 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 						else if (lane < 24) { t = ws.ft_u + 4 * 12 + 4; stride = 12; n = lane - 16; }
 						else { t = ws.ft_v + 4 * 12 + 4; stride = 12; n = lane - 24; }
 						if (!lf_simple) {
-							if (x > 0) lf_across_columns<EDGE_MB>(t + n * stride, lim_mb, interior, hev_thr);
-							__syncwarp();
+							if (x > 0) {
+								lf_across_columns<EDGE_MB>(t + n * stride, lim_mb, interior, hev_thr);
+								__syncwarp();
+							}
 							if (inner) {
 								lf_across_columns<EDGE_INNER>(t + n * stride + 4, lim_in, interior, hev_thr);
 								__syncwarp();
@@ -641,8 +710,10 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 								if (lane < 16) lf_across_columns<EDGE_INNER>(t + n * stride + 12, lim_in, interior, hev_thr);
 								__syncwarp();
 							}
-							if (y > 0) lf_across_rows<EDGE_MB>(t + n, stride, lim_mb, interior, hev_thr);
-							__syncwarp();
+							if (y > 0) {
+								lf_across_rows<EDGE_MB>(t + n, stride, lim_mb, interior, hev_thr);
+								__syncwarp();
+							}
 							if (inner) {
 								lf_across_rows<EDGE_INNER>(t + 4 * stride + n, stride, lim_in, interior, hev_thr);
 								__syncwarp();
@@ -673,47 +744,57 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 						__syncwarp();
 					}
 
-					// ---- store what can no longer change
-					const int wc_lo = (x > 0) ? -1 : 0;
-					{ // luma body: rows 0..11 (0..15 on the last MB row), word columns wc_lo..2 (..3 on the last MB column)
-						const int wc_hi = last_col ? 4 : 3, r_hi = last_row ? 16 : 12;
-						for (int i = lane; i < 16 * 5; i += 32) {
-							const int row = i / 5, wc = i % 5 - 1;
-							if (row < r_hi && wc >= wc_lo && wc < wc_hi)
-								put_word(oy, 16 * x + 4 * wc, 16 * y + row, ld32(ws.ft_y + (row + 4) * 20 + 4 + 4 * wc));
+					// ---- store what can no longer change: the 16x16 (8x8) block whose origin is 4 pixels up and left of the
+					//      macroblock; the last column / row of macroblocks also flush the strips nobody else will
+					{
+						const int row0 = lane >> 2, wc = lane & 3;                      // luma: rows row0, row0+8; word wc
+						const int j = lane & 15, crow = j >> 1, cwc = j & 1;            // chroma: plane lane>>4
+						const uint32_t w0 = ld32(ws.ft_y + row0 * 20 + 4 * wc), w1 = ld32(ws.ft_y + (row0 + 8) * 20 + 4 * wc);
+						const uint32_t wcx = ld32((lane < 16 ? ws.ft_u : ws.ft_v) + crow * 12 + 4 * cwc);
+						if (words_ok && x > 0 && y > 0 && !last_col && !last_row) {
+							// whole block inside the frame: only the last column / row of macroblocks can be cropped
+							uint8_t* d = oy.p + (size_t)(16 * y - 4 + row0) * oy.stride + (16 * x - 4 + 4 * wc);
+							st32(d, w0);
+							st32(d + (size_t)8 * oy.stride, w1);
+							st32((lane < 16 ? ou.p : ov.p) + (size_t)(8 * y - 4 + crow) * ou.stride + (8 * x - 4 + 4 * cwc), wcx);
+						} else {
+							put_word(oy, 16 * x - 4 + 4 * wc, 16 * y - 4 + row0, w0);
+							put_word(oy, 16 * x - 4 + 4 * wc, 16 * y + 4 + row0, w1);
+							put_word(lane < 16 ? ou : ov, 8 * x - 4 + 4 * cwc, 8 * y - 4 + crow, wcx);
+						}
+						if (last_col) { // right strip: columns 12..15 (4..7), rows -4..11 (-4..3)
+							if (lane < 16) put_word(oy, 16 * x + 12, 16 * y - 4 + lane, ld32(ws.ft_y + lane * 20 + 16));
+							else {
+								const int k = lane & 7;
+								put_word(lane < 24 ? ou : ov, 8 * x + 4, 8 * y - 4 + k, ld32((lane < 24 ? ws.ft_u : ws.ft_v) + k * 12 + 8));
+							}
+						}
+						if (last_row) { // bottom strip: rows 12..15 (4..7), columns -4..15 (-4..7)
+							if (lane < 20) {
+								const int rr = lane / 5, ww = lane % 5;
+								if (ww < 4 || last_col) put_word(oy, 16 * x - 4 + 4 * ww, 16 * y + 12 + rr, ld32(ws.ft_y + (16 + rr) * 20 + 4 * ww));
+							}
+							if (lane < 24) {
+								const int pl = lane / 12, k = lane % 12, rr = k / 3, ww = k % 3;
+								if (ww < 2 || last_col)
+									put_word(pl ? ov : ou, 8 * x - 4 + 4 * ww, 8 * y + 4 + rr, ld32((pl ? ws.ft_v : ws.ft_u) + (8 + rr) * 12 + 4 * ww));
+							}
 						}
 					}
-					{ // chroma body: rows 0..3 (0..7), word columns wc_lo..0 (..1)
-						const int wc_hi = last_col ? 2 : 1, r_hi = last_row ? 8 : 4;
-						for (int i = lane; i < 2 * 8 * 3; i += 32) {
-							const int pl = i / 24, j = i % 24, row = j / 3, wc = j % 3 - 1;
-							if (row < r_hi && wc >= wc_lo && wc < wc_hi)
-								put_word(pl ? ov : ou, 8 * x + 4 * wc, 8 * y + row,
-								         ld32((pl ? ws.ft_v : ws.ft_u) + (row + 4) * 12 + 4 + 4 * wc));
+					if (!last_row) { // hand the bottom 4 filtered rows to the row below: columns -4..11 (+12..15 on the last column)
+						if (lane < 16) {
+							if (x > 0 || (lane & 3)) st32(tf_y + (lane >> 2) * line_px + 16 * x - 4 + 4 * (lane & 3), ld32(ws.ft_y + ((lane >> 2) + 16) * 20 + 4 * (lane & 3)));
+						} else {
+							const int k = lane & 7; // 4 rows x 2 words per plane
+							if (x > 0 || (k & 1))
+								st32((lane < 24 ? tf_u : tf_v) + (k >> 1) * line_c + 8 * x - 4 + 4 * (k & 1), ld32((lane < 24 ? ws.ft_u : ws.ft_v) + ((k >> 1) + 8) * 12 + 4 * (k & 1)));
 						}
-					}
-					if (y > 0) { // bottom 4 rows of the macroblock above are final now
-						if (lane < 16)
-							put_word(oy, 16 * x + 4 * (lane & 3), 16 * y - 4 + (lane >> 2), ld32(ws.ft_y + (lane >> 2) * 20 + 4 + 4 * (lane & 3)));
-						else {
-							const int j = lane & 7;
-							put_word(lane < 24 ? ou : ov, 8 * x + 4 * (j & 1), 8 * y - 4 + (j >> 1),
-							         ld32((lane < 24 ? ws.ft_u : ws.ft_v) + (j >> 1) * 12 + 4 + 4 * (j & 1)));
-						}
-					}
-					if (!last_row) { // hand the bottom 4 filtered rows to the row below
-						const int wc_hi = last_col ? 4 : 3;
-						if (lane < 20) {
-							const int row = lane / 5, wc = lane % 5 - 1;
-							if (wc >= wc_lo && wc < wc_hi)
-								st32(tf_y + row * line_px + 16 * x + 4 * wc, ld32(ws.ft_y + (row + 16) * 20 + 4 + 4 * wc));
-						}
-						const int cwc_hi = last_col ? 2 : 1;
-						if (lane < 24) {
-							const int pl = lane / 12, j = lane % 12, row = j / 3, wc = j % 3 - 1;
-							if (wc >= wc_lo && wc < cwc_hi)
-								st32((pl ? tf_v : tf_u) + row * line_c + 8 * x + 4 * wc,
-								     ld32((pl ? ws.ft_v : ws.ft_u) + (row + 8) * 12 + 4 + 4 * wc));
+						if (last_col) {
+							if (lane < 4) st32(tf_y + lane * line_px + 16 * x + 12, ld32(ws.ft_y + (lane + 16) * 20 + 16));
+							else if (lane < 12) {
+								const int k = lane - 4;
+								st32(((k >> 2) ? tf_v : tf_u) + (k & 3) * line_c + 8 * x + 4, ld32(((k >> 2) ? ws.ft_v : ws.ft_u) + ((k & 3) + 8) * 12 + 8));
+							}
 						}
 					}
 				}
@@ -739,8 +820,6 @@ __global__ void __launch_bounds__(NW * 32) vp8_mb_wavefront(const Vp8ImgDesc* __
 					__threadfence_block();
 					prog[y & (kProgRing - 1)] = (y + 1) * kStampRow + x + 1;
 				}
-				c0 = n0;
-				c1 = n1;
 			}
 		}
 	}
