@@ -55,10 +55,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise Vp8GpuError(_errno.ENOENT, f"{LIB_PATH} is missing: run `python __graft_entry__.py build` "
+    path = Path(os.environ.get("VP8_GPU_LIB", LIB_PATH))  # VP8_GPU_LIB: development override (kernel A/B builds)
+    if not path.exists():
+        raise Vp8GpuError(_errno.ENOENT, f"{path} is missing: run `python __graft_entry__.py build` "
                                          "(the CUDA library is the only implementation; there is no CPU fallback)")
-    L = C.CDLL(str(LIB_PATH), use_errno=True)
+    L = C.CDLL(str(path), use_errno=True)
     vp, sz, pp = C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)
     L.vp8_gpu_init.argtypes = [C.c_int, vp, pp]
     L.vp8_gpu_destroy.argtypes = [vp]

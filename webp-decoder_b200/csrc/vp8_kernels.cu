@@ -30,6 +30,13 @@
 
 #include "vp8_dev.h"
 
+#ifndef VP8_LF_GENERIC
+#define VP8_LF_GENERIC 0 // 1: one byte-addressed filter body looped over the 8 edges (smaller code, more instructions)
+#endif
+#ifndef VP8_BPRED_LOOP
+#define VP8_BPRED_LOOP 0 // 1: B_PRED steps as a 5 x 2 loop instead of 10 unrolled steps
+#endif
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------ constants
@@ -180,6 +187,52 @@ __device__ __forceinline__ void iwht4x4(const int (&v)[16], int (&r)[16]) {
 // ------------------------------------------------------------------------------------------------ loop filter
 enum { EDGE_MB = 0, EDGE_INNER = 1, EDGE_SIMPLE = 2 };
 
+#if VP8_LF_GENERIC
+// One position across an edge: q points at q0, `step` is the byte distance between the pixels p3..q3 (1 across a
+// vertical edge, the tile stride across a horizontal one). A single body serves every edge of every plane so that
+// the kernel stays inside the instruction cache; `kind` is warp-uniform.
+// Thresholds: reference vp8_loopfilter.c:24-56; kernels :58-104; dispatch :106-164.
+__device__ __forceinline__ void lf_line(uint8_t* q, int step, int kind, int lim, int interior, int hev_thr) {
+	int p1 = q[-2 * step], p0 = q[-step], q0 = q[0], q1 = q[step];
+	if (2 * absdiff(p0, q0) + (absdiff(p1, q1) >> 1) > lim) return;
+	int p2 = 0, q2 = 0;
+	bool hev = false;
+	if (kind != EDGE_SIMPLE) {
+		const int p3 = q[-4 * step], q3 = q[3 * step];
+		p2 = q[-3 * step];
+		q2 = q[2 * step];
+		const int dp = absdiff(p1, p0), dq = absdiff(q1, q0);
+		int m = __vimax3_s32(absdiff(p3, p2), absdiff(p2, p1), dp);
+		m = __vimax3_s32(m, absdiff(q3, q2), absdiff(q2, q1));
+		if (max(m, dq) > interior) return;
+		hev = max(dp, dq) > hev_thr;
+		if (kind == EDGE_MB && !hev) {
+			const int w = sclamp(sclamp(p1 - q1) + 3 * (q0 - p0));
+			const int a = (27 * w + 63) >> 7, b = (18 * w + 63) >> 7, c = (9 * w + 63) >> 7;
+			q[-step] = (uint8_t)add_clip255(p0, a);
+			q[0] = (uint8_t)add_clip255(q0, -a);
+			q[-2 * step] = (uint8_t)add_clip255(p1, b);
+			q[step] = (uint8_t)add_clip255(q1, -b);
+			q[-3 * step] = (uint8_t)add_clip255(p2, c);
+			q[2 * step] = (uint8_t)add_clip255(q2, -c);
+			return;
+		}
+	}
+	const bool outer = (kind != EDGE_INNER) || hev;
+	int a = 3 * (q0 - p0);
+	if (outer) a += sclamp(p1 - q1);
+	a = sclamp(a);
+	const int f1 = min(a + 4, 127) >> 3, f2 = min(a + 3, 127) >> 3; // a >= -128 already
+	q[0] = (uint8_t)add_clip255(q0, -f1);
+	q[-step] = (uint8_t)add_clip255(p0, f2);
+	if (!outer) {
+		const int h = (f1 + 1) >> 1;
+		q[step] = (uint8_t)add_clip255(q1, -h);
+		q[-2 * step] = (uint8_t)add_clip255(p1, h);
+	}
+}
+
+#else
 // One position across an edge, in registers. Returns true when pixels changed.
 // Thresholds: reference vp8_loopfilter.c:24-56; kernels :58-104; dispatch :106-164.
 template <int KIND>
@@ -252,6 +305,8 @@ __device__ __forceinline__ void lf_across_rows(uint8_t* q, int s, int lim, int i
 		}
 	}
 }
+
+#endif
 
 // ------------------------------------------------------------------------------------------------ the kernel
 #ifndef VP8_MIN_CTAS
@@ -360,8 +415,8 @@ __global__ void __launch_bounds__(NW * 32, VP8_MIN_CTAS(NW)) vp8_mb_wavefront(co
 				if (is_luma_lane) cptr = sd->coeff_y + (mb_row0 * 16 + lane) * 16;
 				else if (lane < 20) cptr = sd->coeff_u + (mb_row0 * 4 + cb) * 16;
 				else if (lane < 24) cptr = sd->coeff_v + (mb_row0 * 4 + cb) * 16;
-				else if (lane == 24) cptr = sd->coeff_y2 + mb_row0 * 16;
-				if (cptr) {
+				else cptr = sd->coeff_y2 + mb_row0 * 16; // lane 24; lanes 25..31 carry it along unused
+				if (lane < 25) {
 					cp_async16(&ws.coef[lane], cptr);
 					cp_async16(&ws.coef[25 + lane], cptr + 8);
 				}
@@ -392,7 +447,7 @@ __global__ void __launch_bounds__(NW * 32, VP8_MIN_CTAS(NW)) vp8_mb_wavefront(co
 				if (y > 0) {
 					if (lane == 0) {
 						const int target = y * kStampRow + min(x + 2, cols);
-						while (prog[(y - 1) & (kProgRing - 1)] < target) __nanosleep(32);
+						while (prog[(y - 1) & (kProgRing - 1)] < target) __nanosleep(64);
 						__threadfence_block();
 					}
 					__syncwarp();
@@ -437,10 +492,10 @@ __global__ void __launch_bounds__(NW * 32, VP8_MIN_CTAS(NW)) vp8_mb_wavefront(co
 					}
 					__syncwarp();
 					if (!last_col) {
-						if (cptr) {
-							const int16_t* nx = cptr + (size_t)(x + 1) * cstep;
-							cp_async16(&ws.coef[lane], nx);
-							cp_async16(&ws.coef[25 + lane], nx + 8);
+						cptr += cstep; // loop-carried on purpose: keeps the stream pointer in registers
+						if (lane < 25) {
+							cp_async16(&ws.coef[lane], cptr);
+							cp_async16(&ws.coef[25 + lane], cptr + 8);
 						}
 						cp_async_commit();
 					}
@@ -563,6 +618,45 @@ __global__ void __launch_bounds__(NW * 32, VP8_MIN_CTAS(NW)) vp8_mb_wavefront(co
 					if (bpred) {
 						// which sub-blocks need the two non-tap predictors (bit = sub-block index)
 						const uint32_t special = __ballot_sync(0xffffffffu, lane < 16 && (bmode <= 1 || bmode == 10));
+#if VP8_BPRED_LOOP
+#pragma unroll 1
+						for (int s2 = 0; s2 < 5; s2++) {
+							// steps 2*s2 and 2*s2+1: half 0 works on sub-block row s2 (columns 0,1), half 1 on row s2-1 (columns 2,3)
+							const bool active = half == 0 ? s2 < 4 : s2 > 0;
+							// bit k set: step k of this pair has a sub-block that needs B_DC / B_TM / out-of-range handling
+							const uint32_t sp2 = (s2 < 4 ? (special >> (4 * s2)) & 3u : 0u) | (s2 > 0 ? (special >> (4 * s2 - 2)) & 3u : 0u);
+#pragma unroll
+							for (int k = 0; k < 2; k++) {
+								const int blk0 = 4 * s2 + k;                                  // half 0's sub-block; half 1 has blk0 - 2
+								const int tile_c = (4 * s2 + 1) * 24 + 4 + 4 * k;            // pixel (0,0) of half 0's sub-block
+								const int mode = __shfl_sync(0xffffffffu, bmode, blk0 + bp_blk);
+								uint32_t t = 0;
+								int e = 0, rs = 0;
+								if (active) {
+									t = bp_tab[mode * 16];
+									e = bp_edge[tile_c];
+									rs = bp_res[blk0 * 16];
+								}
+								const int a = __shfl_sync(0xffffffffu, e, t);
+								const int b = __shfl_sync(0xffffffffu, e, t >> 8);
+								const int c = __shfl_sync(0xffffffffu, e, t >> 16);
+								int v = (a + c + 2 + 2 * b) >> 2;
+								if (sp2 & (1u << k)) {
+									const uint32_t kind = t >> 24;
+									if (kind == 1) v = clip255(a + b - c);
+									// B_DC: (sum of A0..A3 and L0..L3 + 4) >> 3, one warp-wide reduction per half
+									const int mine = dc_tap ? e : 0;
+									const int s_lo = __reduce_add_sync(0xffffffffu, half == 0 ? mine : 0);
+									const int s_hi = __reduce_add_sync(0xffffffffu, half == 1 ? mine : 0);
+									if (kind == 2) v = ((half ? s_hi : s_lo) + 4) >> 3;
+									if (kind == 3) v = 128;
+								}
+								if (active) bp_out[tile_c] = (uint8_t)add_clip255(v, rs);
+								__syncwarp();
+							}
+						}
+					}
+#else
 #pragma unroll
 						for (int s = 0; s < 10; s++) {
 							const int blk0 = (s >> 1) * 4 + (s & 1);                   // half 0's sub-block; half 1 has blk0 - 2
@@ -595,6 +689,7 @@ __global__ void __launch_bounds__(NW * 32, VP8_MIN_CTAS(NW)) vp8_mb_wavefront(co
 							__syncwarp();
 						}
 					}
+#endif
 				} else {
 					// ================================================================== stand-alone m07: load the MB
 					const uint8_t* sy = sd->src_y + (size_t)(16 * y) * sd->src_stride_y + 16 * x;
@@ -697,6 +792,25 @@ __global__ void __launch_bounds__(NW * 32, VP8_MIN_CTAS(NW)) vp8_mb_wavefront(co
 						if (lane < 16) { t = ws.ft_y + 4 * 20 + 4; stride = 20; n = lane; }
 						else if (lane < 24) { t = ws.ft_u + 4 * 12 + 4; stride = 12; n = lane - 16; }
 						else { t = ws.ft_v + 4 * 12 + 4; stride = 12; n = lane - 24; }
+#if VP8_LF_GENERIC
+						// pass p: p < 4 edges between columns at 4*(p&3), p >= 4 edges between rows. Edge 0 is the macroblock edge
+						// (needs the neighbour), edges 4/8/12 are inner edges (luma has three, chroma only the one at 4; the
+						// simple filter touches luma only).
+#pragma unroll 1
+						for (int p = 0; p < 8; p++) {
+							const int e = (p & 3) * 4;
+							const bool rows_dir = p >= 4;
+							if (e == 0 ? (rows_dir ? y == 0 : x == 0) : !inner) continue;
+							if (lane < 16 || (e <= 4 && !lf_simple)) {
+								uint8_t* q = rows_dir ? t + e * stride + n : t + n * stride + e;
+								lf_line(q, rows_dir ? stride : 1, lf_simple ? EDGE_SIMPLE : (e == 0 ? EDGE_MB : EDGE_INNER),
+								        e == 0 ? lim_mb : lim_in, interior, hev_thr);
+							}
+							__syncwarp();
+						}
+					}
+
+#else
 						if (!lf_simple) {
 							if (x > 0) {
 								lf_across_columns<EDGE_MB>(t + n * stride, lim_mb, interior, hev_thr);
@@ -744,6 +858,7 @@ __global__ void __launch_bounds__(NW * 32, VP8_MIN_CTAS(NW)) vp8_mb_wavefront(co
 						__syncwarp();
 					}
 
+#endif
 					// ---- store what can no longer change: the 16x16 (8x8) block whose origin is 4 pixels up and left of the
 					//      macroblock; the last column / row of macroblocks also flush the strips nobody else will
 					{
