@@ -223,19 +223,11 @@ def gpu_arm(args):
     # ---- (2) end to end through the batch API: pinned host inputs -> H2D -> kernels -> D2H into pinned host memory
     e2e = None
     if not args.no_e2e:
-        probe = ctx.upload(kfs, frs)
-        out_bytes = W.load_library().vp8_gpu_ppm_bytes(probe._h) if args.workload == "ppm" else W.load_library().vp8_gpu_i420_bytes(probe._h)
-        probe.free()
-        host_out = W.PinnedBuffer(int(out_bytes))
+        host_out = W.PinnedBuffer(ctx.decode_bytes(kfs, ppm=(args.workload == "ppm")))
 
         def step_e2e():
-            b = ctx.upload(kfs, frs)
-            step_resident(b)
-            if args.workload == "ppm":
-                ctx.download_ppm(b, host_out.array)
-            else:
-                ctx.download_i420(b, host_out.array)
-            b.free()
+            # one public call: chunked upload -> kernels -> download, overlapped on the library's internal streams
+            ctx.decode_into(kfs, frs, host_out.array, filtered=filtered, ppm=(args.workload == "ppm"), chunk=args.chunk)
 
         for _ in range(max(1, min(args.warmup, 2))):
             step_e2e()
@@ -256,6 +248,7 @@ def gpu_arm(args):
         e2e = {"value": world * px_step * n_e2e / (float(t2.item()) / 1e3) / 1e6, "unit": "Mpixel/s",
                "h2d_bytes_per_step": (ctx.h2d_bytes - h0) // n_e2e, "d2h_bytes_per_step": (ctx.d2h_bytes - d0) // n_e2e,
                "steps": n_e2e, "ms_per_step": float(t2.item()) / n_e2e,
+               "api": "vp8_gpu_decode_i420" if args.workload != "ppm" else "vp8_gpu_decode_ppm",
                "note": "host side = already-parsed frames in pinned memory; token decode (m03/m05) not included"}
         host_out.close()
 
@@ -302,6 +295,7 @@ def main():
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--images-per-sm", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--chunk", type=int, default=0, help="frames per pipeline chunk of the end-to-end call (0 = library default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

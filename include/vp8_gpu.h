@@ -103,6 +103,16 @@ int vp8_gpu_download_images(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, Yuv420Image* out
 /* Macroblock-aligned planes of frame i (VP8_GPU_PADDED batches), for inspection. */
 int vp8_gpu_download_padded(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, int i, uint8_t* y, uint8_t* u, uint8_t* v);
 
+/* Whole path in one call, pipelined: the batch is cut into chunks of `chunk` frames (0 = default 128) whose
+ * host->device copies, kernels and device->host copies overlap on internal streams. dst (ideally pinned, as the
+ * frames' arrays) receives frame i at offsets[i]: the -yuv (filtered=0) / -yuvf bytes, resp. the -ppm bytes.
+ * vp8_gpu_decode_bytes gives the capacity needed. Blocking. */
+int vp8_gpu_decode_i420(vp8_gpu_ctx* ctx, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,
+                        int filtered, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk);
+int vp8_gpu_decode_ppm(vp8_gpu_ctx* ctx, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,
+                       uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk);
+size_t vp8_gpu_decode_bytes(const Vp8KeyFrameHeader* const* kf, int n, int ppm);
+
 /* Introspection for the benchmark. */
 int vp8_gpu_batch_size(const vp8_gpu_batch* b);
 uint64_t vp8_gpu_launch_count(const vp8_gpu_ctx* ctx); /* kernels launched by this context so far */

@@ -195,6 +195,24 @@ def test_bench_inputs_full_size_parity_and_replication(lib, gpu_ctx):
     pf.free()
 
 
+def test_pipelined_decode_matches_digests(lib, gpu_ctx, golden, parsed_golden):
+    """vp8_gpu_decode_i420 / _ppm: chunks overlapped on internal streams; many small chunks, pinned and pageable output."""
+    names = sorted(golden)
+    kfs = [parsed_golden[n][0] for n in names]
+    frs = [parsed_golden[n][1] for n in names]
+    for ppm, key, filtered in ((False, "yuvf", True), (False, "yuv", False), (True, "ppm", True)):
+        need = gpu_ctx.decode_bytes(kfs, ppm=ppm)
+        pinned = lib.PinnedBuffer(need)
+        for out in (pinned.array, np.empty(need, np.uint8)):
+            out[:] = 0xAA
+            offs, sizes = gpu_ctx.decode_into(kfs, frs, out, filtered=filtered, ppm=ppm, chunk=7)
+            bad = [n for n, o, s in zip(names, offs, sizes) if sha(out[int(o):int(o) + int(s)]) != golden[n][key]]
+            assert not bad, (key, len(bad), bad[:4])
+        pinned.close()
+    with pytest.raises(OSError):
+        gpu_ctx.decode_into(kfs, frs, np.empty(10, np.uint8))
+
+
 def test_argument_errors(lib, gpu_ctx):
     f = fuzz_frame(5, 64, 64)
     kf, d = f.header(), f.cstruct()

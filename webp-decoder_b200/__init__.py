@@ -41,6 +41,7 @@ EXPORTS = [
     "vp8_gpu_download_i420", "vp8_gpu_download_ppm", "vp8_gpu_download_images", "vp8_gpu_download_padded",
     "vp8_gpu_batch_size", "vp8_gpu_launch_count", "vp8_gpu_h2d_bytes", "vp8_gpu_d2h_bytes",
     "vp8_gpu_last_launch_config", "vp8_gpu_frame_params", "vp8_gpu_kernel_time",
+    "vp8_gpu_decode_i420", "vp8_gpu_decode_ppm", "vp8_gpu_decode_bytes",
 ]
 
 _lib = None
@@ -94,6 +95,10 @@ def load_library() -> C.CDLL:
     L.vp8_gpu_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.vp8_gpu_frame_params.argtypes = [vp, vp, vp]
     L.vp8_gpu_frame_params.restype = None
+    L.vp8_gpu_decode_i420.argtypes = [vp, pp, pp, C.c_int, C.c_int, vp, sz, vp, vp, C.c_int]
+    L.vp8_gpu_decode_ppm.argtypes = [vp, pp, pp, C.c_int, vp, sz, vp, vp, C.c_int]
+    L.vp8_gpu_decode_bytes.argtypes = [pp, C.c_int, C.c_int]
+    L.vp8_gpu_decode_bytes.restype = sz
     L.yuv420_alloc.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.yuv420_free.argtypes = [vp]
     L.yuv420_free.restype = None
@@ -260,6 +265,26 @@ class Context:
         _check(self._L.vp8_gpu_download_padded(self._h, batch._h, i, y.ctypes.data, u.ctypes.data, v.ctypes.data),
                "vp8_gpu_download_padded")
         return y, u, v
+
+    # ---- whole path, pipelined ---------------------------------------------------------------------------
+    def decode_bytes(self, kfs, ppm: bool = False) -> int:
+        n = len(kfs)
+        kp = (C.c_void_p * n)(*[_addr(k) for k in kfs])
+        return int(self._L.vp8_gpu_decode_bytes(kp, n, int(ppm)))
+
+    def decode_into(self, kfs, frames, out: np.ndarray, filtered: bool = True, ppm: bool = False, chunk: int = 0):
+        """vp8_gpu_decode_i420 / vp8_gpu_decode_ppm: upload, kernels and download overlapped chunk by chunk.
+        `out` is a uint8 buffer (ideally a PinnedBuffer's array); returns (offsets, sizes)."""
+        n, kp, fp = self._ptr_arrays(kfs, frames)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous
+        offs, sizes = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        if ppm:
+            rc = self._L.vp8_gpu_decode_ppm(self._h, kp, fp, n, out.ctypes.data, out.nbytes, offs.ctypes.data, sizes.ctypes.data, chunk)
+        else:
+            rc = self._L.vp8_gpu_decode_i420(self._h, kp, fp, n, int(bool(filtered)), out.ctypes.data, out.nbytes,
+                                             offs.ctypes.data, sizes.ctypes.data, chunk)
+        _check(rc, "vp8_gpu_decode")
+        return offs, sizes
 
     # ---- convenience -------------------------------------------------------------------------------------
     def decode_i420(self, kfs, frames, filtered: bool = True):

@@ -76,6 +76,8 @@ struct vp8_gpu_ctx {
 	// device-side duration of every wavefront launch since the last vp8_gpu_kernel_time() query
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed; // recorded, not yet read
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spare;
+	cudaStream_t pipe[3] = {nullptr, nullptr, nullptr}; // chunk pipeline of vp8_gpu_decode_*
+	cudaEvent_t pipe_ev = nullptr;
 };
 
 namespace {
@@ -83,6 +85,8 @@ namespace {
 struct FrameMeta {
 	uint32_t width, height, mb_cols, mb_rows;
 	size_t in_off[9];   // coeff_y, coeff_u, coeff_v, coeff_y2, bmode, ymode, uv_mode, segment_id, has_coeff
+	const uint8_t* span_src = nullptr; // non-null: the arrays sit in one host block, copied with a single transfer
+	size_t span_off = 0, span_bytes = 0;
 	bool has_seg, has_hc;
 	size_t tight_off;   // tight I420 (Y|U|V) within d_tight
 	size_t pad_off[3];  // padded planes within d_pad
@@ -114,6 +118,7 @@ struct vp8_gpu_batch {
 	PlaneState state = PLANES_NONE;
 	bool filtered = false, have_rgb = false, have_coeffs = true;
 	int desc_key = -1; // kernel_mode*2 + layout of the descriptors currently on the device
+	cudaStream_t stream = nullptr; // all work on this batch is issued here (the context's stream unless pipelined)
 };
 
 namespace {
@@ -171,14 +176,15 @@ int ensure_bounce(vp8_gpu_ctx* c) {
 // pinned bounce buffers so the memcpy of chunk k+1 overlaps the DMA of chunk k.
 struct Uploader {
 	vp8_gpu_ctx* c;
+	cudaStream_t st;
 	int cur = 0;
 	size_t fill = 0;          // bytes staged in bounce[cur]
 	uint8_t* dev_at = nullptr; // device address matching bounce[cur][0]
 
 	int flush() {
 		if (fill) {
-			CU(cudaMemcpyAsync(dev_at, c->bounce[cur], fill, cudaMemcpyHostToDevice, c->stream));
-			CU(cudaEventRecord(c->bounce_ev[cur], c->stream));
+			CU(cudaMemcpyAsync(dev_at, c->bounce[cur], fill, cudaMemcpyHostToDevice, st));
+			CU(cudaEventRecord(c->bounce_ev[cur], st));
 			c->bounce_busy[cur] = true;
 			cur ^= 1;
 			fill = 0;
@@ -197,7 +203,7 @@ struct Uploader {
 		if (!bytes) return 0;
 		c->h2d += bytes;
 		if (is_pinned(src)) {
-			CU(cudaMemcpyAsync(dev, src, bytes, cudaMemcpyHostToDevice, c->stream));
+			CU(cudaMemcpyAsync(dev, src, bytes, cudaMemcpyHostToDevice, st));
 			return 0;
 		}
 		if (ensure_bounce(c)) return -1;
@@ -225,12 +231,12 @@ struct Uploader {
 };
 
 // Device -> host for one contiguous range.
-int download(vp8_gpu_ctx* c, void* dst, const uint8_t* dev, size_t bytes) {
+int download(vp8_gpu_ctx* c, cudaStream_t st, void* dst, const uint8_t* dev, size_t bytes, bool wait = true) {
 	if (!bytes) return 0;
 	c->d2h += bytes;
 	if (is_pinned(dst)) {
-		CU(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
-		CU(cudaStreamSynchronize(c->stream));
+		CU(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, st));
+		if (wait) CU(cudaStreamSynchronize(st));
 		return 0;
 	}
 	if (ensure_bounce(c)) return -1;
@@ -252,8 +258,8 @@ int download(vp8_gpu_ctx* c, void* dst, const uint8_t* dev, size_t bytes) {
 		bool issued = false;
 		if (off < bytes) {
 			const size_t len = std::min(kBounceBytes, bytes - off);
-			CU(cudaMemcpyAsync(c->bounce[k], dev + off, len, cudaMemcpyDeviceToHost, c->stream));
-			CU(cudaEventRecord(c->bounce_ev[k], c->stream));
+			CU(cudaMemcpyAsync(c->bounce[k], dev + off, len, cudaMemcpyDeviceToHost, st));
+			CU(cudaEventRecord(c->bounce_ev[k], st));
 			pend_off[k] = off;
 			pend_len[k] = len;
 			off += len;
@@ -327,7 +333,7 @@ void frame_params(const Vp8DecodedFrame* f, int16_t dq[4][6], uint8_t lf[4][2][4
 void batch_destroy(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
 	if (!b) return;
 	// work queued on the stream may still reference these blocks
-	cudaStreamSynchronize(c->stream);
+	cudaStreamSynchronize(b->stream ? b->stream : c->stream);
 	dev_release(c, b->d_in, b->in_bytes);
 	dev_release(c, b->d_tight, b->tight_bytes);
 	dev_release(c, b->d_pad, b->pad_bytes);
@@ -352,7 +358,7 @@ int validate_frame(const Vp8KeyFrameHeader* kf, const Vp8DecodedFrame* f, bool n
 
 // Lay out and upload the per-frame arrays. With need_coeffs == false only what the loop filter reads is staged.
 int batch_create(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* fr, int n, bool need_coeffs,
-                 vp8_gpu_batch** out) {
+                 vp8_gpu_batch** out, cudaStream_t st = nullptr) {
 	if (!c || !kf || !fr || !out || n <= 0) return fail(EINVAL, "bad arguments");
 	for (int i = 0; i < n; i++)
 		if (validate_frame(kf[i], fr[i], need_coeffs)) return -1;
@@ -361,6 +367,7 @@ int batch_create(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8De
 	vp8_gpu_batch* b = new (std::nothrow) vp8_gpu_batch;
 	if (!b) return fail(ENOMEM, "batch");
 	b->n = n;
+	b->stream = st ? st : c->stream;
 	b->have_coeffs = need_coeffs;
 	b->meta.resize(n);
 	size_t in = 0, tight = 0, pad = 0, rgb = 0;
@@ -377,9 +384,32 @@ int batch_create(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8De
 		const size_t sz[9] = {need_coeffs ? mb * 512 : 0, need_coeffs ? mb * 128 : 0, need_coeffs ? mb * 128 : 0,
 		                      need_coeffs ? mb * 32 : 0,  need_coeffs ? mb * 16 : 0,  mb,
 		                      need_coeffs ? mb : 0,       m.has_seg ? mb : 0,         m.has_hc ? mb : 0};
+		const uint8_t* src[9] = {(const uint8_t*)f->coeff_y, (const uint8_t*)f->coeff_u, (const uint8_t*)f->coeff_v,
+		                         (const uint8_t*)f->coeff_y2, f->bmode, f->ymode, f->uv_mode, f->segment_id, f->has_coeff};
+		// Arrays carved from one host block (vp8_parse arenas do that) travel as ONE transfer and keep their relative
+		// placement on the device; scattered arrays (the reference's ten callocs) are laid out and copied one by one.
+		const uint8_t *lo = nullptr, *hi = nullptr;
+		size_t payload = 0;
+		bool aligned = true;
 		for (int k = 0; k < 9; k++) {
-			m.in_off[k] = in;
-			in += align_up(sz[k]);
+			if (!sz[k]) continue;
+			if (!lo || src[k] < lo) lo = src[k];
+			if (!hi || src[k] + sz[k] > hi) hi = src[k] + sz[k];
+			payload += sz[k];
+		}
+		for (int k = 0; k < 4; k++)
+			if (sz[k] && ((src[k] - lo) & 15)) aligned = false; // cp.async needs 16-byte aligned coefficient blocks
+		if (need_coeffs && aligned && (size_t)(hi - lo) <= payload + payload / 64 + 4096) {
+			m.span_src = lo;
+			m.span_off = in;
+			m.span_bytes = (size_t)(hi - lo);
+			for (int k = 0; k < 9; k++) m.in_off[k] = sz[k] ? in + (size_t)(src[k] - lo) : in;
+			in += align_up(m.span_bytes);
+		} else {
+			for (int k = 0; k < 9; k++) {
+				m.in_off[k] = in;
+				in += align_up(sz[k]);
+			}
 		}
 		const size_t cw = (m.width + 1) / 2, ch = (m.height + 1) / 2;
 		m.tight_off = tight;
@@ -409,11 +439,18 @@ int batch_create(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8De
 		batch_destroy(c, b);
 		return -1;
 	}
-	Uploader up{c};
+	Uploader up{c, b->stream};
 	for (int i = 0; i < n; i++) {
 		const FrameMeta& m = b->meta[i];
 		const Vp8DecodedFrame* f = fr[i];
 		const size_t mb = (size_t)m.mb_cols * m.mb_rows;
+		if (m.span_src) {
+			if (up.put(b->d_in + m.span_off, m.span_src, m.span_bytes)) {
+				batch_destroy(c, b);
+				return -1;
+			}
+			continue;
+		}
 		const void* src[9] = {f->coeff_y, f->coeff_u, f->coeff_v, f->coeff_y2, f->bmode, f->ymode, f->uv_mode, f->segment_id, f->has_coeff};
 		const size_t sz[9] = {need_coeffs ? mb * 512 : 0, need_coeffs ? mb * 128 : 0, need_coeffs ? mb * 128 : 0,
 		                      need_coeffs ? mb * 32 : 0,  need_coeffs ? mb * 16 : 0,  mb,
@@ -489,7 +526,7 @@ int push_descs(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layout) {
 		d.lf_simple = m.lf_simple;
 	}
 	// pageable source: the runtime stages it before returning, so the vector may die right after
-	CU(cudaMemcpyAsync(b->d_desc, h.data(), sizeof(Vp8ImgDesc) * b->n, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(b->d_desc, h.data(), sizeof(Vp8ImgDesc) * b->n, cudaMemcpyHostToDevice, b->stream));
 	b->desc_key = kernel_mode * 2 + layout;
 	return 0;
 }
@@ -523,9 +560,9 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 		CU(cudaEventCreate(&ev.first));
 		CU(cudaEventCreate(&ev.second));
 	}
-	CU(cudaEventRecord(ev.first, c->stream));
-	const int rc = vp8_launch_wavefront(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, c->stream);
-	CU(cudaEventRecord(ev.second, c->stream));
+	CU(cudaEventRecord(ev.first, b->stream));
+	const int rc = vp8_launch_wavefront(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, b->stream);
+	CU(cudaEventRecord(ev.second, b->stream));
 	c->timed.push_back(ev);
 	if (c->timed.size() > 4096) { // nobody is asking: recycle the oldest
 		c->spare.push_back(c->timed.front());
@@ -582,7 +619,7 @@ int rgb_of_host_image(vp8_gpu_ctx* c, const Yuv420Image* img, std::vector<uint8_
 		return -1;
 	}
 	int rc = 0;
-	Uploader up{c};
+	Uploader up{c, c->stream};
 	uint8_t* dy = d_in;
 	uint8_t* du = d_in + align_up(ysz);
 	uint8_t* dv = du + align_up(csz);
@@ -604,7 +641,7 @@ int rgb_of_host_image(vp8_gpu_ctx* c, const Yuv420Image* img, std::vector<uint8_
 	}
 	if (!rc) {
 		rgb.resize(rgb_bytes);
-		rc = download(c, rgb.data(), d_rgb, rgb_bytes);
+		rc = download(c, c->stream, rgb.data(), d_rgb, rgb_bytes);
 	}
 	cudaStreamSynchronize(c->stream);
 	dev_release(c, d_in, total);
@@ -776,6 +813,9 @@ void vp8_gpu_destroy(vp8_gpu_ctx* c) {
 			cudaEventDestroy(ev.first);
 			cudaEventDestroy(ev.second);
 		}
+	for (auto& p : c->pipe)
+		if (p) cudaStreamDestroy(p);
+	if (c->pipe_ev) cudaEventDestroy(c->pipe_ev);
 	if (c->own_stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -891,8 +931,8 @@ int vp8_gpu_rgb(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
 		const uint32_t groups = ((m.width + 3) / 4) * m.height;
 		max_blocks = std::max(max_blocks, (groups + 255) / 256);
 	}
-	CU(cudaMemcpyAsync(b->d_rgbdesc, h.data(), sizeof(Vp8RgbDesc) * b->n, cudaMemcpyHostToDevice, c->stream));
-	const int rc = vp8_launch_rgb(b->d_rgbdesc, b->n, max_blocks, c->stream);
+	CU(cudaMemcpyAsync(b->d_rgbdesc, h.data(), sizeof(Vp8RgbDesc) * b->n, cudaMemcpyHostToDevice, b->stream));
+	const int rc = vp8_launch_rgb(b->d_rgbdesc, b->n, max_blocks, b->stream);
 	if (rc) return fail(EIO, "rgb launch", (cudaError_t)rc);
 	c->launches++;
 	b->have_rgb = true;
@@ -910,7 +950,7 @@ int vp8_gpu_download_i420(vp8_gpu_ctx* c, vp8_gpu_batch* b, uint8_t* dst, size_t
 	CU(cudaSetDevice(c->device));
 	const FrameMeta& last = b->meta.back();
 	const size_t used = last.tight_off + (size_t)last.width * last.height + 2 * (size_t)((last.width + 1) / 2) * ((last.height + 1) / 2);
-	if (download(c, dst, b->d_tight, used)) return -1;
+	if (download(c, b->stream, dst, b->d_tight, used)) return -1;
 	for (int i = 0; i < b->n; i++) {
 		const FrameMeta& m = b->meta[i];
 		if (offsets) offsets[i] = m.tight_off;
@@ -926,7 +966,7 @@ int vp8_gpu_download_ppm(vp8_gpu_ctx* c, vp8_gpu_batch* b, uint8_t* dst, size_t 
 	CU(cudaSetDevice(c->device));
 	const FrameMeta& last = b->meta.back();
 	const size_t used = last.rgb_off + kPpmSlot + (size_t)last.width * last.height * 3;
-	if (download(c, dst, b->d_rgb, used)) return -1;
+	if (download(c, b->stream, dst, b->d_rgb, used)) return -1;
 	for (int i = 0; i < b->n; i++) {
 		const FrameMeta& m = b->meta[i];
 		char hdr[32];
@@ -944,8 +984,8 @@ int vp8_gpu_download_padded(vp8_gpu_ctx* c, vp8_gpu_batch* b, int i, uint8_t* y,
 	CU(cudaSetDevice(c->device));
 	const FrameMeta& m = b->meta[i];
 	const size_t px = (size_t)m.mb_cols * 16 * m.mb_rows * 16;
-	if (download(c, y, b->d_pad + m.pad_off[0], px) || download(c, u, b->d_pad + m.pad_off[1], px / 4) ||
-	    download(c, v, b->d_pad + m.pad_off[2], px / 4))
+	if (download(c, b->stream, y, b->d_pad + m.pad_off[0], px) || download(c, b->stream, u, b->d_pad + m.pad_off[1], px / 4) ||
+	    download(c, b->stream, v, b->d_pad + m.pad_off[2], px / 4))
 		return -1;
 	return 0;
 }
@@ -965,15 +1005,16 @@ int vp8_gpu_download_images(vp8_gpu_ctx* c, vp8_gpu_batch* b, Yuv420Image* out) 
 		const size_t cw = (m.width + 1) / 2, ch = (m.height + 1) / 2;
 		if (b->state == PLANES_TIGHT) {
 			const uint8_t* s = b->d_tight + m.tight_off;
-			rc = download(c, img->y, s, (size_t)m.width * m.height) || download(c, img->u, s + (size_t)m.width * m.height, cw * ch) ||
-			     download(c, img->v, s + (size_t)m.width * m.height + cw * ch, cw * ch);
+			rc = download(c, b->stream, img->y, s, (size_t)m.width * m.height) ||
+			     download(c, b->stream, img->u, s + (size_t)m.width * m.height, cw * ch) ||
+			     download(c, b->stream, img->v, s + (size_t)m.width * m.height + cw * ch, cw * ch);
 		} else {
 			// crop while copying (reference vp8_recon.c:693-707)
 			const size_t pw = (size_t)m.mb_cols * 16;
-			cudaError_t e = cudaMemcpy2DAsync(img->y, m.width, b->d_pad + m.pad_off[0], pw, m.width, m.height, cudaMemcpyDeviceToHost, c->stream);
-			if (e == cudaSuccess) e = cudaMemcpy2DAsync(img->u, cw, b->d_pad + m.pad_off[1], pw / 2, cw, ch, cudaMemcpyDeviceToHost, c->stream);
-			if (e == cudaSuccess) e = cudaMemcpy2DAsync(img->v, cw, b->d_pad + m.pad_off[2], pw / 2, cw, ch, cudaMemcpyDeviceToHost, c->stream);
-			if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+			cudaError_t e = cudaMemcpy2DAsync(img->y, m.width, b->d_pad + m.pad_off[0], pw, m.width, m.height, cudaMemcpyDeviceToHost, b->stream);
+			if (e == cudaSuccess) e = cudaMemcpy2DAsync(img->u, cw, b->d_pad + m.pad_off[1], pw / 2, cw, ch, cudaMemcpyDeviceToHost, b->stream);
+			if (e == cudaSuccess) e = cudaMemcpy2DAsync(img->v, cw, b->d_pad + m.pad_off[2], pw / 2, cw, ch, cudaMemcpyDeviceToHost, b->stream);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
 			if (e != cudaSuccess) rc = fail(EIO, "cropping download", e);
 			c->d2h += (size_t)m.width * m.height + 2 * cw * ch;
 		}
@@ -986,6 +1027,97 @@ int vp8_gpu_download_images(vp8_gpu_ctx* c, vp8_gpu_batch* b, Yuv420Image* out) 
 		return -1;
 	}
 	return 0;
+}
+
+// Chunked pipeline: chunk k's host->device copies, kernels and device->host copy run on internal stream k % 3, so the
+// copy engines (one per direction) and the SMs work on different chunks at the same time. Blocking: returns when
+// dst holds every frame. Output layout = the layout of one big batch (frame i at offsets[i], 256-byte aligned).
+static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,
+                            int filtered, bool want_ppm, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk) {
+	if (!c || !kf || !frames || !dst || n <= 0) return fail(EINVAL, "bad arguments");
+	for (int i = 0; i < n; i++)
+		if (validate_frame(kf[i], frames[i], true)) return -1;
+	CU(cudaSetDevice(c->device));
+	if (chunk <= 0) chunk = 128;
+	// global layout
+	std::vector<size_t> off(n + 1, 0);
+	for (int i = 0; i < n; i++) {
+		const size_t w = kf[i]->width, h = kf[i]->height;
+		off[i + 1] = off[i] + (want_ppm ? align_up(kPpmSlot + w * h * 3) : align_up(w * h + 2 * ((w + 1) / 2) * ((h + 1) / 2)));
+	}
+	if (cap < off[n]) return fail(EINVAL, "destination too small");
+	for (auto& p : c->pipe)
+		if (!p) CU(cudaStreamCreateWithFlags(&p, cudaStreamNonBlocking));
+	if (!c->pipe_ev) CU(cudaEventCreateWithFlags(&c->pipe_ev, cudaEventDisableTiming));
+	// whatever the caller queued on the context's stream comes first
+	CU(cudaEventRecord(c->pipe_ev, c->stream));
+	for (auto& p : c->pipe) CU(cudaStreamWaitEvent(p, c->pipe_ev, 0));
+
+	vp8_gpu_batch* inflight[3] = {nullptr, nullptr, nullptr};
+	int rc = 0;
+	int k = 0;
+	for (int first = 0; first < n && !rc; first += chunk, k++) {
+		const int cnt = std::min(chunk, n - first), slot = k % 3;
+		if (inflight[slot]) { // retire the chunk that used this stream three chunks ago (frees its device blocks)
+			batch_destroy(c, inflight[slot]);
+			inflight[slot] = nullptr;
+		}
+		vp8_gpu_batch* b = nullptr;
+		rc = batch_create(c, kf + first, frames + first, cnt, true, &b, c->pipe[slot]);
+		if (rc) break;
+		inflight[slot] = b;
+		rc = vp8_gpu_run(c, b, filtered, VP8_GPU_TIGHT);
+		if (!rc && want_ppm) rc = vp8_gpu_rgb(c, b);
+		if (rc) break;
+		const FrameMeta& last = b->meta.back();
+		if (want_ppm) {
+			const size_t used = last.rgb_off + kPpmSlot + (size_t)last.width * last.height * 3;
+			rc = download(c, b->stream, dst + off[first], b->d_rgb, used, false);
+		} else {
+			const size_t used = last.tight_off + (size_t)last.width * last.height + 2 * (size_t)((last.width + 1) / 2) * ((last.height + 1) / 2);
+			rc = download(c, b->stream, dst + off[first], b->d_tight, used, false);
+		}
+	}
+	const int saved = errno;
+	for (auto& b : inflight)
+		if (b) batch_destroy(c, b); // synchronises the chunk's stream
+	if (rc) {
+		errno = saved;
+		return -1;
+	}
+	for (int i = 0; i < n; i++) {
+		const size_t w = kf[i]->width, h = kf[i]->height;
+		if (want_ppm) {
+			char hdr[32];
+			const int hl = ppm_header(hdr, (uint32_t)w, (uint32_t)h);
+			memcpy(dst + off[i] + kPpmSlot - hl, hdr, hl);
+			if (offsets) offsets[i] = off[i] + kPpmSlot - hl;
+			if (sizes) sizes[i] = hl + w * h * 3;
+		} else {
+			if (offsets) offsets[i] = off[i];
+			if (sizes) sizes[i] = w * h + 2 * ((w + 1) / 2) * ((h + 1) / 2);
+		}
+	}
+	return 0;
+}
+
+int vp8_gpu_decode_i420(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n, int filtered,
+                        uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk) {
+	return decode_pipelined(c, kf, frames, n, filtered, false, dst, cap, offsets, sizes, chunk);
+}
+
+int vp8_gpu_decode_ppm(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n, uint8_t* dst,
+                       size_t cap, size_t* offsets, size_t* sizes, int chunk) {
+	return decode_pipelined(c, kf, frames, n, 1, true, dst, cap, offsets, sizes, chunk);
+}
+
+size_t vp8_gpu_decode_bytes(const Vp8KeyFrameHeader* const* kf, int n, int ppm) {
+	size_t total = 0;
+	for (int i = 0; kf && i < n; i++) {
+		const size_t w = kf[i]->width, h = kf[i]->height;
+		total += ppm ? align_up(kPpmSlot + w * h * 3) : align_up(w * h + 2 * ((w + 1) / 2) * ((h + 1) / 2));
+	}
+	return total;
 }
 
 uint64_t vp8_gpu_launch_count(const vp8_gpu_ctx* c) { return c ? c->launches : 0; }
@@ -1109,7 +1241,7 @@ int vp8_loopfilter_apply_keyframe(Yuv420Image* img, const Vp8DecodedFrame* decod
 	const FrameMeta& m = b->meta[0];
 	const uint32_t pw = img->width, ph = img->height;
 	if (!rc) {
-		Uploader up{c};
+		Uploader up{c, b->stream};
 		for (uint32_t r = 0; r < ph && !rc; r++) rc = up.put(b->d_pad + m.pad_off[0] + (size_t)r * pw, img->y + (size_t)r * img->stride_y, pw);
 		for (uint32_t r = 0; r < ph / 2 && !rc; r++) rc = up.put(b->d_pad + m.pad_off[1] + (size_t)r * (pw / 2), img->u + (size_t)r * img->stride_uv, pw / 2);
 		for (uint32_t r = 0; r < ph / 2 && !rc; r++) rc = up.put(b->d_pad + m.pad_off[2] + (size_t)r * (pw / 2), img->v + (size_t)r * img->stride_uv, pw / 2);
