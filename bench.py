@@ -155,6 +155,8 @@ def gpu_arm(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx = W.Context(local, stream.cuda_stream)
+    if args.kernel:
+        ctx.set_kernel(args.kernel)
     if args.warps or args.images_per_sm:
         ctx.set_tuning(args.warps, args.images_per_sm)
 
@@ -292,6 +294,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="yuvf", choices=["yuvf", "yuv", "ppm"])
     ap.add_argument("--batch", type=int, default=1024, help="frames per GPU per step")
+    ap.add_argument("--kernel", type=int, default=0, help="wavefront kernel: 1 warp per macroblock, 2 half-warp per macroblock (0 = library default)")
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--images-per-sm", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=5)

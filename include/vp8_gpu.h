@@ -63,6 +63,10 @@ const char* vp8_gpu_last_error(void);
  * images per SM (0 = as many as fit). */
 int vp8_gpu_set_tuning(vp8_gpu_ctx* ctx, int warps_per_image, int images_per_sm);
 
+/* Which wavefront kernel runs m06/m07: 1 = one warp per macroblock (vp8_kernels.cu), 2 = one half-warp per macroblock,
+ * two rows per warp (vp8_pairs.cu). Both are bit-exact; the environment variable VP8_GPU_KERNEL presets it. */
+int vp8_gpu_set_kernel(vp8_gpu_ctx* ctx, int version);
+
 /* Pinned host memory: frames whose arrays live here are copied to the device without staging. */
 void* vp8_gpu_host_alloc(size_t bytes);
 void vp8_gpu_host_free(void* p);

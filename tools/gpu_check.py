@@ -51,9 +51,11 @@ def report(name, got, want, w, h, limit=6):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--kernel", type=int, default=1, help="1 = warp per macroblock, 2 = half-warp per macroblock")
     args = ap.parse_args()
     orc = Oracle()
     ctx = W.Context(0)
+    ctx.set_kernel(args.kernel)
     nofilt = dict(lf_level=0, segmentation_enabled=0, lf_delta_enabled=0)
     plain = dict(segmentation_enabled=0, lf_delta_enabled=0, lf_sharpness=0, lf_use_simple=0)
     cases = [
@@ -87,7 +89,7 @@ def main():
         w, h = fr.width, fr.height
         print(f"[{name}] {w}x{h} lf_level={fr.params['lf_level']} simple={fr.params['lf_use_simple']} seg={fr.params['segmentation_enabled']}")
         kf, d = fr.header(), fr.cstruct()
-        for warps in ((4, 8, 32) if not args.quick else (4,)):
+        for warps in ((4,) if args.quick else ((4, 8, 32) if args.kernel == 1 else (4, 8, 16))):
             ctx.set_tuning(warps, 0)
             want_u = orc.decode_i420(fr, False)
             got_u = ctx.decode_i420([kf], [d], filtered=False)[0]

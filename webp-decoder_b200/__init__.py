@@ -41,7 +41,7 @@ EXPORTS = [
     "vp8_gpu_download_i420", "vp8_gpu_download_ppm", "vp8_gpu_download_images", "vp8_gpu_download_padded",
     "vp8_gpu_batch_size", "vp8_gpu_launch_count", "vp8_gpu_h2d_bytes", "vp8_gpu_d2h_bytes",
     "vp8_gpu_last_launch_config", "vp8_gpu_frame_params", "vp8_gpu_kernel_time",
-    "vp8_gpu_decode_i420", "vp8_gpu_decode_ppm", "vp8_gpu_decode_bytes",
+    "vp8_gpu_decode_i420", "vp8_gpu_decode_ppm", "vp8_gpu_decode_bytes", "vp8_gpu_set_kernel",
 ]
 
 _lib = None
@@ -68,6 +68,7 @@ def load_library() -> C.CDLL:
     L.vp8_gpu_sync.argtypes = [vp]
     L.vp8_gpu_last_error.restype = C.c_char_p
     L.vp8_gpu_set_tuning.argtypes = [vp, C.c_int, C.c_int]
+    L.vp8_gpu_set_kernel.argtypes = [vp, C.c_int]
     L.vp8_gpu_host_alloc.argtypes = [sz]
     L.vp8_gpu_host_alloc.restype = vp
     L.vp8_gpu_host_free.argtypes = [vp]
@@ -203,6 +204,10 @@ class Context:
 
     def set_tuning(self, warps_per_image: int = 0, images_per_sm: int = 0):
         _check(self._L.vp8_gpu_set_tuning(self._h, warps_per_image, images_per_sm), "vp8_gpu_set_tuning")
+
+    def set_kernel(self, version: int):
+        """1 = warp per macroblock, 2 = half-warp per macroblock (two rows per warp)."""
+        _check(self._L.vp8_gpu_set_kernel(self._h, version), "vp8_gpu_set_kernel")
 
     def sync(self):
         _check(self._L.vp8_gpu_sync(self._h), "vp8_gpu_sync")

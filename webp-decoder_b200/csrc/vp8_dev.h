@@ -1,5 +1,6 @@
 // vp8_dev.h - descriptors shared between the host library and the kernels.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 // One decoded key frame as the kernels see it. All pointers are device pointers.
@@ -64,4 +65,11 @@ int vp8_launch_wavefront(int mode, int warps_per_image, const Vp8ImgDesc* descs_
                          int grid_ctas, void* stream);
 int vp8_wavefront_smem_bytes(int mode, int warps_per_image, int max_mb_cols);
 int vp8_wavefront_max_ctas_per_sm(int mode, int warps_per_image, int max_mb_cols);
+// Second-generation kernel (vp8_pairs.cu): half-warp per macroblock, two rows per warp. warps_per_image in {4, 8, 16}.
+// scratch: vp8_pairs_scratch_bytes(grid, max_mb_cols) bytes of device memory private to this launch.
+int vp8_launch_pairs(int mode, int warps_per_image, const Vp8ImgDesc* descs_dev, int n_images, int max_mb_cols, int grid_ctas,
+                     uint8_t* scratch, void* stream);
+int vp8_pairs_smem_bytes(int warps_per_image, int max_mb_cols);
+int vp8_pairs_max_ctas_per_sm(int mode, int warps_per_image, int max_mb_cols);
+size_t vp8_pairs_scratch_bytes(int grid_ctas, int max_mb_cols);
 int vp8_launch_rgb(const Vp8RgbDesc* descs_dev, int n_images, uint32_t total_blocks, void* stream);

@@ -67,6 +67,7 @@ struct vp8_gpu_ctx {
 	bool own_stream = false;
 	int sm_count = 0;
 	int tune_warps = 0, tune_imgs_per_sm = 0;
+	int kernel_version = 1; // 1: vp8_mb_wavefront (warp per macroblock), 2: vp8_mb_pairs (half-warp per macroblock)
 	uint8_t* bounce[2] = {nullptr, nullptr};
 	cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
 	bool bounce_busy[2] = {false, false};
@@ -119,6 +120,8 @@ struct vp8_gpu_batch {
 	bool filtered = false, have_rgb = false, have_coeffs = true;
 	int desc_key = -1; // kernel_mode*2 + layout of the descriptors currently on the device
 	cudaStream_t stream = nullptr; // all work on this batch is issued here (the context's stream unless pipelined)
+	uint8_t* d_scratch = nullptr;  // filtered-row line buffers of the pair kernel (one line set per CTA)
+	size_t scratch_bytes = 0;
 };
 
 namespace {
@@ -340,6 +343,7 @@ void batch_destroy(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
 	dev_release(c, b->d_rgb, b->rgb_bytes);
 	dev_release(c, b->d_desc, sizeof(Vp8ImgDesc) * b->n);
 	dev_release(c, b->d_rgbdesc, sizeof(Vp8RgbDesc) * b->n);
+	dev_release(c, b->d_scratch, b->scratch_bytes);
 	delete b;
 }
 
@@ -543,15 +547,28 @@ int pick_warps(const vp8_gpu_ctx* c, int n_images) {
 
 int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layout) {
 	if (push_descs(c, b, kernel_mode, layout)) return -1;
+	const bool pairs = c->kernel_version == 2;
 	int warps = pick_warps(c, b->n);
+	if (pairs) warps = std::min(warps, 16); // a pair-kernel warp already carries two macroblock rows
 	int per_sm = 0;
 	for (;; warps /= 2) {
-		per_sm = vp8_wavefront_max_ctas_per_sm(kernel_mode, warps, b->max_mb_cols);
+		per_sm = pairs ? vp8_pairs_max_ctas_per_sm(kernel_mode, warps, b->max_mb_cols)
+		               : vp8_wavefront_max_ctas_per_sm(kernel_mode, warps, b->max_mb_cols);
 		if (per_sm > 0 || warps == 4) break;
 	}
 	if (per_sm <= 0) return fail(EIO, "wavefront kernel does not fit on an SM (frame too wide?)", cudaGetLastError());
 	if (c->tune_imgs_per_sm > 0) per_sm = std::min(per_sm, c->tune_imgs_per_sm);
 	const int grid = std::min(b->n, per_sm * c->sm_count);
+	if (pairs) {
+		const size_t need = vp8_pairs_scratch_bytes(grid, b->max_mb_cols);
+		if (b->scratch_bytes < need) {
+			dev_release(c, b->d_scratch, b->scratch_bytes);
+			b->d_scratch = nullptr;
+			b->scratch_bytes = 0;
+			if (dev_alloc(c, need, (void**)&b->d_scratch)) return -1;
+			b->scratch_bytes = need;
+		}
+	}
 	std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
 	if (!c->spare.empty()) {
 		ev = c->spare.back();
@@ -561,7 +578,8 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 		CU(cudaEventCreate(&ev.second));
 	}
 	CU(cudaEventRecord(ev.first, b->stream));
-	const int rc = vp8_launch_wavefront(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, b->stream);
+	const int rc = pairs ? vp8_launch_pairs(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, b->d_scratch, b->stream)
+	                     : vp8_launch_wavefront(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, b->stream);
 	CU(cudaEventRecord(ev.second, b->stream));
 	c->timed.push_back(ev);
 	if (c->timed.size() > 4096) { // nobody is asking: recycle the oldest
@@ -572,7 +590,7 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 	c->launches++;
 	c->last_warps = warps;
 	c->last_grid = grid;
-	c->last_smem = vp8_wavefront_smem_bytes(kernel_mode, warps, b->max_mb_cols);
+	c->last_smem = pairs ? vp8_pairs_smem_bytes(warps, b->max_mb_cols) : vp8_wavefront_smem_bytes(kernel_mode, warps, b->max_mb_cols);
 	return 0;
 }
 
@@ -793,6 +811,7 @@ int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out) {
 		}
 		c->own_stream = true;
 	}
+	if (const char* k = getenv("VP8_GPU_KERNEL")) c->kernel_version = atoi(k) == 2 ? 2 : 1;
 	if (const char* w = getenv("VP8_GPU_WARPS")) c->tune_warps = atoi(w);
 	if (const char* w = getenv("VP8_GPU_IMAGES_PER_SM")) c->tune_imgs_per_sm = atoi(w);
 	*out = c;
@@ -832,6 +851,12 @@ int vp8_gpu_set_tuning(vp8_gpu_ctx* c, int warps_per_image, int images_per_sm) {
 		return fail(EINVAL, "bad tuning");
 	c->tune_warps = warps_per_image;
 	c->tune_imgs_per_sm = images_per_sm;
+	return 0;
+}
+
+int vp8_gpu_set_kernel(vp8_gpu_ctx* c, int version) {
+	if (!c || (version != 1 && version != 2)) return fail(EINVAL, "bad kernel version");
+	c->kernel_version = version;
 	return 0;
 }
 

@@ -30,283 +30,9 @@
 
 #include "vp8_dev.h"
 
-#ifndef VP8_LF_GENERIC
-#define VP8_LF_GENERIC 0 // 1: one byte-addressed filter body looped over the 8 edges (smaller code, more instructions)
-#endif
-#ifndef VP8_BPRED_LOOP
-#define VP8_BPRED_LOOP 0 // 1: B_PRED steps as a 5 x 2 loop instead of 10 unrolled steps
-#endif
+#include "vp8_common.cuh"
 
 namespace {
-
-// ------------------------------------------------------------------------------------------------ constants
-// (mode, pixel) -> first tap | 0x10 for 2-tap, over the edge vector
-//   E[0..2]=L3 E[3]=L2 E[4]=L1 E[5]=L0 E[6]=P E[7..14]=A0..A7 E[15]=A7
-// Rows 0 (B_DC) and 1 (B_TM) are placeholders; those two modes are computed arithmetically.
-// Equivalent to the ten unrolled cases of reference subblock_predict (vp8_recon.c:218-358).
-#define T3(i) (i)
-#define T2(i) (0x10 | (i))
-__constant__ uint8_t c_bpred_taps[10 * 16] = {
-    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-    /* VE */ T3(6), T3(7), T3(8), T3(9), T3(6), T3(7), T3(8), T3(9), T3(6), T3(7), T3(8), T3(9), T3(6), T3(7), T3(8), T3(9),
-    /* HE */ T3(4), T3(4), T3(4), T3(4), T3(3), T3(3), T3(3), T3(3), T3(2), T3(2), T3(2), T3(2), T3(1), T3(1), T3(1), T3(1),
-    /* LD */ T3(7), T3(8), T3(9), T3(10), T3(8), T3(9), T3(10), T3(11), T3(9), T3(10), T3(11), T3(12), T3(10), T3(11), T3(12), T3(13),
-    /* RD */ T3(5), T3(6), T3(7), T3(8), T3(4), T3(5), T3(6), T3(7), T3(3), T3(4), T3(5), T3(6), T3(2), T3(3), T3(4), T3(5),
-    /* VR */ T2(6), T2(7), T2(8), T2(9), T3(5), T3(6), T3(7), T3(8), T3(4), T2(6), T2(7), T2(8), T3(3), T3(5), T3(6), T3(7),
-    /* VL */ T2(7), T2(8), T2(9), T2(10), T3(7), T3(8), T3(9), T3(10), T2(8), T2(9), T2(10), T3(11), T3(8), T3(9), T3(10), T3(12),
-    /* HD */ T2(5), T3(5), T3(6), T3(7), T2(4), T3(4), T2(5), T3(5), T2(3), T3(3), T2(4), T3(4), T2(2), T3(2), T2(3), T3(3),
-    /* HU */ T2(4), T3(3), T2(3), T3(2), T2(3), T3(2), T2(2), T3(1), T2(2), T3(1), T3(0), T3(0), T3(0), T3(0), T3(0), T3(0),
-};
-#undef T3
-#undef T2
-
-constexpr int kProgRing = 64;      // progress stamps, ring over macroblock rows (>= 2*NW)
-constexpr int kStampRow = 4096;    // stamp = (row+1)*kStampRow + macroblocks done in that row
-constexpr int kBtabWords = 2 * 11 * 16;
-constexpr int kSmemFixed = 256 + 256 + kBtabWords * 4; // progress ring + image descriptor + B_PRED lane table
-
-// Per-warp shared-memory workspace.
-//   rt_*: reconstruction tile with a 1-pixel top/left border (what intra prediction reads).
-//         luma row r in [-1,15] at (r+1)*24, column c in [-1,19] at 4+c (columns 16..19 = above-right);
-//         chroma row r in [-1,7] at (r+1)*12, column c in [-1,7] at 4+c.
-//   ft_*: filter tile with 4-pixel top/left aprons. luma row r in [-4,15] at (r+4)*20, column c at 4+c;
-//         chroma row r in [-4,7] at (r+4)*12, column c at 4+c.
-//   coef: the macroblock's 25 coefficient blocks as landed by cp.async: 16-byte half h of block i at [h*25+i]
-//         (blocks 0..15 luma, 16..19 U, 20..23 V, 24 Y2), so that lane i reads both halves without bank conflicts.
-struct __align__(16) WarpWs {
-	uint8_t rt_y[17 * 24];
-	uint8_t rt_u[9 * 12];
-	uint8_t rt_v[9 * 12];
-	uint8_t lcol[32];     // unfiltered left neighbours packed: y[16] u[8] v[8]
-	int16_t res[16][16];  // luma residuals of a B_PRED macroblock; res[0] doubles as the WHT output
-	uint8_t ft_y[20 * 20];
-	uint8_t ft_u[12 * 12];
-	uint8_t ft_v[12 * 12];
-	uint4 coef[50];
-	uint8_t pad_[32];
-};
-static_assert(sizeof(WarpWs) % 16 == 0, "WarpWs alignment");
-static_assert(offsetof(WarpWs, res) % 16 == 0 && offsetof(WarpWs, coef) % 16 == 0, "vector slots must be 16-byte aligned");
-
-struct OutPlane {
-	uint8_t* p;
-	uint32_t stride, w, h;
-	bool word_ok;
-};
-
-// ------------------------------------------------------------------------------------------------ small helpers
-__device__ __forceinline__ int s16(int v) { return (int)(short)v; }
-__device__ __forceinline__ int clip255(int v) { return __vimin_s32_relu(v, 255); }                 // VIMNMX.RELU
-__device__ __forceinline__ int add_clip255(int a, int b) { return __viaddmin_s32_relu(a, b, 255); } // VIADDMNMX.RELU
-__device__ __forceinline__ int sclamp(int v) { return min(max(v, -128), 127); }
-__device__ __forceinline__ int absdiff(int a, int b) { return (int)__sad(a, b, 0u); }               // VABSDIFF
-__device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
-__device__ __forceinline__ void st32(uint8_t* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
-__device__ __forceinline__ uint32_t sum4(uint32_t w) { return __dp4a(w, 0x01010101u, 0u); }
-
-// 16-byte global -> shared copy that bypasses L1 (coefficients are read exactly once).
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// Store 4 pixels at (ox, oy) of an output plane, honouring the crop (negative coordinates are outside too).
-__device__ __forceinline__ void put_word(const OutPlane& o, int ox, int oy, uint32_t v) {
-	if ((uint32_t)oy >= o.h || (uint32_t)ox >= o.w) return;
-	uint8_t* d = o.p + (size_t)oy * o.stride + ox;
-	if (o.word_ok && (uint32_t)ox + 4 <= o.w) {
-		st32(d, v);
-	} else {
-#pragma unroll
-		for (int k = 0; k < 4; k++)
-			if ((uint32_t)ox + k < o.w) d[k] = (uint8_t)(v >> (8 * k));
-	}
-}
-
-// ------------------------------------------------------------------------------------------------ transforms
-// RFC 6386 14.4 butterfly. Reference inv_dct4x4 (vp8_recon.c:107-148): vertical pass, int16 truncation, horizontal
-// pass with (x+4)>>3.
-__device__ __forceinline__ void idct_1d(int x0, int x1, int x2, int x3, int& o0, int& o1, int& o2, int& o3) {
-	int e = x0 + x2, g = x0 - x2;
-	int s1 = (x1 * 35468) >> 16, s3 = (x3 * 35468) >> 16;
-	int c1 = x1 + ((x1 * 20091) >> 16), c3 = x3 + ((x3 * 20091) >> 16);
-	int lo = s1 - c3, hi = c1 + s3;
-	o0 = e + hi;
-	o1 = g + lo;
-	o2 = g - lo;
-	o3 = e - hi;
-}
-
-__device__ __forceinline__ void idct4x4(const int (&v)[16], int (&r)[16]) {
-	int t[16];
-#pragma unroll
-	for (int c = 0; c < 4; c++) {
-		int o0, o1, o2, o3;
-		idct_1d(v[c], v[4 + c], v[8 + c], v[12 + c], o0, o1, o2, o3);
-		t[c] = s16(o0);
-		t[4 + c] = s16(o1);
-		t[8 + c] = s16(o2);
-		t[12 + c] = s16(o3);
-	}
-#pragma unroll
-	for (int k = 0; k < 4; k++) {
-		int o0, o1, o2, o3;
-		idct_1d(t[4 * k], t[4 * k + 1], t[4 * k + 2], t[4 * k + 3], o0, o1, o2, o3);
-		r[4 * k] = s16((o0 + 4) >> 3);
-		r[4 * k + 1] = s16((o1 + 4) >> 3);
-		r[4 * k + 2] = s16((o2 + 4) >> 3);
-		r[4 * k + 3] = s16((o3 + 4) >> 3);
-	}
-}
-
-// Reference inv_wht4x4 (vp8_recon.c:80-105).
-__device__ __forceinline__ void iwht4x4(const int (&v)[16], int (&r)[16]) {
-	int t[16];
-#pragma unroll
-	for (int c = 0; c < 4; c++) {
-		int s03 = v[c] + v[12 + c], s12 = v[4 + c] + v[8 + c];
-		int d12 = v[4 + c] - v[8 + c], d03 = v[c] - v[12 + c];
-		t[c] = s16(s03 + s12);
-		t[4 + c] = s16(d12 + d03);
-		t[8 + c] = s16(s03 - s12);
-		t[12 + c] = s16(d03 - d12);
-	}
-#pragma unroll
-	for (int k = 0; k < 4; k++) {
-		int s03 = t[4 * k] + t[4 * k + 3], s12 = t[4 * k + 1] + t[4 * k + 2];
-		int d12 = t[4 * k + 1] - t[4 * k + 2], d03 = t[4 * k] - t[4 * k + 3];
-		r[4 * k] = s16((s03 + s12 + 3) >> 3);
-		r[4 * k + 1] = s16((d12 + d03 + 3) >> 3);
-		r[4 * k + 2] = s16((s03 - s12 + 3) >> 3);
-		r[4 * k + 3] = s16((d03 - d12 + 3) >> 3);
-	}
-}
-
-// ------------------------------------------------------------------------------------------------ loop filter
-enum { EDGE_MB = 0, EDGE_INNER = 1, EDGE_SIMPLE = 2 };
-
-#if VP8_LF_GENERIC
-// One position across an edge: q points at q0, `step` is the byte distance between the pixels p3..q3 (1 across a
-// vertical edge, the tile stride across a horizontal one). A single body serves every edge of every plane so that
-// the kernel stays inside the instruction cache; `kind` is warp-uniform.
-// Thresholds: reference vp8_loopfilter.c:24-56; kernels :58-104; dispatch :106-164.
-__device__ __forceinline__ void lf_line(uint8_t* q, int step, int kind, int lim, int interior, int hev_thr) {
-	int p1 = q[-2 * step], p0 = q[-step], q0 = q[0], q1 = q[step];
-	if (2 * absdiff(p0, q0) + (absdiff(p1, q1) >> 1) > lim) return;
-	int p2 = 0, q2 = 0;
-	bool hev = false;
-	if (kind != EDGE_SIMPLE) {
-		const int p3 = q[-4 * step], q3 = q[3 * step];
-		p2 = q[-3 * step];
-		q2 = q[2 * step];
-		const int dp = absdiff(p1, p0), dq = absdiff(q1, q0);
-		int m = __vimax3_s32(absdiff(p3, p2), absdiff(p2, p1), dp);
-		m = __vimax3_s32(m, absdiff(q3, q2), absdiff(q2, q1));
-		if (max(m, dq) > interior) return;
-		hev = max(dp, dq) > hev_thr;
-		if (kind == EDGE_MB && !hev) {
-			const int w = sclamp(sclamp(p1 - q1) + 3 * (q0 - p0));
-			const int a = (27 * w + 63) >> 7, b = (18 * w + 63) >> 7, c = (9 * w + 63) >> 7;
-			q[-step] = (uint8_t)add_clip255(p0, a);
-			q[0] = (uint8_t)add_clip255(q0, -a);
-			q[-2 * step] = (uint8_t)add_clip255(p1, b);
-			q[step] = (uint8_t)add_clip255(q1, -b);
-			q[-3 * step] = (uint8_t)add_clip255(p2, c);
-			q[2 * step] = (uint8_t)add_clip255(q2, -c);
-			return;
-		}
-	}
-	const bool outer = (kind != EDGE_INNER) || hev;
-	int a = 3 * (q0 - p0);
-	if (outer) a += sclamp(p1 - q1);
-	a = sclamp(a);
-	const int f1 = min(a + 4, 127) >> 3, f2 = min(a + 3, 127) >> 3; // a >= -128 already
-	q[0] = (uint8_t)add_clip255(q0, -f1);
-	q[-step] = (uint8_t)add_clip255(p0, f2);
-	if (!outer) {
-		const int h = (f1 + 1) >> 1;
-		q[step] = (uint8_t)add_clip255(q1, -h);
-		q[-2 * step] = (uint8_t)add_clip255(p1, h);
-	}
-}
-
-#else
-// One position across an edge, in registers. Returns true when pixels changed.
-// Thresholds: reference vp8_loopfilter.c:24-56; kernels :58-104; dispatch :106-164.
-template <int KIND>
-__device__ __forceinline__ bool lf_position(int p3, int& p2, int& p1, int& p0, int& q0, int& q1, int& q2, int q3, int lim,
-                                            int interior, int hev_thr) {
-	if (2 * absdiff(p0, q0) + (absdiff(p1, q1) >> 1) > lim) return false;
-	bool hev = false;
-	if (KIND != EDGE_SIMPLE) {
-		const int dp = absdiff(p1, p0), dq = absdiff(q1, q0);
-		int m = __vimax3_s32(absdiff(p3, p2), absdiff(p2, p1), dp);
-		m = __vimax3_s32(m, absdiff(q3, q2), absdiff(q2, q1));
-		if (max(m, dq) > interior) return false;
-		hev = max(dp, dq) > hev_thr;
-		if (KIND == EDGE_MB && !hev) {
-			int w = sclamp(sclamp(p1 - q1) + 3 * (q0 - p0));
-			int a = (27 * w + 63) >> 7, b = (18 * w + 63) >> 7, c = (9 * w + 63) >> 7;
-			p0 = add_clip255(p0, a);
-			q0 = add_clip255(q0, -a);
-			p1 = add_clip255(p1, b);
-			q1 = add_clip255(q1, -b);
-			p2 = add_clip255(p2, c);
-			q2 = add_clip255(q2, -c);
-			return true;
-		}
-	}
-	const bool outer = (KIND != EDGE_INNER) || hev;
-	int a = 3 * (q0 - p0);
-	if (outer) a += sclamp(p1 - q1);
-	a = sclamp(a);
-	int f1 = min(a + 4, 127) >> 3, f2 = min(a + 3, 127) >> 3; // a >= -128 already
-	q0 = add_clip255(q0, -f1);
-	p0 = add_clip255(p0, f2);
-	if (!outer) {
-		int h = (f1 + 1) >> 1;
-		q1 = add_clip255(q1, -h);
-		p1 = add_clip255(p1, h);
-	}
-	return true;
-}
-
-// Filter across a vertical edge: q points at the word holding q0..q3 of this lane's pixel row (4-byte aligned).
-template <int KIND>
-__device__ __forceinline__ void lf_across_columns(uint8_t* q, int lim, int interior, int hev_thr) {
-	uint32_t wp = ld32(q - 4), wq = ld32(q);
-	int p3 = wp & 255, p2 = (wp >> 8) & 255, p1 = (wp >> 16) & 255, p0 = wp >> 24;
-	int q0 = wq & 255, q1 = (wq >> 8) & 255, q2 = (wq >> 16) & 255, q3 = wq >> 24;
-	if (lf_position<KIND>(p3, p2, p1, p0, q0, q1, q2, q3, lim, interior, hev_thr)) {
-		st32(q - 4, (uint32_t)p3 | (p2 << 8) | (p1 << 16) | ((uint32_t)p0 << 24));
-		st32(q, (uint32_t)q0 | (q1 << 8) | (q2 << 16) | ((uint32_t)q3 << 24));
-	}
-}
-
-// Filter across a horizontal edge: q points at q0 of this lane's pixel column, s = row stride.
-template <int KIND>
-__device__ __forceinline__ void lf_across_rows(uint8_t* q, int s, int lim, int interior, int hev_thr) {
-	int p3 = 0, q3 = 0;
-	int p2 = q[-3 * s], p1 = q[-2 * s], p0 = q[-s], q0 = q[0], q1 = q[s], q2 = q[2 * s];
-	if (KIND != EDGE_SIMPLE) {
-		p3 = q[-4 * s];
-		q3 = q[3 * s];
-	}
-	if (lf_position<KIND>(p3, p2, p1, p0, q0, q1, q2, q3, lim, interior, hev_thr)) {
-		q[-s] = (uint8_t)p0;
-		q[0] = (uint8_t)q0;
-		if (KIND != EDGE_SIMPLE) {
-			q[-3 * s] = (uint8_t)p2;
-			q[-2 * s] = (uint8_t)p1;
-			q[s] = (uint8_t)q1;
-			q[2 * s] = (uint8_t)q2;
-		}
-	}
-}
-
-#endif
 
 // ------------------------------------------------------------------------------------------------ the kernel
 #ifndef VP8_MIN_CTAS
