@@ -52,8 +52,10 @@ def test_reference_fuzz_digests(gpu_ctx):
     assert not [s for s, p in zip(seeds, ppms) if sha(p) != fz[s]["ppm"]]
 
 
-@pytest.mark.parametrize("warps", [4, 8, 16, 32])
-def test_fuzz_vs_oracle_all_warp_shapes(gpu_ctx, oracle, warps):
+@pytest.mark.parametrize("kernel,warps", [(1, 4), (1, 8), (1, 16), (1, 32), (2, 4), (2, 8), (2, 16)])
+def test_fuzz_vs_oracle_all_kernels_and_warp_shapes(gpu_ctx, oracle, kernel, warps):
+    """Both wavefront kernels (warp per macroblock / half-warp per macroblock) in every CTA shape."""
+    gpu_ctx.set_kernel(kernel)
     gpu_ctx.set_tuning(warps, 0)
     try:
         frames = []
@@ -68,6 +70,20 @@ def test_fuzz_vs_oracle_all_warp_shapes(gpu_ctx, oracle, warps):
                 assert np.array_equal(o, oracle.decode_i420(f, filtered)), (f.width, f.height, filtered)
     finally:
         gpu_ctx.set_tuning(0, 0)
+        gpu_ctx.set_kernel(2)
+
+
+def test_first_generation_kernel_still_matches_reference_digests(gpu_ctx, golden, parsed_golden):
+    names = sorted(golden)
+    kfs = [parsed_golden[n][0] for n in names]
+    frs = [parsed_golden[n][1] for n in names]
+    gpu_ctx.set_kernel(1)
+    try:
+        for filtered, key in ((False, "yuv"), (True, "yuvf")):
+            outs = gpu_ctx.decode_i420(kfs, frs, filtered=filtered)
+            assert not [n for n, o in zip(names, outs) if sha(o) != golden[n][key]]
+    finally:
+        gpu_ctx.set_kernel(2)
 
 
 def test_edge_geometries(gpu_ctx, oracle):

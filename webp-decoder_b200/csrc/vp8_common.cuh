@@ -90,16 +90,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Store 4 pixels at (ox, oy) of an output plane, honouring the crop (negative coordinates are outside too).
+// The byte-wise tail is rare (frame borders, unaligned strides): kept out of line so that it is not replicated at every
+// store site (the kernels are instruction-cache bound).
+__device__ __noinline__ void put_bytes(uint8_t* d, uint32_t v, uint32_t n) {
+	for (uint32_t k = 0; k < n; k++) d[k] = (uint8_t)(v >> (8 * k));
+}
 __device__ __forceinline__ void put_word(const OutPlane& o, int ox, int oy, uint32_t v) {
 	if ((uint32_t)oy >= o.h || (uint32_t)ox >= o.w) return;
 	uint8_t* d = o.p + (size_t)oy * o.stride + ox;
-	if (o.word_ok && (uint32_t)ox + 4 <= o.w) {
-		st32(d, v);
-	} else {
-#pragma unroll
-		for (int k = 0; k < 4; k++)
-			if ((uint32_t)ox + k < o.w) d[k] = (uint8_t)(v >> (8 * k));
-	}
+	if (o.word_ok && (uint32_t)ox + 4 <= o.w) st32(d, v);
+	else put_bytes(d, v, min(4u, o.w - (uint32_t)ox));
 }
 
 // ------------------------------------------------------------------------------------------------ transforms

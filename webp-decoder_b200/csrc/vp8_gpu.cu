@@ -67,7 +67,7 @@ struct vp8_gpu_ctx {
 	bool own_stream = false;
 	int sm_count = 0;
 	int tune_warps = 0, tune_imgs_per_sm = 0;
-	int kernel_version = 1; // 1: vp8_mb_wavefront (warp per macroblock), 2: vp8_mb_pairs (half-warp per macroblock)
+	int kernel_version = 2; // 1: vp8_mb_wavefront (warp per macroblock), 2: vp8_mb_pairs (half-warp per macroblock)
 	uint8_t* bounce[2] = {nullptr, nullptr};
 	cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
 	bool bounce_busy[2] = {false, false};
@@ -811,7 +811,7 @@ int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out) {
 		}
 		c->own_stream = true;
 	}
-	if (const char* k = getenv("VP8_GPU_KERNEL")) c->kernel_version = atoi(k) == 2 ? 2 : 1;
+	if (const char* k = getenv("VP8_GPU_KERNEL")) c->kernel_version = atoi(k) == 1 ? 1 : 2;
 	if (const char* w = getenv("VP8_GPU_WARPS")) c->tune_warps = atoi(w);
 	if (const char* w = getenv("VP8_GPU_IMAGES_PER_SM")) c->tune_imgs_per_sm = atoi(w);
 	*out = c;

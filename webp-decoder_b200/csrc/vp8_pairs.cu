@@ -39,6 +39,18 @@ static_assert(sizeof(HalfWs) % 16 == 0 && offsetof(HalfWs, res) % 16 == 0 && off
 __device__ __forceinline__ uint32_t ldcg32(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint32_t*>(p)); }
 __device__ __forceinline__ void stcg32(uint8_t* p, uint32_t v) { __stcg(reinterpret_cast<uint32_t*>(p), v); }
 
+#ifndef VP8P_BPRED_UNROLL
+#define VP8P_BPRED_UNROLL 16 // sub-block steps unrolled per loop iteration (16 = fully unrolled)
+#endif
+#ifndef VP8P_BLOCK_UNROLL
+#define VP8P_BLOCK_UNROLL 2 // 2: both 4x4 blocks of a lane unrolled, 1: looped
+#endif
+#ifndef VP8P_LF_LOOP
+#define VP8P_LF_LOOP 0 // 1: inner edges 4/8/12 as a loop, 0: unrolled
+#endif
+#define VP8P_STR2(x) #x
+#define VP8P_STR(x) VP8P_STR2(x)
+#define VP8P_UNROLL(n) _Pragma(VP8P_STR(unroll n))
 #ifndef VP8_PAIR_MIN_CTAS
 #define VP8_PAIR_MIN_CTAS(NW) ((NW) == 4 ? 7 : (NW) == 8 ? 3 : 1)
 #endif
@@ -294,7 +306,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 							}
 						}
 
-#pragma unroll
+						VP8P_UNROLL(VP8P_BLOCK_UNROLL)
 						for (int k = 0; k < 2; k++) {
 							const uint4 c0 = ws.coef[(2 * k) * 13 + hl], c1 = ws.coef[(2 * k + 1) * 13 + hl];
 							const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
@@ -391,7 +403,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 					if (__any_sync(FULL, bp)) {
 						const uint32_t sp = __ballot_sync(FULL, bp && (bmode <= 1 || bmode == 10));
 						const uint32_t spm = (sp | (sp >> 16)) & 0xffffu; // sub-blocks needing B_DC / B_TM / 128 in either half
-#pragma unroll
+						VP8P_UNROLL(VP8P_BPRED_UNROLL)
 						for (int s = 0; s < 16; s++) {
 							const int tile_c = ((s >> 2) * 4 + 1) * 24 + 4 + (s & 3) * 4; // pixel (0,0) of sub-block s
 							const int mode = __shfl_sync(FULL, bmode, hbit | s);
@@ -521,6 +533,29 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 								__syncwarp();
 							}
 							const bool any_in = __any_sync(FULL, f_in);
+#if VP8P_LF_LOOP
+							if (any_in) {
+								if (f_in) lf_across_columns<EDGE_INNER>(tc + cn * 12 + 4, lim_in, interior, hev_thr);
+#pragma unroll 1
+								for (int e = 4; e < 16; e += 4) {
+									if (f_in) lf_across_columns<EDGE_INNER>(ty + hl * 20 + e, lim_in, interior, hev_thr);
+									__syncwarp();
+								}
+							}
+							if (__any_sync(FULL, f_top)) {
+								if (f_top) lf_across_rows<EDGE_MB>(ty + hl, 20, lim_mb, interior, hev_thr);
+								if (f_top) lf_across_rows<EDGE_MB>(tc + cn, 12, lim_mb, interior, hev_thr);
+								__syncwarp();
+							}
+							if (any_in) {
+								if (f_in) lf_across_rows<EDGE_INNER>(tc + 4 * 12 + cn, 12, lim_in, interior, hev_thr);
+#pragma unroll 1
+								for (int e = 4; e < 16; e += 4) {
+									if (f_in) lf_across_rows<EDGE_INNER>(ty + e * 20 + hl, 20, lim_in, interior, hev_thr);
+									__syncwarp();
+								}
+							}
+#else
 							if (any_in) {
 								if (f_in) lf_across_columns<EDGE_INNER>(ty + hl * 20 + 4, lim_in, interior, hev_thr);
 								if (f_in) lf_across_columns<EDGE_INNER>(tc + cn * 12 + 4, lim_in, interior, hev_thr);
@@ -544,6 +579,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 								if (f_in) lf_across_rows<EDGE_INNER>(ty + 12 * 20 + hl, 20, lim_in, interior, hev_thr);
 								__syncwarp();
 							}
+#endif
 						} else {
 							// simple filter: luma only (vp8_loopfilter.c:228-244)
 							if (f_left) lf_across_columns<EDGE_SIMPLE>(ty + hl * 20, lim_mb, 0, 0);
