@@ -83,10 +83,11 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload):
+def ncu_traffic(workload, kernel_version):
     p = ROOT / "profiles" / "traffic.json"
     if p.exists():
-        return json.loads(p.read_text()).get(workload)
+        t = json.loads(p.read_text()).get(workload)
+        return t.get(str(kernel_version)) if isinstance(t, dict) else t
     return None
 
 
@@ -155,8 +156,8 @@ def gpu_arm(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx = W.Context(local, stream.cuda_stream)
-    if args.kernel:
-        ctx.set_kernel(args.kernel)
+    kernel_version = args.kernel or int(os.environ.get("VP8_GPU_KERNEL", "2") or 2)
+    ctx.set_kernel(kernel_version)
     if args.warps or args.images_per_sm:
         ctx.set_tuning(args.warps, args.images_per_sm)
 
@@ -271,7 +272,8 @@ def gpu_arm(args):
                        "cache": f"inputs {sum(820 * pf.frames[i].mb_total for i in order) / 1e9:.2f} GB per step, far larger than the 126 MB L2",
                        "launch": cfg, "parity_spot_check_vs_reference_digests": parity},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "kernel": "vp8_mb_wavefront",
+                         "traffic": ncu_traffic(args.workload, kernel_version), "peak_source": peak_src,
+                         "kernel": "vp8_mb_pairs" if kernel_version == 2 else "vp8_mb_wavefront",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": kern_n},
             "cpu_baseline": cpu,
             "e2e": e2e,
