@@ -117,6 +117,12 @@ int vp8_gpu_decode_ppm(vp8_gpu_ctx* ctx, const Vp8KeyFrameHeader* const* kf, con
                        uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk);
 size_t vp8_gpu_decode_bytes(const Vp8KeyFrameHeader* const* kf, int n, int ppm);
 
+/* m09 framing of an RGB24 image (what vp8_gpu_download_ppm / vp8_gpu_decode_ppm return behind the PPM header): the exact
+ * bytes reference yuv420_write_png_fd emits (yuv2rgb_png.c:208-364). out must hold vp8_gpu_png_bound bytes; returns the
+ * length, 0 on error. Host-side (stored deflate, slice-by-8 CRC-32, blocked Adler-32). */
+size_t vp8_gpu_png_bound(uint32_t width, uint32_t height);
+size_t vp8_gpu_png_frame(const uint8_t* rgb, uint32_t width, uint32_t height, uint8_t* out);
+
 /* Introspection for the benchmark. */
 int vp8_gpu_batch_size(const vp8_gpu_batch* b);
 uint64_t vp8_gpu_launch_count(const vp8_gpu_ctx* ctx); /* kernels launched by this context so far */

@@ -16,7 +16,7 @@ def test_reference_cli_linked_against_libvp8gpu(golden, tmp_path):
     if not exe.exists():
         pytest.skip("oracle/_ref/decoder_gpu not built (needs /root/reference at build time)")
     names = [n for n in sorted(golden) if golden[n]["width"] * golden[n]["height"] >= 64 * 40]
-    picks = names[::23][:5] + ["enc_noise_1x1_q10_rdo_lf.webp" if "enc_noise_1x1_q10_rdo_lf.webp" in golden else names[0]]
+    picks = names[::40][:3] + ["enc_noise_1x1_q10_rdo_lf.webp" if "enc_noise_1x1_q10_rdo_lf.webp" in golden else names[0]]
     checked = 0
     for n in picks:
         for flag, key in (("-yuv", "yuv"), ("-yuvf", "yuvf"), ("-ppm", "ppm"), ("-png", "png")):
@@ -25,4 +25,4 @@ def test_reference_cli_linked_against_libvp8gpu(golden, tmp_path):
             assert r.returncode == 0, (n, flag, r.stderr)
             assert hashlib.sha256(out.read_bytes()).hexdigest() == golden[n][key], (n, flag)
             checked += 1
-    assert checked == 4 * len(picks) >= 20
+    assert checked == 4 * len(picks) >= 12

@@ -36,6 +36,11 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True, cwd=str(HERE))
+    # batch CLI front end, linked against the library it sits next to
+    cli = HERE / "csrc" / "vp8gpu_batch.cpp"
+    if cli.exists():
+        subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", str(HERE / "vp8gpu_batch"), str(cli), "-L" + str(HERE), "-lvp8gpu",
+                        "-Wl,-rpath,$ORIGIN"], check=True, cwd=str(HERE))
     return LIB
 
 

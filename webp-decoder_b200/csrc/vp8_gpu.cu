@@ -1145,6 +1145,18 @@ size_t vp8_gpu_decode_bytes(const Vp8KeyFrameHeader* const* kf, int n, int ppm) 
 	return total;
 }
 
+size_t vp8_gpu_png_bound(uint32_t width, uint32_t height) {
+	const size_t raw = ((size_t)width * 3 + 1) * height;
+	return 8 + 25 + 12 + (2 + raw + 5 * ((raw + 65534) / 65535) + 4) + 12;
+}
+
+size_t vp8_gpu_png_frame(const uint8_t* rgb, uint32_t width, uint32_t height, uint8_t* out) {
+	std::vector<uint8_t> png;
+	if (!rgb || !out || !width || !height || png_frame(rgb, width, height, png)) return 0;
+	memcpy(out, png.data(), png.size());
+	return png.size();
+}
+
 uint64_t vp8_gpu_launch_count(const vp8_gpu_ctx* c) { return c ? c->launches : 0; }
 uint64_t vp8_gpu_h2d_bytes(const vp8_gpu_ctx* c) { return c ? c->h2d : 0; }
 uint64_t vp8_gpu_d2h_bytes(const vp8_gpu_ctx* c) { return c ? c->d2h : 0; }
