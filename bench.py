@@ -42,16 +42,18 @@ def algorithmic_bytes(w, h, workload):
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons DURING the timed region (profiling recipe's clocks line)."""
+    """nvidia-smi clocks and throttle reasons under load (profiling recipe's clocks line). Started before the warm-up;
+    samples whose timestamp falls inside the timed region are preferred, else all samples since the warm-up began
+    (the GPU runs the same kernel back to back through both)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.proc, self.t0, self.t1 = gpu_index, [], None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -60,20 +62,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_timed(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if not self.proc:
             return None
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        if not sm:
+        ok = [(ts, r) for ts, r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        inside = [(ts, r) for ts, r in ok if self.t0 is not None and self.t0 <= ts <= self.t1]
+        use, window = (inside, "timed region") if inside else (ok, "warm-up + timed region")
+        if not use:
             return None
+        sm = [float(r[1]) for _, r in use]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][2]), "samples": len(sm), "reasons": reasons}
+        reasons = sorted({n for _, r in use for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(use[0][1][2]), "power_w_max": max(float(r[3]) for _, r in use),
+                "samples": len(sm), "window": window, "reasons": reasons}
 
 
 def measured_peak():
@@ -186,19 +195,22 @@ def gpu_arm(args):
 
     # ---- (1) kernel stage, inputs resident in HBM
     batch = ctx.upload(kfs, frs)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step_resident(batch)
     ctx.kernel_time()
     sync_all()
-    sampler = ClockSampler(local)
-    sampler.start()
     l0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
         step_resident(batch)
     e1.record(stream)
     sync_all()
+    sampler.mark_timed(tw0, time.perf_counter())
     elapsed_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     launches = ctx.launches - l0
