@@ -652,7 +652,7 @@ int rgb_of_host_image(vp8_gpu_ctx* c, const Yuv420Image* img, std::vector<uint8_
 		if (e != cudaSuccess) rc = fail(EIO, "descriptor upload", e);
 	}
 	if (!rc) {
-		const uint32_t groups = ((w + 3) / 4) * h;
+		const uint32_t groups = ((w + 7) / 8) * h;
 		const int lrc = vp8_launch_rgb(d_desc, 1, (groups + 255) / 256, c->stream);
 		if (lrc) rc = fail(EIO, "rgb launch", (cudaError_t)lrc);
 		else c->launches++;
@@ -953,7 +953,7 @@ int vp8_gpu_rgb(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
 			d.stride_uv = m.mb_cols * 8;
 		}
 		d.rgb = b->d_rgb + m.rgb_off + kPpmSlot;
-		const uint32_t groups = ((m.width + 3) / 4) * m.height;
+		const uint32_t groups = ((m.width + 7) / 8) * m.height;
 		max_blocks = std::max(max_blocks, (groups + 255) / 256);
 	}
 	CU(cudaMemcpyAsync(b->d_rgbdesc, h.data(), sizeof(Vp8RgbDesc) * b->n, cudaMemcpyHostToDevice, b->stream));

@@ -668,7 +668,8 @@ __global__ void __launch_bounds__(NW * 32, VP8_MIN_CTAS(NW)) vp8_mb_wavefront(co
 
 // ------------------------------------------------------------------------------------------------ m08: YUV -> RGB
 // Reference mult_hi / vp8_clip8 / vp8_yuv_to_rgb (yuv2rgb_ppm.c:19-41).
-__device__ __forceinline__ uint32_t fix_clip(int v) { return (v & ~16383) == 0 ? (uint32_t)(v >> 6) : (v < 0 ? 0u : 255u); }
+// (v & ~16383) == 0 ? v >> 6 : (v < 0 ? 0 : 255)  ==  clamp(v, 0, 16383) >> 6   (16383 >> 6 == 255)
+__device__ __forceinline__ uint32_t fix_clip(int v) { return (uint32_t)__vimin_s32_relu(v, 16383) >> 6; }
 
 __device__ __forceinline__ void yuv_to_rgb(int Y, int U, int V, uint32_t& R, uint32_t& G, uint32_t& B) {
 	const int yy = (Y * 19077) >> 8;
@@ -685,29 +686,12 @@ __device__ __forceinline__ int fancy(int Nn, int Nf, int Fn, int Ff) {
 }
 
 constexpr int kRgbThreads = 256;
-constexpr int kRgbPxPerThread = 4;
 
-// One thread = 4 horizontally adjacent pixels of one image. grid = (blocks per image, images).
-__global__ void __launch_bounds__(kRgbThreads) vp8_i420_to_rgb(const Vp8RgbDesc* __restrict__ descs) {
-	const Vp8RgbDesc d = descs[blockIdx.y];
-	const uint32_t w = d.width, h = d.height, cw = (w + 1) >> 1, ch = (h + 1) >> 1;
-	const uint32_t groups_per_row = (w + kRgbPxPerThread - 1) / kRgbPxPerThread;
-	const uint32_t g = blockIdx.x * kRgbThreads + threadIdx.x;
-	if (g >= groups_per_row * h) return;
-	const uint32_t py = g / groups_per_row, px0 = (g % groups_per_row) * kRgbPxPerThread;
-
-	// near / far chroma rows (reference yuv420_write_ppm_fd row pairing, yuv2rgb_ppm.c:164-201)
-	const uint32_t nrow = py >> 1;
-	uint32_t frow;
-	if (py == 0) frow = 0;
-	else if (py & 1) frow = min(nrow + 1, ch - 1);
-	else frow = nrow - 1;
-	const uint8_t* un = d.u + (size_t)nrow * d.stride_uv;
-	const uint8_t* uf = d.u + (size_t)frow * d.stride_uv;
-	const uint8_t* vn = d.v + (size_t)nrow * d.stride_uv;
-	const uint8_t* vf = d.v + (size_t)frow * d.stride_uv;
+// 4 pixels px0..px0+3 of row py, any geometry (row ends, odd widths, unaligned planes). px0 is a multiple of 4.
+__device__ __noinline__ void rgb_group4(const Vp8RgbDesc& d, uint32_t py, uint32_t px0, const uint8_t* un, const uint8_t* uf,
+                                           const uint8_t* vn, const uint8_t* vf) {
+	const uint32_t w = d.width, cw = (w + 1) >> 1;
 	const uint8_t* yrow = d.y + (size_t)py * d.stride_y;
-
 	// chroma columns j-1 .. j+2 with j = px0/2 cover all four pixels; clamp indices (clamped taps are unused)
 	const int j = (int)(px0 >> 1);
 	int un4[4], uf4[4], vn4[4], vf4[4];
@@ -752,6 +736,84 @@ __global__ void __launch_bounds__(kRgbThreads) vp8_i420_to_rgb(const Vp8RgbDesc*
 	} else {
 		for (uint32_t k = 0; k < 12 && px0 * 3 + k < w * 3; k++) dst[k] = out[k];
 	}
+}
+
+// One thread = 8 horizontally adjacent pixels of one image. grid = (blocks per image, images).
+// Interior groups of aligned images take the vector path: one 8-byte luma load, one 4-byte load per chroma row and plane
+// (+ the two neighbour bytes), 24 output bytes as three 8-byte stores. Row ends and unaligned images fall back to
+// rgb_group4, which handles every geometry.
+__global__ void __launch_bounds__(kRgbThreads, 4) vp8_i420_to_rgb(const Vp8RgbDesc* __restrict__ descs) {
+	const Vp8RgbDesc d = descs[blockIdx.y];
+	const uint32_t w = d.width, h = d.height, cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+	const uint32_t groups_per_row = (w + 7) / 8;
+	const uint32_t g = blockIdx.x * kRgbThreads + threadIdx.x;
+	if (g >= groups_per_row * h) return;
+	const uint32_t py = g / groups_per_row, gx = g % groups_per_row, px0 = gx * 8;
+
+	// near / far chroma rows (reference yuv420_write_ppm_fd row pairing, yuv2rgb_ppm.c:164-201)
+	const uint32_t nrow = py >> 1;
+	uint32_t frow;
+	if (py == 0) frow = 0;
+	else if (py & 1) frow = min(nrow + 1, ch - 1);
+	else frow = nrow - 1;
+	const uint8_t* un = d.u + (size_t)nrow * d.stride_uv;
+	const uint8_t* uf = d.u + (size_t)frow * d.stride_uv;
+	const uint8_t* vn = d.v + (size_t)nrow * d.stride_uv;
+	const uint8_t* vf = d.v + (size_t)frow * d.stride_uv;
+
+	const bool aligned = ((reinterpret_cast<uintptr_t>(d.y) | d.stride_y) & 7) == 0 &&
+	                     ((reinterpret_cast<uintptr_t>(d.u) | reinterpret_cast<uintptr_t>(d.v) | d.stride_uv) & 3) == 0 &&
+	                     (reinterpret_cast<uintptr_t>(d.rgb) & 7) == 0 && (w & 7) == 0;
+	if (!aligned) {
+		rgb_group4(d, py, px0, un, uf, vn, vf);
+		if (px0 + 4 < w) rgb_group4(d, py, px0 + 4, un, uf, vn, vf);
+		return;
+	}
+
+	const uint32_t j = px0 >> 1; // first chroma column of the group, a multiple of 4; columns j-1 .. j+4 are needed
+	const bool first = gx == 0, last = gx == groups_per_row - 1;
+	const uint2 yw = *reinterpret_cast<const uint2*>(d.y + (size_t)py * d.stride_y + px0);
+	int n[2][6], f[2][6]; // [plane][column j-1+i]; the out-of-row neighbours of the first / last group are never used
+	{
+		const uint8_t* N[2] = {un, vn};
+		const uint8_t* F[2] = {uf, vf};
+#pragma unroll
+		for (int p = 0; p < 2; p++) {
+			const uint32_t a = *reinterpret_cast<const uint32_t*>(N[p] + j), b = *reinterpret_cast<const uint32_t*>(F[p] + j);
+			n[p][0] = first ? 0 : N[p][j - 1];
+			f[p][0] = first ? 0 : F[p][j - 1];
+			n[p][5] = last ? 0 : N[p][j + 4];
+			f[p][5] = last ? 0 : F[p][j + 4];
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				n[p][1 + i] = (a >> (8 * i)) & 255;
+				f[p][1 + i] = (b >> (8 * i)) & 255;
+			}
+		}
+	}
+	uint32_t o[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		// even pixel: near column j+k/2, far one to the left; odd pixel: near column j+(k-1)/2, far one to the right
+		const int ni = (k >> 1) + 1, fi = (k & 1) ? ni + 1 : ni - 1;
+		int U = fancy(n[0][ni], n[0][fi], f[0][ni], f[0][fi]);
+		int V = fancy(n[1][ni], n[1][fi], f[1][ni], f[1][fi]);
+		// the first pixel of a row and (even widths) the last one have no far column: (3 near + far-row + 2) >> 2
+		if ((k == 0 && first) || (k == 7 && last)) {
+			U = (3 * n[0][ni] + f[0][ni] + 2) >> 2;
+			V = (3 * n[1][ni] + f[1][ni] + 2) >> 2;
+		}
+		const int Y = (k < 4 ? yw.x >> (8 * k) : yw.y >> (8 * (k - 4))) & 255;
+		uint32_t R, G, B;
+		yuv_to_rgb(Y, U, V, R, G, B);
+		o[(3 * k) >> 2] |= R << (8 * ((3 * k) & 3));
+		o[(3 * k + 1) >> 2] |= G << (8 * ((3 * k + 1) & 3));
+		o[(3 * k + 2) >> 2] |= B << (8 * ((3 * k + 2) & 3));
+	}
+	uint2* dst = reinterpret_cast<uint2*>(d.rgb + ((size_t)py * w + px0) * 3);
+	dst[0] = make_uint2(o[0], o[1]);
+	dst[1] = make_uint2(o[2], o[3]);
+	dst[2] = make_uint2(o[4], o[5]);
 }
 
 template <int NW, bool RECON, bool FILTER>
