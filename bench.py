@@ -193,6 +193,20 @@ def gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # ---- host front end (m01 + m02 + m05 equivalent): what feeding the GPU from .webp bytes costs on this box's cores
+    host_fe = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        datas = [Path(f).read_bytes() for f in files] * 16
+        threads = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        tmp = P.parse_batch(datas, threads=threads)
+        dt = time.perf_counter() - t0
+        host_fe = {"value": sum(tmp.kfs[i].width * tmp.kfs[i].height for i in range(tmp.n)) / dt / 1e6, "unit": "Mpixel/s",
+                   "threads": threads, "frames": tmp.n,
+                   "note": "vp8_parse_batch (container + header + bool/token decode), one image per host thread; serial per frame, "
+                           "so an end-to-end run that starts from .webp bytes is bound by this, not by the GPU stage"}
+        tmp.free()
+
     # ---- (1) kernel stage, inputs resident in HBM
     batch = ctx.upload(kfs, frs)
     torch.cuda.synchronize()
@@ -288,6 +302,7 @@ def gpu_arm(args):
                          "kernel": "vp8_mb_pairs" if kernel_version == 2 else "vp8_mb_wavefront",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": kern_n},
             "cpu_baseline": cpu,
+            "host_front_end": host_fe,
             "e2e": e2e,
             "gpu_launches": launches,
             "clocks": clocks,
