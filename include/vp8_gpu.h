@@ -67,6 +67,11 @@ int vp8_gpu_set_tuning(vp8_gpu_ctx* ctx, int warps_per_image, int images_per_sm)
  * two rows per warp (vp8_pairs.cu). Both are bit-exact; the environment variable VP8_GPU_KERNEL presets it. */
 int vp8_gpu_set_kernel(vp8_gpu_ctx* ctx, int version);
 
+/* Transport of the pipelined calls (vp8_gpu_decode_*): compact != 0 (default) ships each frame without its all-zero
+ * 4x4 blocks (per-macroblock presence mask + packed blocks, built by host_threads workers; 0 = all cores), which is
+ * what the host->device link is bound by; compact == 0 ships the dense arrays as they are. */
+int vp8_gpu_set_transport(vp8_gpu_ctx* ctx, int compact, int host_threads);
+
 /* Pinned host memory: frames whose arrays live here are copied to the device without staging. */
 void* vp8_gpu_host_alloc(size_t bytes);
 void vp8_gpu_host_free(void* p);

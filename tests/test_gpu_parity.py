@@ -216,15 +216,26 @@ def test_pipelined_decode_matches_digests(lib, gpu_ctx, golden, parsed_golden):
     names = sorted(golden)
     kfs = [parsed_golden[n][0] for n in names]
     frs = [parsed_golden[n][1] for n in names]
-    for ppm, key, filtered in ((False, "yuvf", True), (False, "yuv", False), (True, "ppm", True)):
-        need = gpu_ctx.decode_bytes(kfs, ppm=ppm)
-        pinned = lib.PinnedBuffer(need)
-        for out in (pinned.array, np.empty(need, np.uint8)):
-            out[:] = 0xAA
-            offs, sizes = gpu_ctx.decode_into(kfs, frs, out, filtered=filtered, ppm=ppm, chunk=7)
-            bad = [n for n, o, s in zip(names, offs, sizes) if sha(out[int(o):int(o) + int(s)]) != golden[n][key]]
-            assert not bad, (key, len(bad), bad[:4])
-        pinned.close()
+    try:
+        for compact in (True, False):  # compact transport (zero blocks dropped on the host) and dense transport
+            gpu_ctx.set_transport(compact, 3)
+            h2d0 = gpu_ctx.h2d_bytes
+            for ppm, key, filtered in ((False, "yuvf", True), (False, "yuv", False), (True, "ppm", True)):
+                need = gpu_ctx.decode_bytes(kfs, ppm=ppm)
+                pinned = lib.PinnedBuffer(need)
+                for out in (pinned.array, np.empty(need, np.uint8)):
+                    out[:] = 0xAA
+                    offs, sizes = gpu_ctx.decode_into(kfs, frs, out, filtered=filtered, ppm=ppm, chunk=7)
+                    bad = [n for n, o, s in zip(names, offs, sizes) if sha(out[int(o):int(o) + int(s)]) != golden[n][key]]
+                    assert not bad, (compact, key, len(bad), bad[:4])
+                pinned.close()
+            moved = gpu_ctx.h2d_bytes - h2d0
+            if compact:
+                compact_bytes = moved
+            else:
+                assert compact_bytes < 0.6 * moved, (compact_bytes, moved)  # the corpus is mostly sparse
+    finally:
+        gpu_ctx.set_transport(True, 0)
     with pytest.raises(OSError):
         gpu_ctx.decode_into(kfs, frs, np.empty(10, np.uint8))
 

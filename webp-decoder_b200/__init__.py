@@ -42,7 +42,7 @@ EXPORTS = [
     "vp8_gpu_batch_size", "vp8_gpu_launch_count", "vp8_gpu_h2d_bytes", "vp8_gpu_d2h_bytes",
     "vp8_gpu_last_launch_config", "vp8_gpu_frame_params", "vp8_gpu_kernel_time",
     "vp8_gpu_decode_i420", "vp8_gpu_decode_ppm", "vp8_gpu_decode_bytes", "vp8_gpu_set_kernel",
-    "vp8_gpu_png_bound", "vp8_gpu_png_frame",
+    "vp8_gpu_png_bound", "vp8_gpu_png_frame", "vp8_gpu_set_transport",
 ]
 
 _lib = None
@@ -70,6 +70,7 @@ def load_library() -> C.CDLL:
     L.vp8_gpu_last_error.restype = C.c_char_p
     L.vp8_gpu_set_tuning.argtypes = [vp, C.c_int, C.c_int]
     L.vp8_gpu_set_kernel.argtypes = [vp, C.c_int]
+    L.vp8_gpu_set_transport.argtypes = [vp, C.c_int, C.c_int]
     L.vp8_gpu_host_alloc.argtypes = [sz]
     L.vp8_gpu_host_alloc.restype = vp
     L.vp8_gpu_host_free.argtypes = [vp]
@@ -209,6 +210,10 @@ class Context:
     def set_kernel(self, version: int):
         """1 = warp per macroblock, 2 = half-warp per macroblock (two rows per warp)."""
         _check(self._L.vp8_gpu_set_kernel(self._h, version), "vp8_gpu_set_kernel")
+
+    def set_transport(self, compact: bool = True, host_threads: int = 0):
+        """Pipelined calls: ship frames without their all-zero 4x4 blocks (compacted by host threads) or dense."""
+        _check(self._L.vp8_gpu_set_transport(self._h, int(compact), host_threads), "vp8_gpu_set_transport")
 
     def sync(self):
         _check(self._L.vp8_gpu_sync(self._h), "vp8_gpu_sync")

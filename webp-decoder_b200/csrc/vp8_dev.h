@@ -39,7 +39,14 @@ struct Vp8ImgDesc {
 	// (vp8_loopfilter.c:166-199).
 	uint8_t lf[4][2][4];
 	uint8_t lf_simple;
-	uint8_t pad_[7];
+	// Compact coefficient layout (vp8_pairs.cu only). When set, the four coeff_* pointers are re-purposed:
+	//   coeff_y  -> packed non-zero 4x4 blocks, 32 bytes each, in (macroblock, block) order
+	//   coeff_u  -> uint32 mb_mask[mb]: bit b set = block b of the macroblock is present
+	//               (b = 0..15 luma raster, 16..19 U, 20..23 V, 24 Y2)
+	//   coeff_v  -> uint32 mb_first[mb]: index (in 32-byte blocks) of the macroblock's first packed block
+	// Absent blocks are all-zero. Built on the host by compact_frame() in vp8_gpu.cu.
+	uint8_t compact;
+	uint8_t pad_[6];
 };
 
 // Work item of the RGB kernel: one image, tight I420 in, tight RGB24 out.

@@ -12,7 +12,9 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -79,6 +81,10 @@ struct vp8_gpu_ctx {
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spare;
 	cudaStream_t pipe[3] = {nullptr, nullptr, nullptr}; // chunk pipeline of vp8_gpu_decode_*
 	cudaEvent_t pipe_ev = nullptr;
+	uint8_t* cstage[3] = {nullptr, nullptr, nullptr};   // pinned staging of compacted chunks, one per pipeline slot
+	size_t cstage_bytes[3] = {0, 0, 0};
+	int host_threads = 0;                               // workers compacting frames (0 = all cores, at most 32)
+	bool compact_transport = true;                      // pipelined decode ships coefficients without their all-zero blocks
 };
 
 namespace {
@@ -88,6 +94,7 @@ struct FrameMeta {
 	size_t in_off[9];   // coeff_y, coeff_u, coeff_v, coeff_y2, bmode, ymode, uv_mode, segment_id, has_coeff
 	const uint8_t* span_src = nullptr; // non-null: the arrays sit in one host block, copied with a single transfer
 	size_t span_off = 0, span_bytes = 0;
+	bool compact = false;              // compact layout: in_off[0..2] = packed blocks, mb_mask, mb_first (see Vp8ImgDesc)
 	bool has_seg, has_hc;
 	size_t tight_off;   // tight I420 (Y|U|V) within d_tight
 	size_t pad_off[3];  // padded planes within d_pad
@@ -528,6 +535,7 @@ int push_descs(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layout) {
 		memcpy(d.dq, m.dq, sizeof(d.dq));
 		memcpy(d.lf, m.lf, sizeof(d.lf));
 		d.lf_simple = m.lf_simple;
+		d.compact = m.compact ? 1 : 0;
 	}
 	// pageable source: the runtime stages it before returning, so the vector may die right after
 	CU(cudaMemcpyAsync(b->d_desc, h.data(), sizeof(Vp8ImgDesc) * b->n, cudaMemcpyHostToDevice, b->stream));
@@ -813,6 +821,8 @@ int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out) {
 	}
 	if (const char* k = getenv("VP8_GPU_KERNEL")) c->kernel_version = atoi(k) == 1 ? 1 : 2;
 	if (const char* w = getenv("VP8_GPU_WARPS")) c->tune_warps = atoi(w);
+	if (const char* w = getenv("VP8_GPU_HOST_THREADS")) c->host_threads = atoi(w);
+	if (const char* w = getenv("VP8_GPU_COMPACT")) c->compact_transport = atoi(w) != 0;
 	if (const char* w = getenv("VP8_GPU_IMAGES_PER_SM")) c->tune_imgs_per_sm = atoi(w);
 	*out = c;
 	return 0;
@@ -834,6 +844,8 @@ void vp8_gpu_destroy(vp8_gpu_ctx* c) {
 		}
 	for (auto& p : c->pipe)
 		if (p) cudaStreamDestroy(p);
+	for (auto& p : c->cstage)
+		if (p) cudaFreeHost(p);
 	if (c->pipe_ev) cudaEventDestroy(c->pipe_ev);
 	if (c->own_stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -851,6 +863,13 @@ int vp8_gpu_set_tuning(vp8_gpu_ctx* c, int warps_per_image, int images_per_sm) {
 		return fail(EINVAL, "bad tuning");
 	c->tune_warps = warps_per_image;
 	c->tune_imgs_per_sm = images_per_sm;
+	return 0;
+}
+
+int vp8_gpu_set_transport(vp8_gpu_ctx* c, int compact, int host_threads) {
+	if (!c || host_threads < 0) return fail(EINVAL, "bad transport options");
+	c->compact_transport = compact != 0;
+	c->host_threads = host_threads;
 	return 0;
 }
 
@@ -1054,6 +1073,162 @@ int vp8_gpu_download_images(vp8_gpu_ctx* c, vp8_gpu_batch* b, Yuv420Image* out) 
 	return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ compact transport
+// Most 4x4 blocks of a real frame carry no coefficient at all. The dense arrays of Vp8DecodedFrame (800 bytes per
+// macroblock) are what the host->device link is bound by, so the pipelined path ships a compact frame instead:
+//   [mb_mask u32 x mb][mb_first u32 x mb][ymode][uv_mode][segment_id][has_coeff][bmode 16 x mb][pad to 32][packed blocks]
+// mb_mask bit b = block b present (0..15 luma, 16..19 U, 20..23 V, 24 Y2); mb_first = index of the macroblock's first packed
+// 32-byte block. vp8_mb_pairs reads this layout directly, so there is no expansion pass and HBM reads shrink as well.
+struct CompactLayout {
+	size_t o_mask, o_first, o_ymode, o_uv, o_seg, o_hc, o_bmode, o_packed, worst;
+};
+CompactLayout compact_layout(size_t mb) {
+	CompactLayout L;
+	L.o_mask = 0;
+	L.o_first = 4 * mb;
+	L.o_ymode = 8 * mb;
+	L.o_uv = 9 * mb;
+	L.o_seg = 10 * mb;
+	L.o_hc = 11 * mb;
+	L.o_bmode = 12 * mb;
+	L.o_packed = align_up(28 * mb, 32);
+	L.worst = align_up(L.o_packed + 800 * mb);
+	return L;
+}
+
+inline bool block_nonzero(const int16_t* p) {
+	uint64_t a, b, c, d;
+	memcpy(&a, p, 8);
+	memcpy(&b, p + 4, 8);
+	memcpy(&c, p + 8, 8);
+	memcpy(&d, p + 12, 8);
+	return (a | b | c | d) != 0;
+}
+
+// Returns the number of bytes of dst that are in use.
+size_t compact_frame(const Vp8DecodedFrame* f, uint8_t* dst) {
+	const size_t mb = (size_t)f->mb_cols * f->mb_rows;
+	const CompactLayout L = compact_layout(mb);
+	uint32_t* mask = reinterpret_cast<uint32_t*>(dst + L.o_mask);
+	uint32_t* first = reinterpret_cast<uint32_t*>(dst + L.o_first);
+	uint8_t* out = dst + L.o_packed;
+	uint32_t count = 0;
+	for (size_t i = 0; i < mb; i++) {
+		uint32_t m = 0;
+		first[i] = count;
+		const int16_t* src[4] = {f->coeff_y + i * 256, f->coeff_u + i * 64, f->coeff_v + i * 64, f->coeff_y2 + i * 16};
+		const int nblk[4] = {16, 4, 4, 1}, bit[4] = {0, 16, 20, 24};
+		for (int g = 0; g < 4; g++)
+			for (int b = 0; b < nblk[g]; b++) {
+				const int16_t* p = src[g] + 16 * b;
+				if (block_nonzero(p)) {
+					memcpy(out + (size_t)count * 32, p, 32);
+					count++;
+					m |= 1u << (bit[g] + b);
+				}
+			}
+		mask[i] = m;
+	}
+	memcpy(dst + L.o_ymode, f->ymode, mb);
+	memcpy(dst + L.o_uv, f->uv_mode, mb);
+	if (f->segmentation_enabled && f->segment_id) memcpy(dst + L.o_seg, f->segment_id, mb);
+	if (f->has_coeff) memcpy(dst + L.o_hc, f->has_coeff, mb);
+	memcpy(dst + L.o_bmode, f->bmode, 16 * mb);
+	return L.o_packed + (size_t)count * 32;
+}
+
+// A batch whose input arena holds compact frames: compacted by host threads into the pinned staging slot, then one
+// transfer per frame of just the bytes in use.
+int batch_create_compact(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* fr, int n, int slot,
+                         cudaStream_t st, vp8_gpu_batch** out) {
+	vp8_gpu_batch* b = new (std::nothrow) vp8_gpu_batch;
+	if (!b) return fail(ENOMEM, "batch");
+	b->n = n;
+	b->stream = st;
+	b->meta.resize(n);
+	size_t in = 0, tight = 0, rgb = 0;
+	std::vector<size_t> frame_off(n);
+	for (int i = 0; i < n; i++) {
+		FrameMeta& m = b->meta[i];
+		const Vp8DecodedFrame* f = fr[i];
+		m.width = kf[i]->width;
+		m.height = kf[i]->height;
+		m.mb_cols = f->mb_cols;
+		m.mb_rows = f->mb_rows;
+		const size_t mb = (size_t)m.mb_cols * m.mb_rows;
+		const CompactLayout L = compact_layout(mb);
+		m.has_seg = f->segmentation_enabled && f->segment_id;
+		m.has_hc = f->has_coeff != nullptr;
+		m.compact = true;
+		frame_off[i] = in;
+		m.in_off[0] = in + L.o_packed; // packed blocks
+		m.in_off[1] = in + L.o_mask;   // mb_mask
+		m.in_off[2] = in + L.o_first;  // mb_first
+		m.in_off[3] = in;              // (coeff_y2 slot unused)
+		m.in_off[4] = in + L.o_bmode;
+		m.in_off[5] = in + L.o_ymode;
+		m.in_off[6] = in + L.o_uv;
+		m.in_off[7] = in + L.o_seg;
+		m.in_off[8] = in + L.o_hc;
+		in += L.worst;
+		const size_t cw = (m.width + 1) / 2, ch = (m.height + 1) / 2;
+		m.tight_off = tight;
+		tight += align_up((size_t)m.width * m.height + 2 * cw * ch);
+		m.pad_off[0] = m.pad_off[1] = m.pad_off[2] = 0;
+		m.rgb_off = rgb;
+		rgb += align_up(kPpmSlot + (size_t)m.width * m.height * 3);
+		frame_params(f, m.dq, m.lf);
+		m.lf_simple = f->lf_use_simple;
+		m.any_filter = false;
+		for (int s = 0; s < (m.has_seg ? 4 : 1); s++)
+			for (int k = 0; k < 2; k++) m.any_filter |= m.lf[s][k][0] != 0;
+		b->max_mb_cols = std::max<int>(b->max_mb_cols, m.mb_cols);
+	}
+	b->in_bytes = in;
+	b->tight_bytes = tight;
+	b->pad_bytes = 0;
+	b->rgb_bytes = rgb;
+	// pinned staging slot, grown on demand
+	if (c->cstage_bytes[slot] < in) {
+		if (c->cstage[slot]) cudaFreeHost(c->cstage[slot]);
+		c->cstage[slot] = nullptr;
+		c->cstage_bytes[slot] = 0;
+		cudaError_t e = cudaHostAlloc((void**)&c->cstage[slot], in, cudaHostAllocDefault);
+		if (e != cudaSuccess) {
+			delete b;
+			return fail(ENOMEM, "pinned staging for compact transport", e);
+		}
+		c->cstage_bytes[slot] = in;
+	}
+	if (dev_alloc(c, in, (void**)&b->d_in) || dev_alloc(c, sizeof(Vp8ImgDesc) * n, (void**)&b->d_desc)) {
+		batch_destroy(c, b);
+		return -1;
+	}
+	// compaction on host threads, one frame per thread at a time
+	uint8_t* stage = c->cstage[slot];
+	std::vector<size_t> used(n);
+	int threads = c->host_threads > 0 ? c->host_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+	threads = std::min(threads, n);
+	std::atomic<int> next{0};
+	auto work = [&]() {
+		for (int i; (i = next.fetch_add(1)) < n;) used[i] = compact_frame(fr[i], stage + frame_off[i]);
+	};
+	std::vector<std::thread> pool;
+	for (int t = 1; t < threads; t++) pool.emplace_back(work);
+	work();
+	for (auto& t : pool) t.join();
+	for (int i = 0; i < n; i++) {
+		cudaError_t e = cudaMemcpyAsync(b->d_in + frame_off[i], stage + frame_off[i], used[i], cudaMemcpyHostToDevice, st);
+		if (e != cudaSuccess) {
+			batch_destroy(c, b);
+			return fail(EIO, "compact frame upload", e);
+		}
+		c->h2d += used[i];
+	}
+	*out = b;
+	return 0;
+}
+
 // Chunked pipeline: chunk k's host->device copies, kernels and device->host copy run on internal stream k % 3, so the
 // copy engines (one per direction) and the SMs work on different chunks at the same time. Blocking: returns when
 // dst holds every frame. Output layout = the layout of one big batch (frame i at offsets[i], 256-byte aligned).
@@ -1063,7 +1238,7 @@ static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, 
 	for (int i = 0; i < n; i++)
 		if (validate_frame(kf[i], frames[i], true)) return -1;
 	CU(cudaSetDevice(c->device));
-	if (chunk <= 0) chunk = 128;
+	if (chunk <= 0) chunk = 64;
 	// global layout
 	std::vector<size_t> off(n + 1, 0);
 	for (int i = 0; i < n; i++) {
@@ -1088,7 +1263,8 @@ static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, 
 			inflight[slot] = nullptr;
 		}
 		vp8_gpu_batch* b = nullptr;
-		rc = batch_create(c, kf + first, frames + first, cnt, true, &b, c->pipe[slot]);
+		if (c->compact_transport && c->kernel_version == 2) rc = batch_create_compact(c, kf + first, frames + first, cnt, slot, c->pipe[slot], &b);
+		else rc = batch_create(c, kf + first, frames + first, cnt, true, &b, c->pipe[slot]);
 		if (rc) break;
 		inflight[slot] = b;
 		rc = vp8_gpu_run(c, b, filtered, VP8_GPU_TIGHT);

@@ -39,6 +39,25 @@ static_assert(sizeof(HalfWs) % 16 == 0 && offsetof(HalfWs, res) % 16 == 0 && off
 __device__ __forceinline__ uint32_t ldcg32(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint32_t*>(p)); }
 __device__ __forceinline__ void stcg32(uint8_t* p, uint32_t v) { __stcg(reinterpret_cast<uint32_t*>(p), v); }
 
+// Compact layout: request this lane's (up to two) present blocks of one macroblock; returns their presence bits.
+__device__ __forceinline__ uint32_t fetch_compact(HalfWs& ws, const uint8_t* packed, uint32_t mask, uint32_t first, int bit0, int hl) {
+	if (hl >= 13) return 0;
+	const uint32_t nz = (mask >> bit0) & (hl < 12 ? 3u : 1u);
+	uint32_t idx = first + __popc(mask & ((1u << bit0) - 1u));
+	if (nz & 1) {
+		const uint8_t* src = packed + (size_t)idx * 32;
+		cp_async16(&ws.coef[0 * 13 + hl], src);
+		cp_async16(&ws.coef[1 * 13 + hl], src + 16);
+		idx++;
+	}
+	if (nz & 2) {
+		const uint8_t* src = packed + (size_t)idx * 32;
+		cp_async16(&ws.coef[2 * 13 + hl], src);
+		cp_async16(&ws.coef[3 * 13 + hl], src + 16);
+	}
+	return nz;
+}
+
 #ifndef VP8P_BPRED_UNROLL
 #define VP8P_BPRED_UNROLL 16 // sub-block steps unrolled per loop iteration (16 = fully unrolled)
 #endif
@@ -100,6 +119,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 	const int tl_by = tl_luma ? (hl >> 1) * 4 : (hl & 1) * 4;   // block row offset inside the plane tile
 	const int tl_bx0 = tl_luma ? (hl & 1) * 8 : 0;              // column offset of the lane's first block (second: +4)
 	const int cstep = tl_luma ? 256 : (tl_chroma ? 64 : 16);    // int16 per macroblock in this lane's coefficient stream
+	const int bit0 = tl_luma ? 2 * hl : (hl < 10 ? 16 + 2 * (hl - 8) : (hl < 12 ? 20 + 2 * (hl - 10) : 24)); // compact layout: mask bit of the lane's first block
 	//   B_PRED: lane = pixel of the current sub-block
 	const int px_r = hl >> 2, px_c = hl & 3;
 	const int e_dy = hl <= 2 ? 3 : (hl <= 5 ? 5 - hl : -1);
@@ -134,6 +154,12 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 		const uint8_t* const g_ymode = sd->ymode;
 		const uint8_t* const g_seg = sd->segment_id;
 		const uint8_t* const g_hc = sd->has_coeff;
+		// compact layout: packed blocks / per-macroblock mask / first-block index live behind the re-purposed coeff pointers;
+		// they are re-read from the shared-memory descriptor at each use to keep registers free
+#define G_COMPACT (sd->compact != 0)
+#define G_PACKED reinterpret_cast<const uint8_t*>(sd->coeff_y)
+#define G_MASK reinterpret_cast<const uint32_t*>(sd->coeff_u)
+#define G_FIRST reinterpret_cast<const uint32_t*>(sd->coeff_v)
 
 		for (int p = warp; 2 * p < rows; p += NW) {
 			const int y = 2 * p + half;
@@ -144,6 +170,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 			// ---- row start: out-of-frame left neighbours (129) and corner (127 on the top row, else 129)
 			const int16_t* cptr = sd->coeff_y2;
 			int x_pref = 0; // next macroblock column whose coefficients have not been requested yet
+			uint32_t staged_nz = 3; // compact layout: which of the lane's two staged blocks are present (dense layout: both)
 			if (RECON) {
 				ws.lcol[hl] = 129;
 				ws.lcol[16 + hl] = 129;
@@ -154,14 +181,16 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 				if (hl == 0) ws.rt_y[3] = corner;
 				if (hl == 1) ws.rt_u[3] = corner;
 				if (hl == 2) ws.rt_v[3] = corner;
-				if (row_ok) {
+				if (row_ok && !G_COMPACT) {
 					if (tl_luma) cptr = sd->coeff_y + (mb_row0 * 16 + 2 * hl) * 16;
 					else if (hl < 10) cptr = sd->coeff_u + (mb_row0 * 4 + 2 * (hl - 8)) * 16;
 					else if (hl < 12) cptr = sd->coeff_v + (mb_row0 * 4 + 2 * (hl - 10)) * 16;
 					else cptr = sd->coeff_y2 + mb_row0 * 16;
 				}
 				if (half == 0 && row_ok) { // row y starts at step 0: its first macroblock's blocks go on their way now
-					if (hl < 13) {
+					if (G_COMPACT) {
+						staged_nz = fetch_compact(ws, G_PACKED, G_MASK[mb_row0], G_FIRST[mb_row0], bit0, hl);
+					} else if (hl < 13) {
 						cp_async16(&ws.coef[0 * 13 + hl], cptr);
 						cp_async16(&ws.coef[1 * 13 + hl], cptr + 8);
 						if (hl < 12) {
@@ -250,7 +279,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 					if (v && !bpred && hl == 12) {
 						const uint4 c0 = ws.coef[0 * 13 + 12], c1 = ws.coef[1 * 13 + 12];
 						uint4* z = reinterpret_cast<uint4*>(ws.res[0]);
-						if ((c0.x | c0.y | c0.z | c0.w | c1.x | c1.y | c1.z | c1.w) == 0) {
+						if (!(staged_nz & 1) || (c0.x | c0.y | c0.z | c0.w | c1.x | c1.y | c1.z | c1.w) == 0) {
 							z[0] = make_uint4(0, 0, 0, 0);
 							z[1] = make_uint4(0, 0, 0, 0);
 						} else {
@@ -308,7 +337,11 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 
 						VP8P_UNROLL(VP8P_BLOCK_UNROLL)
 						for (int k = 0; k < 2; k++) {
-							const uint4 c0 = ws.coef[(2 * k) * 13 + hl], c1 = ws.coef[(2 * k + 1) * 13 + hl];
+							uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+							if (staged_nz & (1u << k)) {
+								c0 = ws.coef[(2 * k) * 13 + hl];
+								c1 = ws.coef[(2 * k + 1) * 13 + hl];
+							}
 							const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 							const int bi = 2 * hl + k; // luma block index (raster) when tl_luma
 							int r[16];
@@ -385,7 +418,9 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 
 					// ---- staged coefficients are consumed: request the next macroblock of this half's row
 					if (row_ok && x + 1 == x_pref && x_pref < cols) {
-						if (hl < 13) {
+						if (G_COMPACT) {
+							staged_nz = fetch_compact(ws, G_PACKED, G_MASK[mb_row0 + x_pref], G_FIRST[mb_row0 + x_pref], bit0, hl);
+						} else if (hl < 13) {
 							cp_async16(&ws.coef[0 * 13 + hl], cptr);
 							cp_async16(&ws.coef[1 * 13 + hl], cptr + 8);
 							if (hl < 12) {
