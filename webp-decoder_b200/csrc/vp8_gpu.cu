@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -85,6 +86,7 @@ struct vp8_gpu_ctx {
 	size_t cstage_bytes[3] = {0, 0, 0};
 	int host_threads = 0;                               // workers compacting frames (0 = all cores, at most 32)
 	bool compact_transport = true;                      // pipelined decode ships coefficients without their all-zero blocks
+	double trace_compact_ms = 0, trace_total_ms = 0, trace_retire_ms = 0; // VP8_GPU_TRACE=1: where a pipelined call spends host time
 };
 
 namespace {
@@ -164,7 +166,7 @@ void dev_release(vp8_gpu_ctx* c, void* p, size_t bytes) {
 	c->cache.push_back({p, dev_block_bytes(bytes)});
 	size_t total = 0;
 	for (auto& b : c->cache) total += b.bytes;
-	while (c->cache.size() > 16 || total > (64ull << 30)) { // bound what we hold on to
+	while (c->cache.size() > 96 || total > (64ull << 30)) { // bound what we hold on to
 		total -= c->cache.front().bytes;
 		cudaFree(c->cache.front().p);
 		c->cache.erase(c->cache.begin());
@@ -340,10 +342,10 @@ void frame_params(const Vp8DecodedFrame* f, int16_t dq[4][6], uint8_t lf[4][2][4
 }
 
 // ------------------------------------------------------------------------------------------------ batches
-void batch_destroy(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
+void batch_destroy(vp8_gpu_ctx* c, vp8_gpu_batch* b, bool known_idle = false) {
 	if (!b) return;
 	// work queued on the stream may still reference these blocks
-	cudaStreamSynchronize(b->stream ? b->stream : c->stream);
+	if (!known_idle) cudaStreamSynchronize(b->stream ? b->stream : c->stream);
 	dev_release(c, b->d_in, b->in_bytes);
 	dev_release(c, b->d_tight, b->tight_bytes);
 	dev_release(c, b->d_pad, b->pad_bytes);
@@ -1205,6 +1207,7 @@ int batch_create_compact(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, con
 		return -1;
 	}
 	// compaction on host threads, one frame per thread at a time
+	const auto t_c0 = std::chrono::steady_clock::now();
 	uint8_t* stage = c->cstage[slot];
 	std::vector<size_t> used(n);
 	int threads = c->host_threads > 0 ? c->host_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
@@ -1217,6 +1220,7 @@ int batch_create_compact(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, con
 	for (int t = 1; t < threads; t++) pool.emplace_back(work);
 	work();
 	for (auto& t : pool) t.join();
+	c->trace_compact_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_c0).count();
 	for (int i = 0; i < n; i++) {
 		cudaError_t e = cudaMemcpyAsync(b->d_in + frame_off[i], stage + frame_off[i], used[i], cudaMemcpyHostToDevice, st);
 		if (e != cudaSuccess) {
@@ -1253,35 +1257,84 @@ static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, 
 	CU(cudaEventRecord(c->pipe_ev, c->stream));
 	for (auto& p : c->pipe) CU(cudaStreamWaitEvent(p, c->pipe_ev, 0));
 
-	vp8_gpu_batch* inflight[3] = {nullptr, nullptr, nullptr};
+	// Three engines, three streams: pipe[0] carries every host->device copy, pipe[1] the kernels, pipe[2] every
+	// device->host copy; events chain chunk k's stages. A pinned staging slot is free again as soon as its own copies
+	// are done, a chunk retires (device blocks back to the cache) when its download is done; up to kDepth chunks in flight.
+	constexpr int kDepth = 6;
+	struct Chunk {
+		vp8_gpu_batch* b = nullptr;
+		cudaEvent_t up = nullptr, done = nullptr;
+	};
+	Chunk ring[kDepth];
+	cudaEvent_t ev_kernel = nullptr;
 	int rc = 0;
+	auto make_event = [&](cudaEvent_t* e) -> int {
+		CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+		return 0;
+	};
+	auto retire = [&](Chunk& ch) {
+		if (!ch.b) return;
+		cudaEventSynchronize(ch.done);
+		batch_destroy(c, ch.b, true); // its download is done, so nothing queued references its blocks any more
+		ch.b = nullptr;
+	};
+	rc = make_event(&ev_kernel);
+	for (int i = 0; i < kDepth && !rc; i++) rc = make_event(&ring[i].up) || make_event(&ring[i].done);
+	const auto t_p0 = std::chrono::steady_clock::now();
+	c->trace_compact_ms = c->trace_retire_ms = 0;
+	cudaStream_t s_up = c->pipe[0], s_run = c->pipe[1], s_down = c->pipe[2];
 	int k = 0;
 	for (int first = 0; first < n && !rc; first += chunk, k++) {
 		const int cnt = std::min(chunk, n - first), slot = k % 3;
-		if (inflight[slot]) { // retire the chunk that used this stream three chunks ago (frees its device blocks)
-			batch_destroy(c, inflight[slot]);
-			inflight[slot] = nullptr;
-		}
+		Chunk& ch = ring[k % kDepth];
+		const auto t_r0 = std::chrono::steady_clock::now();
+		retire(ch);                                                       // the chunk kDepth steps back
+		if (k >= 3) cudaEventSynchronize(ring[(k - 3) % kDepth].up);      // staging slot reuse: its copies have left the host
+		c->trace_retire_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_r0).count();
 		vp8_gpu_batch* b = nullptr;
-		if (c->compact_transport && c->kernel_version == 2) rc = batch_create_compact(c, kf + first, frames + first, cnt, slot, c->pipe[slot], &b);
-		else rc = batch_create(c, kf + first, frames + first, cnt, true, &b, c->pipe[slot]);
+		if (c->compact_transport && c->kernel_version == 2) rc = batch_create_compact(c, kf + first, frames + first, cnt, slot, s_up, &b);
+		else rc = batch_create(c, kf + first, frames + first, cnt, true, &b, s_up);
 		if (rc) break;
-		inflight[slot] = b;
+		ch.b = b;
+		if (cudaEventRecord(ch.up, s_up) != cudaSuccess || cudaStreamWaitEvent(s_run, ch.up, 0) != cudaSuccess) {
+			rc = fail(EIO, "pipeline events", cudaGetLastError());
+			break;
+		}
+		b->stream = s_run; // kernels (and the descriptor upload) of this chunk
 		rc = vp8_gpu_run(c, b, filtered, VP8_GPU_TIGHT);
 		if (!rc && want_ppm) rc = vp8_gpu_rgb(c, b);
 		if (rc) break;
+		if (cudaEventRecord(ev_kernel, s_run) != cudaSuccess || cudaStreamWaitEvent(s_down, ev_kernel, 0) != cudaSuccess) {
+			rc = fail(EIO, "pipeline events", cudaGetLastError());
+			break;
+		}
 		const FrameMeta& last = b->meta.back();
 		if (want_ppm) {
 			const size_t used = last.rgb_off + kPpmSlot + (size_t)last.width * last.height * 3;
-			rc = download(c, b->stream, dst + off[first], b->d_rgb, used, false);
+			rc = download(c, s_down, dst + off[first], b->d_rgb, used, false);
 		} else {
 			const size_t used = last.tight_off + (size_t)last.width * last.height + 2 * (size_t)((last.width + 1) / 2) * ((last.height + 1) / 2);
-			rc = download(c, b->stream, dst + off[first], b->d_tight, used, false);
+			rc = download(c, s_down, dst + off[first], b->d_tight, used, false);
 		}
+		if (!rc && cudaEventRecord(ch.done, s_down) != cudaSuccess) rc = fail(EIO, "pipeline events", cudaGetLastError());
 	}
 	const int saved = errno;
-	for (auto& b : inflight)
-		if (b) batch_destroy(c, b); // synchronises the chunk's stream
+	const auto t_e0 = std::chrono::steady_clock::now();
+	cudaStreamSynchronize(s_up);
+	cudaStreamSynchronize(s_run);
+	cudaStreamSynchronize(s_down);
+	for (auto& ch : ring) {
+		if (ch.b) batch_destroy(c, ch.b, true);
+		if (ch.up) cudaEventDestroy(ch.up);
+		if (ch.done) cudaEventDestroy(ch.done);
+	}
+	if (ev_kernel) cudaEventDestroy(ev_kernel);
+	if (getenv("VP8_GPU_TRACE")) {
+		const auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "[vp8gpu] pipelined call: total %.1f ms, host compaction %.1f ms, waiting on slots/retiring chunks %.1f ms, final drain %.1f ms\n",
+		        std::chrono::duration<double, std::milli>(now - t_p0).count(), c->trace_compact_ms, c->trace_retire_ms,
+		        std::chrono::duration<double, std::milli>(now - t_e0).count());
+	}
 	if (rc) {
 		errno = saved;
 		return -1;
