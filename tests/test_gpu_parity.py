@@ -100,6 +100,23 @@ def test_edge_geometries(gpu_ctx, oracle):
         assert p == oracle.ppm(oracle.rgb(yuvf, f.width, f.height), f.width, f.height), (f.width, f.height)
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_maximum_frame_dimensions(gpu_ctx, oracle, kernel):
+    """VP8 dimensions are 14-bit (vp8_header.c:46-49): the widest (1024 macroblock columns: largest line buffers) and the
+    tallest (1024 macroblock rows: longest wavefront, progress ring wrap-around) frames a bitstream can carry."""
+    gpu_ctx.set_kernel(kernel)
+    try:
+        for w, h in ((16383, 33), (33, 16383), (4099, 257)):
+            f = fuzz_frame(w + h, w, h, density=0.05, lf_level=24, lf_use_simple=0)
+            for filtered in (False, True):
+                got = gpu_ctx.decode_i420([f.header()], [f.cstruct()], filtered=filtered)[0]
+                assert np.array_equal(got, oracle.decode_i420(f, filtered)), (w, h, filtered)
+        f = fuzz_frame(77, 16383, 17, density=0.05)
+        assert gpu_ctx.decode_ppm([f.header()], [f.cstruct()])[0] == oracle.ppm(oracle.rgb(oracle.decode_i420(f, True), 16383, 17), 16383, 17)
+    finally:
+        gpu_ctx.set_kernel(2)
+
+
 def test_all_zero_and_saturated_inputs(gpu_ctx, oracle):
     a = fuzz_frame(1, 96, 80, density=0.0)                          # prediction only, every IDCT short-circuits
     b = fuzz_frame(2, 96, 80, density=1.0, amp=2047, q_index=127)   # every coefficient set, maximal quantiser
