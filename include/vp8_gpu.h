@@ -67,6 +67,12 @@ int vp8_gpu_set_tuning(vp8_gpu_ctx* ctx, int warps_per_image, int images_per_sm)
  * two rows per warp (vp8_pairs.cu). Both are bit-exact; the environment variable VP8_GPU_KERNEL presets it. */
 int vp8_gpu_set_kernel(vp8_gpu_ctx* ctx, int version);
 
+/* Small batches of big frames: the pair kernel can spread ONE image over a thread-block cluster of 2, 4 or 8 CTAs
+ * (co-scheduled, exchanging line buffers and progress stamps through L2). 0 = automatic (used when the batch would
+ * otherwise leave most SMs idle), 1 = never, 2/4/8 = at most that many CTAs per image. */
+int vp8_gpu_set_cluster(vp8_gpu_ctx* ctx, int ctas_per_image);
+int vp8_gpu_last_cluster(const vp8_gpu_ctx* ctx); /* CTAs per image of the last wavefront launch */
+
 /* Transport of the pipelined calls (vp8_gpu_decode_*): compact != 0 (default) ships each frame without its all-zero
  * 4x4 blocks (per-macroblock presence mask + packed blocks, built by host_threads workers; 0 = all cores), which is
  * what the host->device link is bound by; compact == 0 ships the dense arrays as they are. */

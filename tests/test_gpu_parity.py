@@ -117,6 +117,35 @@ def test_maximum_frame_dimensions(gpu_ctx, oracle, kernel):
         gpu_ctx.set_kernel(2)
 
 
+@pytest.mark.parametrize("ctas", [1, 2, 4, 8])
+def test_cluster_mode_one_image_over_several_ctas(gpu_ctx, oracle, ctas):
+    """Few big frames: each image is decoded by a thread-block cluster (row pairs dealt to the warps of 2/4/8 co-scheduled
+    CTAs, line buffers and progress stamps exchanged through L2). Same bytes as the single-CTA path and the oracle."""
+    gpu_ctx.set_cluster(ctas)
+    try:
+        frames = [fuzz_frame(600 + s, 400 + 64 * s, 1100 + 200 * s, density=0.15, lf_level=20 + s, lf_use_simple=0) for s in range(3)]
+        frames.append(fuzz_frame(610, 64, 4000, density=0.2))          # 250 macroblock rows, 4 columns
+        frames.append(fuzz_frame(611, 2500, 600, density=0.1, lf_use_simple=1, lf_level=33))
+        kfs, ds = [f.header() for f in frames], [f.cstruct() for f in frames]
+        for filtered in (False, True):
+            outs = gpu_ctx.decode_i420(kfs, ds, filtered=filtered)
+            for f, o in zip(frames, outs):
+                assert np.array_equal(o, oracle.decode_i420(f, filtered)), (ctas, f.width, f.height, filtered)
+        cfg = gpu_ctx.last_launch_config()
+        assert cfg["ctas_per_image"] == ctas and cfg["grid"] == len(frames) * ctas
+        # stand-alone loop filter (stage API) through the cluster path as well
+        b = gpu_ctx.recon(kfs[:2], ds[:2])
+        gpu_ctx.filter(b)
+        for i in range(2):
+            y, u, v = oracle.recon_padded(frames[i])
+            oracle.loopfilter_padded(frames[i], y, u, v)
+            for got, want in zip(gpu_ctx.download_padded(b, i), (y, u, v)):
+                assert np.array_equal(got, want)
+        b.free()
+    finally:
+        gpu_ctx.set_cluster(0)
+
+
 def test_all_zero_and_saturated_inputs(gpu_ctx, oracle):
     a = fuzz_frame(1, 96, 80, density=0.0)                          # prediction only, every IDCT short-circuits
     b = fuzz_frame(2, 96, 80, density=1.0, amp=2047, q_index=127)   # every coefficient set, maximal quantiser

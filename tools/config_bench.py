@@ -67,3 +67,24 @@ px = 1024 * 1920 * 1080
 out["config4_ppm_1024x1080p"] = {"wavefront_ms": t_w / reps, "rgb_ms": t_r / reps, "mpixel_per_s": px / ((t_w + t_r) / reps) / 1e3,
                                   "rgb_kernel_GBps": 1024 * (1920 * 1080 * 4.5) / (t_r / reps) / 1e6, "bit_exact": ok}
 print(json.dumps(out, indent=1))
+
+# config 3 again with the image spread over a thread-block cluster (pair kernel, 16 warps per CTA)
+ctx3 = W.Context(0)
+ctx3.set_kernel(2)
+lat = {}
+for name in ("checker_3840x2160_q75.webp", "rgbgrad_3840x2160_q75.webp"):
+    for cl in (1, 2, 4, 8):
+        ctx3.set_cluster(cl)
+        i = idx[name]
+        b = ctx3.upload([pf.kfs[i]], [pf.frames[i]])
+        for _ in range(3):
+            ctx3.run(b, True, W.TIGHT)
+        ctx3.kernel_time()
+        for _ in range(20):
+            ctx3.run(b, True, W.TIGHT)
+        ms, n = ctx3.kernel_time()
+        buf, offs, sizes = ctx3.download_i420(b)
+        ok = hashlib.sha256(buf[int(offs[0]):int(offs[0]) + int(sizes[0])]).hexdigest() == dg[name]["yuvf"]
+        lat[f"{name} cluster<= {cl}"] = {"latency_us": ms / n * 1e3, "launch": ctx3.last_launch_config(), "bit_exact": ok}
+        b.free()
+print(json.dumps({"config3_cluster": lat}, indent=1))

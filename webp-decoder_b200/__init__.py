@@ -43,6 +43,7 @@ EXPORTS = [
     "vp8_gpu_last_launch_config", "vp8_gpu_frame_params", "vp8_gpu_kernel_time",
     "vp8_gpu_decode_i420", "vp8_gpu_decode_ppm", "vp8_gpu_decode_bytes", "vp8_gpu_set_kernel",
     "vp8_gpu_png_bound", "vp8_gpu_png_frame", "vp8_gpu_set_transport",
+    "vp8_gpu_set_cluster", "vp8_gpu_last_cluster",
 ]
 
 _lib = None
@@ -71,6 +72,8 @@ def load_library() -> C.CDLL:
     L.vp8_gpu_set_tuning.argtypes = [vp, C.c_int, C.c_int]
     L.vp8_gpu_set_kernel.argtypes = [vp, C.c_int]
     L.vp8_gpu_set_transport.argtypes = [vp, C.c_int, C.c_int]
+    L.vp8_gpu_set_cluster.argtypes = [vp, C.c_int]
+    L.vp8_gpu_last_cluster.argtypes = [vp]
     L.vp8_gpu_host_alloc.argtypes = [sz]
     L.vp8_gpu_host_alloc.restype = vp
     L.vp8_gpu_host_free.argtypes = [vp]
@@ -211,6 +214,10 @@ class Context:
         """1 = warp per macroblock, 2 = half-warp per macroblock (two rows per warp)."""
         _check(self._L.vp8_gpu_set_kernel(self._h, version), "vp8_gpu_set_kernel")
 
+    def set_cluster(self, ctas_per_image: int = 0):
+        """CTAs per image in cluster mode: 0 automatic, 1 never, 2/4/8 upper bound."""
+        _check(self._L.vp8_gpu_set_cluster(self._h, ctas_per_image), "vp8_gpu_set_cluster")
+
     def set_transport(self, compact: bool = True, host_threads: int = 0):
         """Pipelined calls: ship frames without their all-zero 4x4 blocks (compacted by host threads) or dense."""
         _check(self._L.vp8_gpu_set_transport(self._h, int(compact), host_threads), "vp8_gpu_set_transport")
@@ -341,7 +348,8 @@ class Context:
     def last_launch_config(self):
         w, g, s = C.c_int(), C.c_int(), C.c_int()
         _check(self._L.vp8_gpu_last_launch_config(self._h, C.byref(w), C.byref(g), C.byref(s)), "launch config")
-        return {"warps_per_image": w.value, "grid": g.value, "smem_bytes": s.value}
+        return {"warps_per_image": w.value, "grid": g.value, "smem_bytes": s.value,
+                "ctas_per_image": int(self._L.vp8_gpu_last_cluster(self._h))}
 
 
 # -------------------------------------------------------------------------------------------- reference-shaped calls

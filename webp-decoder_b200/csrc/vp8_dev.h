@@ -74,9 +74,11 @@ int vp8_wavefront_smem_bytes(int mode, int warps_per_image, int max_mb_cols);
 int vp8_wavefront_max_ctas_per_sm(int mode, int warps_per_image, int max_mb_cols);
 // Second-generation kernel (vp8_pairs.cu): half-warp per macroblock, two rows per warp. warps_per_image in {4, 8, 16}.
 // scratch: vp8_pairs_scratch_bytes(grid, max_mb_cols) bytes of device memory private to this launch.
+// cluster > 1 (2, 4 or 8; needs warps_per_image == 16): every image is processed by a thread-block cluster of that many
+// CTAs; grid_ctas must be a multiple of it and scratch sized for grid_ctas / cluster slots.
 int vp8_launch_pairs(int mode, int warps_per_image, const Vp8ImgDesc* descs_dev, int n_images, int max_mb_cols, int grid_ctas,
-                     uint8_t* scratch, void* stream);
+                     uint8_t* scratch, int cluster, void* stream);
 int vp8_pairs_smem_bytes(int warps_per_image, int max_mb_cols);
 int vp8_pairs_max_ctas_per_sm(int mode, int warps_per_image, int max_mb_cols);
-size_t vp8_pairs_scratch_bytes(int grid_ctas, int max_mb_cols);
+size_t vp8_pairs_scratch_bytes(int slots, int max_mb_cols);
 int vp8_launch_rgb(const Vp8RgbDesc* descs_dev, int n_images, uint32_t total_blocks, void* stream);

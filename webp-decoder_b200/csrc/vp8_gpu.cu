@@ -70,6 +70,8 @@ struct vp8_gpu_ctx {
 	bool own_stream = false;
 	int sm_count = 0;
 	int tune_warps = 0, tune_imgs_per_sm = 0;
+	int tune_cluster = 0; // CTAs per image in cluster mode: 0 = automatic, 1 = never, 2/4/8 = at most that many
+	int last_cluster = 1;
 	int kernel_version = 2; // 1: vp8_mb_wavefront (warp per macroblock), 2: vp8_mb_pairs (half-warp per macroblock)
 	uint8_t* bounce[2] = {nullptr, nullptr};
 	cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
@@ -568,9 +570,20 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 	}
 	if (per_sm <= 0) return fail(EIO, "wavefront kernel does not fit on an SM (frame too wide?)", cudaGetLastError());
 	if (c->tune_imgs_per_sm > 0) per_sm = std::min(per_sm, c->tune_imgs_per_sm);
-	const int grid = std::min(b->n, per_sm * c->sm_count);
+	int grid = std::min(b->n, per_sm * c->sm_count);
+	// Few big frames: spread each over a thread-block cluster so that one image can use several SMs. Worth it only when
+	// 16-warp CTAs are already in use, the GPU would otherwise be mostly idle and the frame has rows to hand out.
+	int cluster = 1;
+	if (pairs && warps == 16 && c->tune_cluster != 1) {
+		int max_rows = 0;
+		for (auto& m : b->meta) max_rows = std::max<int>(max_rows, m.mb_rows);
+		int want = c->tune_cluster > 1 ? c->tune_cluster : 8;
+		while (want > 1 && (b->n * want > c->sm_count || 32 * (want - 1) >= max_rows)) want /= 2; // every CTA must get rows
+		cluster = want;
+		if (cluster > 1) grid = std::min(b->n, c->sm_count / cluster) * cluster;
+	}
 	if (pairs) {
-		const size_t need = vp8_pairs_scratch_bytes(grid, b->max_mb_cols);
+		const size_t need = vp8_pairs_scratch_bytes(cluster > 1 ? grid / cluster : grid, b->max_mb_cols);
 		if (b->scratch_bytes < need) {
 			dev_release(c, b->d_scratch, b->scratch_bytes);
 			b->d_scratch = nullptr;
@@ -588,7 +601,7 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 		CU(cudaEventCreate(&ev.second));
 	}
 	CU(cudaEventRecord(ev.first, b->stream));
-	const int rc = pairs ? vp8_launch_pairs(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, b->d_scratch, b->stream)
+	const int rc = pairs ? vp8_launch_pairs(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, b->d_scratch, cluster, b->stream)
 	                     : vp8_launch_wavefront(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, b->stream);
 	CU(cudaEventRecord(ev.second, b->stream));
 	c->timed.push_back(ev);
@@ -600,6 +613,7 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 	c->launches++;
 	c->last_warps = warps;
 	c->last_grid = grid;
+	c->last_cluster = cluster;
 	c->last_smem = pairs ? vp8_pairs_smem_bytes(warps, b->max_mb_cols) : vp8_wavefront_smem_bytes(kernel_mode, warps, b->max_mb_cols);
 	return 0;
 }
@@ -823,6 +837,7 @@ int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out) {
 	}
 	if (const char* k = getenv("VP8_GPU_KERNEL")) c->kernel_version = atoi(k) == 1 ? 1 : 2;
 	if (const char* w = getenv("VP8_GPU_WARPS")) c->tune_warps = atoi(w);
+	if (const char* w = getenv("VP8_GPU_CLUSTER")) c->tune_cluster = atoi(w);
 	if (const char* w = getenv("VP8_GPU_HOST_THREADS")) c->host_threads = atoi(w);
 	if (const char* w = getenv("VP8_GPU_COMPACT")) c->compact_transport = atoi(w) != 0;
 	if (const char* w = getenv("VP8_GPU_IMAGES_PER_SM")) c->tune_imgs_per_sm = atoi(w);
@@ -874,6 +889,15 @@ int vp8_gpu_set_transport(vp8_gpu_ctx* c, int compact, int host_threads) {
 	c->host_threads = host_threads;
 	return 0;
 }
+
+int vp8_gpu_set_cluster(vp8_gpu_ctx* c, int ctas_per_image) {
+	if (!c || (ctas_per_image != 0 && ctas_per_image != 1 && ctas_per_image != 2 && ctas_per_image != 4 && ctas_per_image != 8))
+		return fail(EINVAL, "bad cluster size");
+	c->tune_cluster = ctas_per_image;
+	return 0;
+}
+
+int vp8_gpu_last_cluster(const vp8_gpu_ctx* c) { return c ? c->last_cluster : 0; }
 
 int vp8_gpu_set_kernel(vp8_gpu_ctx* c, int version) {
 	if (!c || (version != 1 && version != 2)) return fail(EINVAL, "bad kernel version");

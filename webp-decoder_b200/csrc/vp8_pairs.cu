@@ -36,8 +36,29 @@ struct __align__(16) HalfWs {
 };
 static_assert(sizeof(HalfWs) % 16 == 0 && offsetof(HalfWs, res) % 16 == 0 && offsetof(HalfWs, coef) % 16 == 0, "HalfWs alignment");
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+	uint32_t r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+	uint32_t r;
+	asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+	asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t ldcg32(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint32_t*>(p)); }
 __device__ __forceinline__ void stcg32(uint8_t* p, uint32_t v) { __stcg(reinterpret_cast<uint32_t*>(p), v); }
+// unfiltered line buffer: shared memory normally, L2 (never L1) when the image is spread over a cluster
+template <bool CL>
+__device__ __forceinline__ uint32_t ld_line(const uint8_t* p) { return CL ? ldcg32(p) : ld32(p); }
+template <bool CL>
+__device__ __forceinline__ void st_line(uint8_t* p, uint32_t v) {
+	if (CL) stcg32(p, v);
+	else st32(p, v);
+}
 
 // Compact layout: request this lane's (up to two) present blocks of one macroblock; returns their presence bits.
 __device__ __forceinline__ uint32_t fetch_compact(HalfWs& ws, const uint8_t* packed, uint32_t mask, uint32_t first, int bit0, int hl) {
@@ -58,6 +79,8 @@ __device__ __forceinline__ uint32_t fetch_compact(HalfWs& ws, const uint8_t* pac
 	return nz;
 }
 
+constexpr int kClusterProg = 1024; // progress stamps per image in cluster mode (VP8 frames have at most 1024 macroblock rows)
+
 #ifndef VP8P_BPRED_UNROLL
 #define VP8P_BPRED_UNROLL 16 // sub-block steps unrolled per loop iteration (16 = fully unrolled)
 #endif
@@ -74,25 +97,38 @@ __device__ __forceinline__ uint32_t fetch_compact(HalfWs& ws, const uint8_t* pac
 #define VP8_PAIR_MIN_CTAS(NW) ((NW) == 4 ? 7 : (NW) == 8 ? 3 : 1)
 #endif
 
-template <int NW, bool RECON, bool FILTER>
-__global__ void __launch_bounds__(NW * 32, VP8_PAIR_MIN_CTAS(NW))
+// CL = false: one CTA per image, unfiltered line buffer and progress stamps in shared memory.
+// CL = true : one thread-block CLUSTER per image (launched with a cluster dimension, so its CTAs are co-scheduled and may
+//             spin on each other): row pairs are dealt round-robin to the warps of all CTAs of the cluster; the unfiltered
+//             line buffer and the progress stamps live next to the filtered line in the L2-resident scratch and are
+//             published / acquired with gpu-scope fences. This is what lets ONE big frame use several SMs.
+template <int NW, bool RECON, bool FILTER, bool CL>
+__global__ void __launch_bounds__(NW * 32, CL ? 1 : VP8_PAIR_MIN_CTAS(NW))
 vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, uint8_t* __restrict__ tf_scratch) {
 	extern __shared__ __align__(16) uint8_t smem[];
 	volatile int* prog = reinterpret_cast<volatile int*>(smem);
 	Vp8ImgDesc* sd = reinterpret_cast<Vp8ImgDesc*>(smem + 256);
 	uint32_t* btab = reinterpret_cast<uint32_t*>(smem + 512);
-	uint8_t* tu_y = smem + kSmemFixed; // unfiltered bottom rows of the row above (shared memory)
-	uint8_t* tu_u = tu_y + line_px;
-	uint8_t* tu_v = tu_u + line_px / 2;
 	const int line_c = line_px / 2;
-	uint8_t* tf_y = tf_scratch + (size_t)blockIdx.x * 8 * line_px; // last four filtered rows of the row above (L2)
+	const int c_rank = CL ? (int)cluster_ctarank() : 0, c_size = CL ? (int)cluster_nctarank() : 1;
+	const int slot = CL ? blockIdx.x / c_size : blockIdx.x, n_slots = CL ? gridDim.x / c_size : gridDim.x;
+	// per-slot scratch in global memory (L2): [tf: 8 x line][tu: 2 x line][progress stamps: one per macroblock row]
+	uint8_t* const sc = tf_scratch + (size_t)slot * ((size_t)10 * line_px + kClusterProg * 4);
+	uint8_t* tf_y = sc; // last four filtered rows of the row above
 	uint8_t* tf_u = tf_y + 4 * line_px;
 	uint8_t* tf_v = tf_u + 2 * line_px;
+	// unfiltered bottom rows of the row above: shared memory, or the scratch when the image is spread over a cluster
+	uint8_t* tu_y = CL ? sc + 8 * line_px : smem + kSmemFixed;
+	uint8_t* tu_u = tu_y + line_px;
+	uint8_t* tu_v = tu_u + line_px / 2;
+	if (CL) prog = reinterpret_cast<volatile int*>(sc + (size_t)10 * line_px);
+	// a cluster can have every row of the image in flight: one stamp per row, no ring
+	constexpr int prog_mask = CL ? kClusterProg - 1 : kProgRing - 1;
 
 	constexpr uint32_t FULL = 0xffffffffu;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int hl = lane & 15, half = lane >> 4, hbit = lane & 16;
-	HalfWs& ws = reinterpret_cast<HalfWs*>(smem + kSmemFixed + 2 * line_px)[warp * 2 + half];
+	HalfWs& ws = reinterpret_cast<HalfWs*>(smem + kSmemFixed + (CL ? 0 : 2 * line_px))[warp * 2 + half];
 
 	static_assert(sizeof(Vp8ImgDesc) <= 256, "descriptor must fit its shared-memory slot");
 	static_assert(4 * NW <= kProgRing, "progress ring too small");
@@ -131,15 +167,27 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 	const bool dc_tap = (hl >= 2 && hl <= 5) || (hl >= 7 && hl <= 10);
 	//   loop filter: luma line hl; chroma plane hl>>3, line hl&7
 
-	for (int img = blockIdx.x; img < n_images; img += gridDim.x) {
-		__syncthreads(); // previous image fully retired before its line buffers and descriptor are reused
+	for (int img = slot; img < n_images; img += n_slots) {
+		// previous image fully retired before its line buffers, stamps and descriptor are reused
+		if (CL) cluster_sync_all();
+		else __syncthreads();
 		{
 			const uint32_t* src = reinterpret_cast<const uint32_t*>(descs + img);
 			uint32_t* dst = reinterpret_cast<uint32_t*>(sd);
 			for (int i = tid; i < (int)(sizeof(Vp8ImgDesc) / 4); i += NW * 32) dst[i] = src[i];
-			if (tid < kProgRing) prog[tid] = 0;
+			if (CL) {
+				if (c_rank == 0)
+					for (int i = tid; i < kClusterProg; i += NW * 32) prog[i] = 0;
+			} else if (tid < kProgRing) {
+				prog[tid] = 0;
+			}
 		}
-		__syncthreads();
+		if (CL) {
+			__threadfence();
+			cluster_sync_all();
+		} else {
+			__syncthreads();
+		}
 
 		const int cols = sd->mb_cols, rows = sd->mb_rows;
 		OutPlane oy{sd->out_y, sd->out_stride_y, sd->out_w, sd->out_h,
@@ -161,7 +209,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 #define G_MASK reinterpret_cast<const uint32_t*>(sd->coeff_u)
 #define G_FIRST reinterpret_cast<const uint32_t*>(sd->coeff_v)
 
-		for (int p = warp; 2 * p < rows; p += NW) {
+		for (int p = c_rank * NW + warp; 2 * p < rows; p += NW * c_size) {
 			const int y = 2 * p + half;
 			const bool row_ok = y < rows;
 			const bool last_row = (y == rows - 1);
@@ -228,8 +276,9 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 				if (p > 0 && t < cols) {
 					if (lane == 0) {
 						const int target = 2 * p * kStampRow + min(t + 2, cols);
-						while (prog[(2 * p - 1) & (kProgRing - 1)] < target) __nanosleep(64);
-						__threadfence_block();
+						while (prog[(2 * p - 1) & prog_mask] < target) __nanosleep(64);
+						if (CL) __threadfence();
+						else __threadfence_block();
 					}
 				}
 				__syncwarp();
@@ -248,12 +297,12 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 						uint32_t w = 0x7f7f7f7fu;
 						if (y > 0) {
 							if (hl < 5) {
-								if (hl == 4 && last_col) w = 0x01010101u * tu_y[16 * x + 15];
-								else w = ld32(tu_y + 16 * x + 4 * hl);
+								if (hl == 4 && last_col) w = 0x01010101u * (ld_line<CL>(tu_y + 16 * x + 12) >> 24);
+								else w = ld_line<CL>(tu_y + 16 * x + 4 * hl);
 							} else if (hl < 7) {
-								w = ld32(tu_u + 8 * x + 4 * (hl - 5));
+								w = ld_line<CL>(tu_u + 8 * x + 4 * (hl - 5));
 							} else {
-								w = ld32(tu_v + 8 * x + 4 * (hl - 7));
+								w = ld_line<CL>(tu_v + 8 * x + 4 * (hl - 7));
 							}
 						}
 						if (hl < 5) {
@@ -697,15 +746,16 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 					if (hl == 9) ws.rt_u[3] = (uint8_t)corner_b;
 					if (hl == 10) ws.rt_v[3] = (uint8_t)corner_b;
 					if (!last_row) {
-						if (hl < 4) st32(tu_y + 16 * x + 4 * hl, bot_w);
-						else if (hl < 6) st32(tu_u + 8 * x + 4 * (hl - 4), bot_w);
-						else if (hl < 8) st32(tu_v + 8 * x + 4 * (hl - 6), bot_w);
+						if (hl < 4) st_line<CL>(tu_y + 16 * x + 4 * hl, bot_w);
+						else if (hl < 6) st_line<CL>(tu_u + 8 * x + 4 * (hl - 4), bot_w);
+						else if (hl < 8) st_line<CL>(tu_v + 8 * x + 4 * (hl - 6), bot_w);
 					}
 				}
 				__syncwarp();
 				if (hl == 0 && v) {
-					__threadfence_block();
-					prog[y & (kProgRing - 1)] = (y + 1) * kStampRow + x + 1;
+					if (CL) __threadfence();
+					else __threadfence_block();
+					prog[y & prog_mask] = (y + 1) * kStampRow + x + 1;
 				}
 			}
 		}
@@ -713,17 +763,38 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 }
 
 template <int NW, bool RECON, bool FILTER>
-int launch_pairs_t(const Vp8ImgDesc* descs, int n, int line_px, int grid, size_t smem, uint8_t* scratch, cudaStream_t st) {
-	auto k = vp8_mb_pairs<NW, RECON, FILTER>;
+int launch_pairs_t(const Vp8ImgDesc* descs, int n, int line_px, int grid, size_t smem, uint8_t* scratch, int cluster, cudaStream_t st) {
+	if (cluster <= 1) {
+		auto k = vp8_mb_pairs<NW, RECON, FILTER, false>;
+		cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return (int)e;
+		k<<<grid, NW * 32, smem, st>>>(descs, n, line_px, scratch);
+		return (int)cudaGetLastError();
+	}
+	if (NW != 16) return (int)cudaErrorInvalidValue; // the cluster flavour is only built for 16 warps per CTA
+	auto k = vp8_mb_pairs<16, RECON, FILTER, true>;
 	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return (int)e;
-	k<<<grid, NW * 32, smem, st>>>(descs, n, line_px, scratch);
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3(grid);
+	cfg.blockDim = dim3(16 * 32);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = (unsigned)cluster;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	e = cudaLaunchKernelEx(&cfg, k, descs, n, line_px, scratch);
+	if (e != cudaSuccess) return (int)e;
 	return (int)cudaGetLastError();
 }
 
 template <int NW, bool RECON, bool FILTER>
 int occupancy_pairs_t(size_t smem) {
-	auto k = vp8_mb_pairs<NW, RECON, FILTER>;
+	auto k = vp8_mb_pairs<NW, RECON, FILTER, false>;
 	if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
 	int nb = 0;
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, NW * 32, smem) != cudaSuccess) return 0;
@@ -736,7 +807,8 @@ int vp8_pairs_smem_bytes(int warps_per_image, int max_mb_cols) {
 	return kSmemFixed + 2 * 16 * max_mb_cols + warps_per_image * 2 * (int)sizeof(HalfWs);
 }
 
-size_t vp8_pairs_scratch_bytes(int grid_ctas, int max_mb_cols) { return (size_t)grid_ctas * 8 * 16 * max_mb_cols; }
+// one scratch slot per CTA (or per cluster): filtered line (8 B/column), unfiltered line (2 B/column, cluster mode), stamps
+size_t vp8_pairs_scratch_bytes(int slots, int max_mb_cols) { return (size_t)slots * ((size_t)10 * 16 * max_mb_cols + kClusterProg * 4); }
 
 #define VP8_PAIRS_DISPATCH(FN, ...)                                \
 	switch (mode * 100 + warps_per_image) {                        \
@@ -753,11 +825,11 @@ size_t vp8_pairs_scratch_bytes(int grid_ctas, int max_mb_cols) { return (size_t)
 	}
 
 int vp8_launch_pairs(int mode, int warps_per_image, const Vp8ImgDesc* descs_dev, int n_images, int max_mb_cols, int grid_ctas,
-                     uint8_t* scratch, void* stream) {
+                     uint8_t* scratch, int cluster, void* stream) {
 	const size_t smem = (size_t)vp8_pairs_smem_bytes(warps_per_image, max_mb_cols);
 	const int line_px = 16 * max_mb_cols;
 	cudaStream_t st = (cudaStream_t)stream;
-	VP8_PAIRS_DISPATCH(launch_pairs_t, descs_dev, n_images, line_px, grid_ctas, smem, scratch, st)
+	VP8_PAIRS_DISPATCH(launch_pairs_t, descs_dev, n_images, line_px, grid_ctas, smem, scratch, cluster, st)
 }
 
 int vp8_pairs_max_ctas_per_sm(int mode, int warps_per_image, int max_mb_cols) {
