@@ -164,7 +164,6 @@ __device__ __forceinline__ void iwht4x4(const int (&v)[16], int (&r)[16]) {
 // ------------------------------------------------------------------------------------------------ loop filter
 enum { EDGE_MB = 0, EDGE_INNER = 1, EDGE_SIMPLE = 2 };
 
-#if VP8_LF_GENERIC
 // One position across an edge: q points at q0, `step` is the byte distance between the pixels p3..q3 (1 across a
 // vertical edge, the tile stride across a horizontal one). A single body serves every edge of every plane so that
 // the kernel stays inside the instruction cache; `kind` is warp-uniform.
@@ -209,7 +208,6 @@ __device__ __forceinline__ void lf_line(uint8_t* q, int step, int kind, int lim,
 	}
 }
 
-#else
 // One position across an edge, in registers. Returns true when pixels changed.
 // Thresholds: reference vp8_loopfilter.c:24-56; kernels :58-104; dispatch :106-164.
 template <int KIND>
@@ -283,6 +281,5 @@ __device__ __forceinline__ void lf_across_rows(uint8_t* q, int s, int lim, int i
 	}
 }
 
-#endif
 
 } // namespace

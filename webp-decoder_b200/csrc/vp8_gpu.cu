@@ -10,10 +10,15 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -64,6 +69,66 @@ struct FreeBlock {
 
 } // namespace
 
+// Host worker threads that outlive a call (creating 31 threads per 64-frame chunk cost more than the work they did).
+class WorkerPool {
+public:
+	explicit WorkerPool(int n) {
+		for (int i = 0; i < n; i++) workers_.emplace_back([this, i] { loop(i); });
+	}
+	~WorkerPool() {
+		{
+			std::lock_guard<std::mutex> g(mu_);
+			stop_ = true;
+			generation_++;
+		}
+		wake_.notify_all();
+		for (auto& t : workers_) t.join();
+	}
+	int size() const { return (int)workers_.size(); }
+	// Runs fn on `helpers` workers and on the caller; returns when every copy has returned.
+	void run(const std::function<void()>& fn, int helpers) {
+		helpers = std::max(0, std::min(helpers, size()));
+		{
+			std::lock_guard<std::mutex> g(mu_);
+			fn_ = &fn;
+			helpers_ = helpers;
+			pending_ = helpers;
+			generation_++;
+		}
+		wake_.notify_all();
+		fn();
+		std::unique_lock<std::mutex> g(mu_);
+		done_.wait(g, [this] { return pending_ == 0; });
+		fn_ = nullptr;
+	}
+
+private:
+	void loop(int index) {
+		uint64_t seen = 0;
+		for (;;) {
+			const std::function<void()>* fn = nullptr;
+			{
+				std::unique_lock<std::mutex> g(mu_);
+				wake_.wait(g, [&] { return generation_ != seen; });
+				seen = generation_;
+				if (stop_) return;
+				if (index < helpers_) fn = fn_;
+			}
+			if (!fn) continue;
+			(*fn)();
+			std::lock_guard<std::mutex> g(mu_);
+			if (--pending_ == 0) done_.notify_all();
+		}
+	}
+	std::vector<std::thread> workers_;
+	std::mutex mu_;
+	std::condition_variable wake_, done_;
+	const std::function<void()>* fn_ = nullptr;
+	int helpers_ = 0, pending_ = 0;
+	uint64_t generation_ = 0;
+	bool stop_ = false;
+};
+
 struct vp8_gpu_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
@@ -82,11 +147,14 @@ struct vp8_gpu_ctx {
 	// device-side duration of every wavefront launch since the last vp8_gpu_kernel_time() query
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed; // recorded, not yet read
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spare;
-	cudaStream_t pipe[3] = {nullptr, nullptr, nullptr}; // chunk pipeline of vp8_gpu_decode_*
+	cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr}; // chunk pipeline of vp8_gpu_decode_*
 	cudaEvent_t pipe_ev = nullptr;
 	uint8_t* cstage[3] = {nullptr, nullptr, nullptr};   // pinned staging of compacted chunks, one per pipeline slot
 	size_t cstage_bytes[3] = {0, 0, 0};
 	int host_threads = 0;                               // workers compacting frames (0 = all cores, at most 32)
+	int trace_mallocs = 0, trace_frees = 0;             // device block cache misses / evictions (VP8_GPU_TRACE)
+	double trace_malloc_ms = 0;
+	WorkerPool* pool = nullptr;                         // created by the first pipelined call
 	bool compact_transport = true;                      // pipelined decode ships coefficients without their all-zero blocks
 	double trace_compact_ms = 0, trace_total_ms = 0, trace_retire_ms = 0; // VP8_GPU_TRACE=1: where a pipelined call spends host time
 };
@@ -138,19 +206,29 @@ struct vp8_gpu_batch {
 namespace {
 
 // ------------------------------------------------------------------------------------------------ device memory
+// Blocks come in size classes (1 MiB x 2^k) and are only reused within their class, so a pipelined call, whose chunks
+// differ in size, finds every block it needs in the cache from its second run on (a miss costs a cudaMalloc, an
+// eviction a cudaFree that waits for the whole device).
+size_t dev_block_bytes(size_t bytes) {
+	size_t cls = 1u << 20;
+	while (cls < bytes) cls <<= 1;
+	return cls;
+}
+
 int dev_alloc(vp8_gpu_ctx* c, size_t bytes, void** out) {
-	bytes = align_up(bytes ? bytes : 1, 1u << 20);
+	bytes = dev_block_bytes(bytes);
 	int best = -1;
-	for (int i = 0; i < (int)c->cache.size(); i++)
-		if (c->cache[i].bytes >= bytes && c->cache[i].bytes <= 2 * bytes &&
-		    (best < 0 || c->cache[i].bytes < c->cache[best].bytes))
-			best = i;
+	for (int i = 0; i < (int)c->cache.size() && best < 0; i++)
+		if (c->cache[i].bytes == bytes) best = i;
 	if (best >= 0) {
 		*out = c->cache[best].p;
 		c->cache.erase(c->cache.begin() + best);
 		return 0;
 	}
+	const auto t0 = std::chrono::steady_clock::now();
 	cudaError_t e = cudaMalloc(out, bytes);
+	c->trace_mallocs++;
+	c->trace_malloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	if (e != cudaSuccess) {
 		// drop the cache and retry once
 		for (auto& b : c->cache) cudaFree(b.p);
@@ -161,8 +239,6 @@ int dev_alloc(vp8_gpu_ctx* c, size_t bytes, void** out) {
 	return 0;
 }
 
-size_t dev_block_bytes(size_t bytes) { return align_up(bytes ? bytes : 1, 1u << 20); }
-
 void dev_release(vp8_gpu_ctx* c, void* p, size_t bytes) {
 	if (!p) return;
 	c->cache.push_back({p, dev_block_bytes(bytes)});
@@ -170,7 +246,10 @@ void dev_release(vp8_gpu_ctx* c, void* p, size_t bytes) {
 	for (auto& b : c->cache) total += b.bytes;
 	while (c->cache.size() > 96 || total > (64ull << 30)) { // bound what we hold on to
 		total -= c->cache.front().bytes;
+		const auto t0 = std::chrono::steady_clock::now();
 		cudaFree(c->cache.front().p);
+		c->trace_frees++;
+		c->trace_malloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 		c->cache.erase(c->cache.begin());
 	}
 }
@@ -864,6 +943,7 @@ void vp8_gpu_destroy(vp8_gpu_ctx* c) {
 	for (auto& p : c->cstage)
 		if (p) cudaFreeHost(p);
 	if (c->pipe_ev) cudaEventDestroy(c->pipe_ev);
+	delete c->pool;
 	if (c->own_stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -1122,49 +1202,98 @@ CompactLayout compact_layout(size_t mb) {
 	return L;
 }
 
-inline bool block_nonzero(const int16_t* p) {
-	uint64_t a, b, c, d;
-	memcpy(&a, p, 8);
-	memcpy(&b, p + 4, 8);
-	memcpy(&c, p + 8, 8);
-	memcpy(&d, p + 12, 8);
-	return (a | b | c | d) != 0;
+// One macroblock: appends its non-zero 4x4 blocks (32 bytes each) at out, returns the presence mask; *bytes = appended.
+// Branch-free: every block is stored at the running position and the position only moves on when it was non-zero, so
+// out needs 800 writable bytes whatever the content.
+inline uint32_t pack_mb_portable(const int16_t* const src[4], uint8_t* out, size_t* bytes) {
+	static const int nblk[4] = {16, 4, 4, 1}, bit[4] = {0, 16, 20, 24};
+	uint32_t m = 0;
+	size_t pos = 0;
+	for (int g = 0; g < 4; g++)
+		for (int b = 0; b < nblk[g]; b++) {
+			const int16_t* p = src[g] + 16 * b;
+			uint64_t w[4];
+			memcpy(w, p, 32);
+			memcpy(out + pos, w, 32);
+			const uint32_t nz = (w[0] | w[1] | w[2] | w[3]) != 0;
+			pos += 32 * nz;
+			m |= nz << (bit[g] + b);
+		}
+	*bytes = pos;
+	return m;
 }
 
-// Returns the number of bytes of dst that are in use.
-size_t compact_frame(const Vp8DecodedFrame* f, uint8_t* dst) {
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) inline uint32_t pack_mb_avx2(const int16_t* const src[4], uint8_t* out, size_t* bytes) {
+	static const int nblk[4] = {16, 4, 4, 1}, bit[4] = {0, 16, 20, 24};
+	uint32_t m = 0;
+	size_t pos = 0;
+	for (int g = 0; g < 4; g++)
+		for (int b = 0; b < nblk[g]; b++) {
+			const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src[g] + 16 * b));
+			_mm256_storeu_si256(reinterpret_cast<__m256i*>(out + pos), v);
+			const uint32_t nz = !_mm256_testz_si256(v, v);
+			pos += 32 * nz;
+			m |= nz << (bit[g] + b);
+		}
+	*bytes = pos;
+	return m;
+}
+const bool g_have_avx2 = (__builtin_cpu_init(), __builtin_cpu_supports("avx2") != 0);
+#else
+const bool g_have_avx2 = false;
+#endif
+
+// A chunk's frames are compacted by several host threads into ONE arena, which then crosses the link as one transfer
+// (64 per-frame transfers took 3x as long while the device->host engine was busy: profiles/README.md). Threads take
+// space from a shared cursor: the frame's fixed-size head in one piece, the packed blocks in 64 KiB granules, so no
+// thread needs to know another frame's size. mb_first counts 32-byte blocks from the start of the ARENA, the kernel's
+// packed-block base is the arena itself, and a macroblock's blocks (at most 800 bytes) never straddle a granule.
+constexpr size_t kGranule = 64 << 10;
+size_t compact_bound(size_t mb) {
+	const CompactLayout L = compact_layout(mb);
+	return L.o_packed + (800 * mb / (kGranule - 800) + 2) * kGranule;
+}
+
+// Returns the arena offset of the frame's head ([mb_mask][mb_first][modes...], CompactLayout without the packed part).
+size_t compact_frame(const Vp8DecodedFrame* f, uint8_t* arena, std::atomic<size_t>& cursor) {
 	const size_t mb = (size_t)f->mb_cols * f->mb_rows;
 	const CompactLayout L = compact_layout(mb);
+	const size_t head = cursor.fetch_add(L.o_packed);
+	uint8_t* dst = arena + head;
 	uint32_t* mask = reinterpret_cast<uint32_t*>(dst + L.o_mask);
 	uint32_t* first = reinterpret_cast<uint32_t*>(dst + L.o_first);
-	uint8_t* out = dst + L.o_packed;
-	uint32_t count = 0;
+	size_t pos = 0, end = 0; // current granule, arena offsets
 	for (size_t i = 0; i < mb; i++) {
-		uint32_t m = 0;
-		first[i] = count;
-		const int16_t* src[4] = {f->coeff_y + i * 256, f->coeff_u + i * 64, f->coeff_v + i * 64, f->coeff_y2 + i * 16};
-		const int nblk[4] = {16, 4, 4, 1}, bit[4] = {0, 16, 20, 24};
-		for (int g = 0; g < 4; g++)
-			for (int b = 0; b < nblk[g]; b++) {
-				const int16_t* p = src[g] + 16 * b;
-				if (block_nonzero(p)) {
-					memcpy(out + (size_t)count * 32, p, 32);
-					count++;
-					m |= 1u << (bit[g] + b);
-				}
-			}
-		mask[i] = m;
+		if (end - pos < 800) {
+			pos = cursor.fetch_add(kGranule);
+			end = pos + kGranule;
+		}
+		first[i] = (uint32_t)(pos / 32);
+		const int16_t* const src[4] = {f->coeff_y + i * 256, f->coeff_u + i * 64, f->coeff_v + i * 64, f->coeff_y2 + i * 16};
+		size_t bytes = 0;
+#if defined(__x86_64__)
+		mask[i] = g_have_avx2 ? pack_mb_avx2(src, arena + pos, &bytes) : pack_mb_portable(src, arena + pos, &bytes);
+#else
+		mask[i] = pack_mb_portable(src, arena + pos, &bytes);
+#endif
+		pos += bytes;
+	}
+	// hand the unused tail of the last granule back when nobody has taken space after it
+	if (end > pos) {
+		size_t expect = end;
+		cursor.compare_exchange_strong(expect, pos);
 	}
 	memcpy(dst + L.o_ymode, f->ymode, mb);
 	memcpy(dst + L.o_uv, f->uv_mode, mb);
 	if (f->segmentation_enabled && f->segment_id) memcpy(dst + L.o_seg, f->segment_id, mb);
 	if (f->has_coeff) memcpy(dst + L.o_hc, f->has_coeff, mb);
 	memcpy(dst + L.o_bmode, f->bmode, 16 * mb);
-	return L.o_packed + (size_t)count * 32;
+	return head;
 }
 
 // A batch whose input arena holds compact frames: compacted by host threads into the pinned staging slot, then one
-// transfer per frame of just the bytes in use.
+// transfer of the bytes in use.
 int batch_create_compact(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* fr, int n, int slot,
                          cudaStream_t st, vp8_gpu_batch** out) {
 	vp8_gpu_batch* b = new (std::nothrow) vp8_gpu_batch;
@@ -1173,7 +1302,6 @@ int batch_create_compact(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, con
 	b->stream = st;
 	b->meta.resize(n);
 	size_t in = 0, tight = 0, rgb = 0;
-	std::vector<size_t> frame_off(n);
 	for (int i = 0; i < n; i++) {
 		FrameMeta& m = b->meta[i];
 		const Vp8DecodedFrame* f = fr[i];
@@ -1182,21 +1310,10 @@ int batch_create_compact(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, con
 		m.mb_cols = f->mb_cols;
 		m.mb_rows = f->mb_rows;
 		const size_t mb = (size_t)m.mb_cols * m.mb_rows;
-		const CompactLayout L = compact_layout(mb);
 		m.has_seg = f->segmentation_enabled && f->segment_id;
 		m.has_hc = f->has_coeff != nullptr;
 		m.compact = true;
-		frame_off[i] = in;
-		m.in_off[0] = in + L.o_packed; // packed blocks
-		m.in_off[1] = in + L.o_mask;   // mb_mask
-		m.in_off[2] = in + L.o_first;  // mb_first
-		m.in_off[3] = in;              // (coeff_y2 slot unused)
-		m.in_off[4] = in + L.o_bmode;
-		m.in_off[5] = in + L.o_ymode;
-		m.in_off[6] = in + L.o_uv;
-		m.in_off[7] = in + L.o_seg;
-		m.in_off[8] = in + L.o_hc;
-		in += L.worst;
+		in += compact_bound(mb);
 		const size_t cw = (m.width + 1) / 2, ch = (m.height + 1) / 2;
 		m.tight_off = tight;
 		tight += align_up((size_t)m.width * m.height + 2 * cw * ch);
@@ -1209,6 +1326,10 @@ int batch_create_compact(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, con
 		for (int s = 0; s < (m.has_seg ? 4 : 1); s++)
 			for (int k = 0; k < 2; k++) m.any_filter |= m.lf[s][k][0] != 0;
 		b->max_mb_cols = std::max<int>(b->max_mb_cols, m.mb_cols);
+	}
+	if (in / 32 > 0xffffffffull) {
+		delete b;
+		return fail(EINVAL, "compact chunk exceeds the 32-bit block index; use a smaller chunk");
 	}
 	b->in_bytes = in;
 	b->tight_bytes = tight;
@@ -1233,26 +1354,40 @@ int batch_create_compact(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, con
 	// compaction on host threads, one frame per thread at a time
 	const auto t_c0 = std::chrono::steady_clock::now();
 	uint8_t* stage = c->cstage[slot];
-	std::vector<size_t> used(n);
+	std::atomic<size_t> cursor{0};
 	int threads = c->host_threads > 0 ? c->host_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
 	threads = std::min(threads, n);
 	std::atomic<int> next{0};
 	auto work = [&]() {
-		for (int i; (i = next.fetch_add(1)) < n;) used[i] = compact_frame(fr[i], stage + frame_off[i]);
-	};
-	std::vector<std::thread> pool;
-	for (int t = 1; t < threads; t++) pool.emplace_back(work);
-	work();
-	for (auto& t : pool) t.join();
-	c->trace_compact_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_c0).count();
-	for (int i = 0; i < n; i++) {
-		cudaError_t e = cudaMemcpyAsync(b->d_in + frame_off[i], stage + frame_off[i], used[i], cudaMemcpyHostToDevice, st);
-		if (e != cudaSuccess) {
-			batch_destroy(c, b);
-			return fail(EIO, "compact frame upload", e);
+		for (int i; (i = next.fetch_add(1)) < n;) {
+			const size_t head = compact_frame(fr[i], stage, cursor);
+			const CompactLayout L = compact_layout((size_t)fr[i]->mb_cols * fr[i]->mb_rows);
+			FrameMeta& m = b->meta[i];
+			m.in_off[0] = 0;                 // packed blocks: mb_first indexes the whole arena
+			m.in_off[1] = head + L.o_mask;   // mb_mask
+			m.in_off[2] = head + L.o_first;  // mb_first
+			m.in_off[3] = 0;                 // (coeff_y2 slot unused)
+			m.in_off[4] = head + L.o_bmode;
+			m.in_off[5] = head + L.o_ymode;
+			m.in_off[6] = head + L.o_uv;
+			m.in_off[7] = head + L.o_seg;
+			m.in_off[8] = head + L.o_hc;
 		}
-		c->h2d += used[i];
+	};
+	if (threads > 1 && (!c->pool || c->pool->size() < threads - 1)) {
+		delete c->pool;
+		c->pool = new WorkerPool(threads - 1);
 	}
+	if (threads > 1) c->pool->run(work, threads - 1);
+	else work();
+	c->trace_compact_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_c0).count();
+	const size_t used = cursor.load();
+	cudaError_t e = cudaMemcpyAsync(b->d_in, stage, used, cudaMemcpyHostToDevice, st);
+	if (e != cudaSuccess) {
+		batch_destroy(c, b);
+		return fail(EIO, "compact chunk upload", e);
+	}
+	c->h2d += used;
 	*out = b;
 	return 0;
 }
@@ -1281,8 +1416,8 @@ static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, 
 	CU(cudaEventRecord(c->pipe_ev, c->stream));
 	for (auto& p : c->pipe) CU(cudaStreamWaitEvent(p, c->pipe_ev, 0));
 
-	// Three engines, three streams: pipe[0] carries every host->device copy, pipe[1] the kernels, pipe[2] every
-	// device->host copy; events chain chunk k's stages. A pinned staging slot is free again as soon as its own copies
+	// Three engines: pipe[0] carries every host->device copy, pipe[1]/pipe[2] the kernels of even/odd chunks (a chunk
+	// is too small to fill the GPU, so neighbours may overlap), pipe[3] every device->host copy; events chain chunk k's stages. A pinned staging slot is free again as soon as its own copies
 	// are done, a chunk retires (device blocks back to the cache) when its download is done; up to kDepth chunks in flight.
 	constexpr int kDepth = 6;
 	struct Chunk {
@@ -1305,21 +1440,43 @@ static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, 
 	rc = make_event(&ev_kernel);
 	for (int i = 0; i < kDepth && !rc; i++) rc = make_event(&ring[i].up) || make_event(&ring[i].done);
 	const auto t_p0 = std::chrono::steady_clock::now();
-	c->trace_compact_ms = c->trace_retire_ms = 0;
-	cudaStream_t s_up = c->pipe[0], s_run = c->pipe[1], s_down = c->pipe[2];
-	int k = 0;
-	for (int first = 0; first < n && !rc; first += chunk, k++) {
-		const int cnt = std::min(chunk, n - first), slot = k % 3;
+	c->trace_compact_ms = c->trace_retire_ms = c->trace_malloc_ms = 0;
+	c->trace_mallocs = c->trace_frees = 0;
+	cudaStream_t s_up = c->pipe[0], s_down = c->pipe[3];
+	// VP8_GPU_TRACE=2: device-side timeline, four timed events per chunk (upload start/end, kernels end, download end)
+	const bool timeline = getenv("VP8_GPU_TRACE") && atoi(getenv("VP8_GPU_TRACE")) >= 2;
+	std::vector<cudaEvent_t> tl;
+	std::vector<double> tl_host;
+	auto mark = [&](cudaStream_t s) {
+		if (!timeline) return;
+		cudaEvent_t e;
+		cudaEventCreate(&e);
+		cudaEventRecord(e, s);
+		tl.push_back(e);
+	};
+	if (timeline) mark(s_up);
+	// The device->host engine is the slowest stage, so it should start early and never run dry: the first chunks are
+	// small (short time to the first download), so is the last one (short tail after the last kernel).
+	const int quarter = std::max(1, chunk / 4);
+	int k = 0, cnt = 0;
+	for (int first = 0; first < n && !rc; first += cnt, k++) {
+		const int left = n - first, slot = k % 3;
+		cnt = k < 2 ? quarter : k == 2 ? std::max(1, chunk / 2) : chunk;
+		if (left > quarter && left <= cnt + quarter) cnt = left - quarter;
+		cnt = std::min(cnt, left);
+		cudaStream_t s_run = c->pipe[1 + (k & 1)];
 		Chunk& ch = ring[k % kDepth];
 		const auto t_r0 = std::chrono::steady_clock::now();
 		retire(ch);                                                       // the chunk kDepth steps back
 		if (k >= 3) cudaEventSynchronize(ring[(k - 3) % kDepth].up);      // staging slot reuse: its copies have left the host
 		c->trace_retire_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_r0).count();
 		vp8_gpu_batch* b = nullptr;
+		if (timeline) tl_host.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_p0).count());
 		if (c->compact_transport && c->kernel_version == 2) rc = batch_create_compact(c, kf + first, frames + first, cnt, slot, s_up, &b);
 		else rc = batch_create(c, kf + first, frames + first, cnt, true, &b, s_up);
 		if (rc) break;
 		ch.b = b;
+		mark(s_up);
 		if (cudaEventRecord(ch.up, s_up) != cudaSuccess || cudaStreamWaitEvent(s_run, ch.up, 0) != cudaSuccess) {
 			rc = fail(EIO, "pipeline events", cudaGetLastError());
 			break;
@@ -1328,6 +1485,7 @@ static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, 
 		rc = vp8_gpu_run(c, b, filtered, VP8_GPU_TIGHT);
 		if (!rc && want_ppm) rc = vp8_gpu_rgb(c, b);
 		if (rc) break;
+		mark(s_run);
 		if (cudaEventRecord(ev_kernel, s_run) != cudaSuccess || cudaStreamWaitEvent(s_down, ev_kernel, 0) != cudaSuccess) {
 			rc = fail(EIO, "pipeline events", cudaGetLastError());
 			break;
@@ -1341,23 +1499,34 @@ static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, 
 			rc = download(c, s_down, dst + off[first], b->d_tight, used, false);
 		}
 		if (!rc && cudaEventRecord(ch.done, s_down) != cudaSuccess) rc = fail(EIO, "pipeline events", cudaGetLastError());
+		mark(s_down);
 	}
 	const int saved = errno;
 	const auto t_e0 = std::chrono::steady_clock::now();
-	cudaStreamSynchronize(s_up);
-	cudaStreamSynchronize(s_run);
-	cudaStreamSynchronize(s_down);
+	for (auto& p : c->pipe) cudaStreamSynchronize(p);
 	for (auto& ch : ring) {
 		if (ch.b) batch_destroy(c, ch.b, true);
 		if (ch.up) cudaEventDestroy(ch.up);
 		if (ch.done) cudaEventDestroy(ch.done);
 	}
 	if (ev_kernel) cudaEventDestroy(ev_kernel);
+	if (timeline && !rc) {
+		for (size_t i = 0; i + 3 < tl.size() + 0 && (i / 3) < tl_host.size(); i += 3) {
+			float up = 0, run = 0, down = 0;
+			cudaEventElapsedTime(&up, tl[0], tl[1 + i]);
+			cudaEventElapsedTime(&run, tl[0], tl[2 + i]);
+			cudaEventElapsedTime(&down, tl[0], tl[3 + i]);
+			fprintf(stderr, "[vp8gpu] chunk %2zu: host starts compaction at %6.1f ms | upload done %6.1f | kernels done %6.1f | download done %6.1f\n",
+			        i / 3, tl_host[i / 3], up, run, down);
+		}
+	}
+	for (auto e : tl) cudaEventDestroy(e);
 	if (getenv("VP8_GPU_TRACE")) {
 		const auto now = std::chrono::steady_clock::now();
-		fprintf(stderr, "[vp8gpu] pipelined call: total %.1f ms, host compaction %.1f ms, waiting on slots/retiring chunks %.1f ms, final drain %.1f ms\n",
+		fprintf(stderr, "[vp8gpu] pipelined call: total %.1f ms, host compaction %.1f ms, waiting on slots/retiring chunks %.1f ms, final drain %.1f ms, "
+		        "%d cudaMalloc + %d cudaFree %.1f ms\n",
 		        std::chrono::duration<double, std::milli>(now - t_p0).count(), c->trace_compact_ms, c->trace_retire_ms,
-		        std::chrono::duration<double, std::milli>(now - t_e0).count());
+		        std::chrono::duration<double, std::milli>(now - t_e0).count(), c->trace_mallocs, c->trace_frees, c->trace_malloc_ms);
 	}
 	if (rc) {
 		errno = saved;

@@ -87,6 +87,9 @@ constexpr int kClusterProg = 1024; // progress stamps per image in cluster mode 
 #ifndef VP8P_BLOCK_UNROLL
 #define VP8P_BLOCK_UNROLL 2 // 2: both 4x4 blocks of a lane unrolled, 1: looped
 #endif
+#ifndef VP8P_LF_COMPACT
+#define VP8P_LF_COMPACT 0 // 1: ONE byte-addressed filter body looped over the 12 edge passes (smallest code)
+#endif
 #ifndef VP8P_LF_LOOP
 #define VP8P_LF_LOOP 0 // 1: inner edges 4/8/12 as a loop, 0: unrolled
 #endif
@@ -609,6 +612,29 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 					uint8_t* const ty = ws.ft_y + 4 * 20 + 4;                                   // luma pixel (0,0)
 					uint8_t* const tc = (hl < 8 ? ws.ft_u : ws.ft_v) + 4 * 12 + 4;              // this lane's chroma plane (0,0)
 					const int cn = hl & 7;
+#if VP8P_LF_COMPACT
+					if (__any_sync(FULL, do_f)) {
+						// 12 passes: (plane, direction, edge) packed 4 bits each: bit 0 chroma, bits 1-2 edge/4, bit 3 between rows.
+						// Per plane the reference's order holds: left MB edge, inner columns, top MB edge, inner rows.
+						const unsigned long long kPasses = 0xECBA98643210ull;
+#pragma unroll 1
+						for (int p = 0; p < 12; p++) {
+							const int d = (int)(kPasses >> (4 * p)) & 15;
+							const bool chroma = d & 1, rows_dir = d & 8;
+							const int e = (d & 6) * 2;
+							uint8_t* const base = chroma ? tc : ty;
+							const int stride = chroma ? 12 : 20, n = chroma ? cn : hl;
+							const bool act = (e == 0 ? (rows_dir ? f_top : f_left) : f_in) && !(lf_simple && chroma);
+							if (__any_sync(FULL, act)) {
+								if (act)
+									lf_line(rows_dir ? base + e * stride + n : base + n * stride + e, rows_dir ? stride : 1,
+									        lf_simple ? EDGE_SIMPLE : (e == 0 ? EDGE_MB : EDGE_INNER), e == 0 ? lim_mb : lim_in, interior, hev_thr);
+								__syncwarp();
+							}
+						}
+					}
+
+#else
 					if (__any_sync(FULL, do_f)) {
 						if (!lf_simple) {
 							if (__any_sync(FULL, f_left)) {
@@ -683,6 +709,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 						}
 					}
 
+#endif
 					// ---- store what can no longer change: the 16x16 (8x8) block whose origin is 4 pixels up and left of the
 					//      macroblock; the last column / row of macroblocks also flush the strips nobody else will
 					if (v) {
