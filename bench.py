@@ -165,7 +165,7 @@ def gpu_arm(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx = W.Context(local, stream.cuda_stream)
-    kernel_version = args.kernel or int(os.environ.get("VP8_GPU_KERNEL", "2") or 2)
+    kernel_version = args.kernel or int(os.environ.get("VP8_GPU_KERNEL", "3") or 3)
     ctx.set_kernel(kernel_version)
     if args.warps or args.images_per_sm:
         ctx.set_tuning(args.warps, args.images_per_sm)
@@ -299,7 +299,7 @@ def gpu_arm(args):
                        "launch": cfg, "parity_spot_check_vs_reference_digests": parity},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": ncu_traffic(args.workload, kernel_version), "peak_source": peak_src,
-                         "kernel": "vp8_mb_pairs" if kernel_version == 2 else "vp8_mb_wavefront",
+                         "kernel": {1: "vp8_mb_wavefront", 2: "vp8_mb_pairs", 3: "vp8_mb_lockstep"}[kernel_version],
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": kern_n},
             "cpu_baseline": cpu,
             "host_front_end": host_fe,
@@ -323,7 +323,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="yuvf", choices=["yuvf", "yuv", "ppm"])
     ap.add_argument("--batch", type=int, default=1024, help="frames per GPU per step")
-    ap.add_argument("--kernel", type=int, default=0, help="wavefront kernel: 1 warp per macroblock, 2 half-warp per macroblock (0 = library default)")
+    ap.add_argument("--kernel", type=int, default=0, help="wavefront kernel: 1 warp per macroblock, 2 half-warp per macroblock, 3 = 2 with several images per CTA in lockstep (0 = library default)")
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--images-per-sm", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=5)

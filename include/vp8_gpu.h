@@ -64,8 +64,11 @@ const char* vp8_gpu_last_error(void);
 int vp8_gpu_set_tuning(vp8_gpu_ctx* ctx, int warps_per_image, int images_per_sm);
 
 /* Which wavefront kernel runs m06/m07: 1 = one warp per macroblock (vp8_kernels.cu), 2 = one half-warp per macroblock,
- * two rows per warp (vp8_pairs.cu). Both are bit-exact; the environment variable VP8_GPU_KERNEL presets it. */
+ * two rows per warp (vp8_pairs.cu), 3 = as 2, and batches of several images per SM run its lockstep flavour (one CTA per
+ * SM carries up to 7 images and all its warps meet at a barrier once per macroblock step, which keeps them on the same
+ * instruction-cache lines). All are bit-exact; the environment variable VP8_GPU_KERNEL presets it. */
 int vp8_gpu_set_kernel(vp8_gpu_ctx* ctx, int version);
+int vp8_gpu_last_groups(const vp8_gpu_ctx* ctx); /* images per CTA of the last wavefront launch if it was lockstep, else 0 */
 
 /* Small batches of big frames: the pair kernel can spread ONE image over a thread-block cluster of 2, 4 or 8 CTAs
  * (co-scheduled, exchanging line buffers and progress stamps through L2). 0 = automatic (used when the batch would

@@ -52,7 +52,10 @@ def test_reference_fuzz_digests(gpu_ctx):
     assert not [s for s, p in zip(seeds, ppms) if sha(p) != fz[s]["ppm"]]
 
 
-@pytest.mark.parametrize("kernel,warps", [(1, 4), (1, 8), (1, 16), (1, 32), (2, 4), (2, 8), (2, 16)])
+DEFAULT_KERNEL = 3  # what a fresh context runs (vp8_gpu.h: vp8_gpu_set_kernel)
+
+
+@pytest.mark.parametrize("kernel,warps", [(1, 4), (1, 8), (1, 16), (1, 32), (2, 4), (2, 8), (2, 16), (3, 4), (3, 16)])
 def test_fuzz_vs_oracle_all_kernels_and_warp_shapes(gpu_ctx, oracle, kernel, warps):
     """Both wavefront kernels (warp per macroblock / half-warp per macroblock) in every CTA shape."""
     gpu_ctx.set_kernel(kernel)
@@ -70,7 +73,7 @@ def test_fuzz_vs_oracle_all_kernels_and_warp_shapes(gpu_ctx, oracle, kernel, war
                 assert np.array_equal(o, oracle.decode_i420(f, filtered)), (f.width, f.height, filtered)
     finally:
         gpu_ctx.set_tuning(0, 0)
-        gpu_ctx.set_kernel(2)
+        gpu_ctx.set_kernel(DEFAULT_KERNEL)
 
 
 def test_first_generation_kernel_still_matches_reference_digests(gpu_ctx, golden, parsed_golden):
@@ -83,7 +86,7 @@ def test_first_generation_kernel_still_matches_reference_digests(gpu_ctx, golden
             outs = gpu_ctx.decode_i420(kfs, frs, filtered=filtered)
             assert not [n for n, o in zip(names, outs) if sha(o) != golden[n][key]]
     finally:
-        gpu_ctx.set_kernel(2)
+        gpu_ctx.set_kernel(DEFAULT_KERNEL)
 
 
 def test_edge_geometries(gpu_ctx, oracle):
@@ -100,7 +103,7 @@ def test_edge_geometries(gpu_ctx, oracle):
         assert p == oracle.ppm(oracle.rgb(yuvf, f.width, f.height), f.width, f.height), (f.width, f.height)
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_maximum_frame_dimensions(gpu_ctx, oracle, kernel):
     """VP8 dimensions are 14-bit (vp8_header.c:46-49): the widest (1024 macroblock columns: largest line buffers) and the
     tallest (1024 macroblock rows: longest wavefront, progress ring wrap-around) frames a bitstream can carry."""
@@ -114,7 +117,60 @@ def test_maximum_frame_dimensions(gpu_ctx, oracle, kernel):
         f = fuzz_frame(77, 16383, 17, density=0.05)
         assert gpu_ctx.decode_ppm([f.header()], [f.cstruct()])[0] == oracle.ppm(oracle.rgb(oracle.decode_i420(f, True), 16383, 17), 16383, 17)
     finally:
-        gpu_ctx.set_kernel(2)
+        gpu_ctx.set_kernel(DEFAULT_KERNEL)
+
+
+@pytest.mark.parametrize("per_cta", [2, 5, 7])
+def test_lockstep_flavour_several_images_per_cta(gpu_ctx, oracle, per_cta):
+    """Kernel 3, lockstep flavour: one CTA carries several images (4 warps each) and all its warps meet at a barrier once
+    per macroblock step. Mixed sizes in one CTA, frames with a single row pair (three of the four warps never get work),
+    frames taller than the progress ring (64 rows), more images than slots (every group takes several in turn), the
+    stand-alone loop filter through the same schedule."""
+    dims = [(64, 48), (129, 129), (300, 90), (17, 33), (48, 200), (1, 1), (33, 1100), (500, 16), (16, 16), (250, 250)]
+    frames = [fuzz_frame(1200 + s, *dims[s % len(dims)], density=[0.3, 0.02, 0.9, 0.0][s % 4], amp=[40, 400, 2500][s % 3], raw=bool(s & 1))
+              for s in range(43)]
+    kfs, ds = [f.header() for f in frames], [f.cstruct() for f in frames]
+    gpu_ctx.set_kernel(3)
+    gpu_ctx.set_tuning(4, per_cta)
+    try:
+        for filtered in (False, True):
+            outs = gpu_ctx.decode_i420(kfs, ds, filtered=filtered)
+            assert gpu_ctx.last_launch_config()["images_per_cta"] == per_cta
+            bad = [i for i, (f, o) in enumerate(zip(frames, outs)) if not np.array_equal(o, oracle.decode_i420(f, filtered))]
+            assert not bad, (per_cta, filtered, bad)
+        # staged: m06 into padded planes, m07 in place, both through the lockstep schedule
+        b = gpu_ctx.recon(kfs[:12], ds[:12])
+        gpu_ctx.filter(b)
+        assert gpu_ctx.last_launch_config()["images_per_cta"] == per_cta
+        for i in range(12):
+            oy, ou, ov = oracle.recon_padded(frames[i])
+            oracle.loopfilter_padded(frames[i], oy, ou, ov)
+            y, u, v = gpu_ctx.download_padded(b, i)
+            assert np.array_equal(y, oy) and np.array_equal(u, ou) and np.array_equal(v, ov), i
+        b.free()
+    finally:
+        gpu_ctx.set_tuning(0, 0)
+        gpu_ctx.set_kernel(DEFAULT_KERNEL)
+
+
+def test_lockstep_is_what_big_batches_run_by_default(gpu_ctx, oracle):
+    """No tuning: a batch of several images per SM takes the lockstep flavour on its own; very wide frames get fewer
+    images per CTA (their line buffers fill the shared memory sooner)."""
+    frames = [fuzz_frame(3000 + s, 32 + 16 * (s % 3), 32 + 16 * (s % 2), density=0.2) for s in range(720)]
+    outs = gpu_ctx.decode_i420([f.header() for f in frames], [f.cstruct() for f in frames], filtered=True)
+    cfg = gpu_ctx.last_launch_config()
+    assert cfg["images_per_cta"] >= 2 and cfg["warps_per_image"] == 4, cfg
+    bad = [i for i, (f, o) in enumerate(zip(frames, outs)) if not np.array_equal(o, oracle.decode_i420(f, True))]
+    assert not bad, bad[:8]
+    wide = [fuzz_frame(3900 + s, 16383, 17, density=0.05) for s in range(6)]
+    gpu_ctx.set_tuning(4, 7)
+    try:
+        outs = gpu_ctx.decode_i420([f.header() for f in wide], [f.cstruct() for f in wide], filtered=True)
+        cfg = gpu_ctx.last_launch_config()
+        assert 2 <= cfg["images_per_cta"] < 7, cfg
+        assert all(np.array_equal(o, oracle.decode_i420(f, True)) for f, o in zip(wide, outs))
+    finally:
+        gpu_ctx.set_tuning(0, 0)
 
 
 @pytest.mark.parametrize("ctas", [1, 2, 4, 8])
@@ -284,6 +340,27 @@ def test_pipelined_decode_matches_digests(lib, gpu_ctx, golden, parsed_golden):
         gpu_ctx.set_transport(True, 0)
     with pytest.raises(OSError):
         gpu_ctx.decode_into(kfs, frs, np.empty(10, np.uint8))
+
+
+@pytest.mark.parametrize("chunk", [1, 2, 5, 16, 1000])
+def test_pipelined_chunk_schedule_and_arena_granules(gpu_ctx, oracle, chunk):
+    """The pipelined call ramps its chunk sizes (chunk/4, chunk/4, chunk/2, chunk ..., short last chunk) and several
+    host threads compact a chunk into one arena in 64 KiB granules: dense frames that span many granules, sparse ones
+    that fit in one, odd sizes, every chunk size against the oracle."""
+    frames = [fuzz_frame(900 + s, [300, 64, 129, 17, 400][s % 5], [280, 48, 129, 33, 90][s % 5],
+                         density=[0.9, 0.02, 0.3, 0.0][s % 4], amp=[40, 400, 2500][s % 3], raw=bool(s & 1)) for s in range(23)]
+    kfs = [f.header() for f in frames]
+    frs = [f.cstruct() for f in frames]
+    want = [oracle.decode_i420(f, True) for f in frames]
+    try:
+        for threads in (1, 4):
+            gpu_ctx.set_transport(True, threads)
+            out = np.full(gpu_ctx.decode_bytes(kfs), 0x55, np.uint8)
+            offs, sizes = gpu_ctx.decode_into(kfs, frs, out, filtered=True, chunk=chunk)
+            bad = [i for i, (o, s) in enumerate(zip(offs, sizes)) if not np.array_equal(out[int(o):int(o) + int(s)], want[i])]
+            assert not bad, (chunk, threads, bad)
+    finally:
+        gpu_ctx.set_transport(True, 0)
 
 
 def test_argument_errors(lib, gpu_ctx):

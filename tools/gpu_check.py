@@ -51,7 +51,7 @@ def report(name, got, want, w, h, limit=6):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--kernel", type=int, default=1, help="1 = warp per macroblock, 2 = half-warp per macroblock")
+    ap.add_argument("--kernel", type=int, default=1, help="1 = warp per macroblock, 2 = half-warp per macroblock, 3 = 2 + lockstep")
     args = ap.parse_args()
     orc = Oracle()
     ctx = W.Context(0)
@@ -130,6 +130,21 @@ def main():
     good = sum(np.array_equal(o, orc.decode_i420(f, True)) for o, f in zip(outs, frames))
     print(f"[batch of 64 mixed sizes] {good}/64 frames equal ({time.time() - t0:.2f}s)")
     ok &= good == 64
+    if args.kernel == 3:
+        # lockstep flavour: several images per CTA, forced through the tuning knobs so that a small batch takes it
+        frames = [fuzz_frame(700 + s, [64, 129, 300, 17, 48][s % 5], [48, 129, 90, 33, 200][s % 5],
+                             density=[0.3, 0.02, 0.9, 0.0][s % 4], amp=[40, 400, 2500][s % 3], raw=bool(s & 1)) for s in range(45)]
+        want_f = [orc.decode_i420(f, True) for f in frames]
+        want_u = [orc.decode_i420(f, False) for f in frames]
+        for per_cta in (2, 3, 7):
+            ctx.set_tuning(4, per_cta)
+            for filtered, want in ((True, want_f), (False, want_u)):
+                outs = ctx.decode_i420([f.header() for f in frames], [f.cstruct() for f in frames], filtered=filtered)
+                good = sum(np.array_equal(o, w) for o, w in zip(outs, want))
+                cfg = ctx.last_launch_config()
+                print(f"[lockstep {per_cta} images per CTA, filtered={filtered}] {good}/{len(frames)} frames equal, launch {cfg}")
+                ok &= good == len(frames) and cfg["images_per_cta"] == per_cta
+        ctx.set_tuning(0, 0)
     print("ALL OK" if ok else "FAILURES")
     return 0 if ok else 1
 

@@ -36,6 +36,47 @@ __global__ void __launch_bounds__(128) body_kernel(unsigned* out, int iters, int
 	if ((a ^ b ^ c ^ d) == 0x12345678u) out[threadIdx.x] = a; // keep the chains alive
 }
 
+// Same total body, but cut into PHASES pieces with a CTA-wide barrier after each piece: the 28 warps of a 896-thread CTA
+// walk one piece (BLOCKS / PHASES blocks) together before any of them enters the next.
+template <int BLOCKS, int PHASES>
+__global__ void __launch_bounds__(896) phased_kernel(unsigned* out, int iters) {
+	unsigned a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 7, c = a ^ 0x9e3779b9u, d = b + 0x7f4a7c15u;
+	for (int it = 0; it < iters; it++) {
+#pragma unroll
+		for (int k = 0; k < BLOCKS; k++) {
+			a = a * (2 * k + 3) + b;
+			c = c * (2 * k + 5) + d;
+			b = (b >> 3) ^ a;
+			d = (d >> 5) ^ c;
+			a += c & (k + 1);
+			c += a | (k + 2);
+			if ((k + 1) % (BLOCKS / PHASES) == 0) __syncthreads();
+		}
+	}
+	if ((a ^ b ^ c ^ d) == 0x12345678u) out[threadIdx.x] = a;
+}
+
+template <int BLOCKS, int PHASES>
+static void run_phased(unsigned* out, int sms, double khz) {
+	const int iters = 64 * 4096 / BLOCKS;
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	phased_kernel<BLOCKS, PHASES><<<sms, 896>>>(out, iters / 8);
+	cudaEventRecord(e0);
+	phased_kernel<BLOCKS, PHASES><<<sms, 896>>>(out, iters);
+	cudaEventRecord(e1);
+	cudaEventSynchronize(e1);
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	const double blocks = (double)iters * BLOCKS * 28;
+	printf("{\"blocks\": %d, \"approx_body_bytes\": %d, \"ctas_per_sm\": 1, \"arrangement\": \"one 28-warp CTA, barrier every %d bytes\", "
+	       "\"ms\": %.3f, \"blocks_per_us_per_sm\": %.2f, \"blocks_per_kcycle_per_scheduler_at_max_clock\": %.2f}\n",
+	       BLOCKS, 10 * BLOCKS * 16, 10 * BLOCKS * 16 / PHASES, ms, blocks / (ms * 1e3), blocks / 4 / (ms * khz) * 1e3);
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+}
+
 template <int BLOCKS>
 static void run(unsigned* out, int ctas_per_sm, int sms, double khz) {
 	const int iters = 64 * 4096 / BLOCKS; // same number of executed blocks for every size
@@ -80,6 +121,12 @@ int main(int argc, char** argv) {
 		run<512>(out, cps, sms, khz);
 		run<768>(out, cps, sms, khz);
 	}
+	run_phased<384, 1>(out, sms, khz);
+	run_phased<384, 3>(out, sms, khz);
+	run_phased<384, 6>(out, sms, khz);
+	run_phased<384, 12>(out, sms, khz);
+	run_phased<768, 6>(out, sms, khz);
+	run_phased<768, 12>(out, sms, khz);
 	cudaError_t e = cudaDeviceSynchronize();
 	if (e != cudaSuccess) {
 		fprintf(stderr, "cuda error: %s\n", cudaGetErrorString(e));

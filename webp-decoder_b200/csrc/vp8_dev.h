@@ -81,4 +81,10 @@ int vp8_launch_pairs(int mode, int warps_per_image, const Vp8ImgDesc* descs_dev,
 int vp8_pairs_smem_bytes(int warps_per_image, int max_mb_cols);
 int vp8_pairs_max_ctas_per_sm(int mode, int warps_per_image, int max_mb_cols);
 size_t vp8_pairs_scratch_bytes(int slots, int max_mb_cols);
+// Lockstep flavour of the pair kernel (vp8_pairs.cu): one CTA carries `groups` images (1..7, 4 warps each) and all its warps
+// meet at a barrier once per macroblock step. grid_ctas x groups slots; scratch = vp8_pairs_scratch_bytes(grid_ctas * groups, cols).
+int vp8_launch_lockstep(int mode, const Vp8ImgDesc* descs_dev, int n_images, int max_mb_cols, int grid_ctas, int groups, uint8_t* scratch,
+                        void* stream);
+int vp8_lockstep_smem_bytes(int groups, int max_mb_cols);
+int vp8_lockstep_max_groups(int max_mb_cols); // how many groups fit in the shared memory of one SM for this frame width (0: none)
 int vp8_launch_rgb(const Vp8RgbDesc* descs_dev, int n_images, uint32_t total_blocks, void* stream);

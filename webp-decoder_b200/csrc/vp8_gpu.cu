@@ -137,7 +137,9 @@ struct vp8_gpu_ctx {
 	int tune_warps = 0, tune_imgs_per_sm = 0;
 	int tune_cluster = 0; // CTAs per image in cluster mode: 0 = automatic, 1 = never, 2/4/8 = at most that many
 	int last_cluster = 1;
-	int kernel_version = 2; // 1: vp8_mb_wavefront (warp per macroblock), 2: vp8_mb_pairs (half-warp per macroblock)
+	int kernel_version = 3; // 1: vp8_mb_wavefront (warp per macroblock), 2: vp8_mb_pairs (half-warp per macroblock),
+	                        // 3: as 2, and big batches run its lockstep flavour (several images per CTA, barrier per step)
+	int last_groups = 0;    // images per CTA of the last launch when it was the lockstep flavour, else 0
 	uint8_t* bounce[2] = {nullptr, nullptr};
 	cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
 	bool bounce_busy[2] = {false, false};
@@ -638,7 +640,7 @@ int pick_warps(const vp8_gpu_ctx* c, int n_images) {
 
 int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layout) {
 	if (push_descs(c, b, kernel_mode, layout)) return -1;
-	const bool pairs = c->kernel_version == 2;
+	const bool pairs = c->kernel_version >= 2;
 	int warps = pick_warps(c, b->n);
 	if (pairs) warps = std::min(warps, 16); // a pair-kernel warp already carries two macroblock rows
 	int per_sm = 0;
@@ -661,8 +663,21 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 		cluster = want;
 		if (cluster > 1) grid = std::min(b->n, c->sm_count / cluster) * cluster;
 	}
+	// Many images: the lockstep flavour packs `groups` of them into one CTA per SM (kernel 3 only, where the classic
+	// choice would be 4 warps per image anyway).
+	int groups = 0;
+	if (c->kernel_version == 3 && warps == 4 && cluster == 1) {
+		int g = vp8_lockstep_max_groups(b->max_mb_cols);
+		if (c->tune_warps == 4 && c->tune_imgs_per_sm > 0) g = std::min(g, c->tune_imgs_per_sm); // explicit: whatever the batch size
+		else g = std::min(g, (b->n + c->sm_count - 1) / c->sm_count);
+		g = std::min(g, b->n);
+		if (g >= 2) {
+			groups = g;
+			grid = std::min(c->sm_count, (b->n + groups - 1) / groups);
+		}
+	}
 	if (pairs) {
-		const size_t need = vp8_pairs_scratch_bytes(cluster > 1 ? grid / cluster : grid, b->max_mb_cols);
+		const size_t need = vp8_pairs_scratch_bytes(groups ? grid * groups : cluster > 1 ? grid / cluster : grid, b->max_mb_cols);
 		if (b->scratch_bytes < need) {
 			dev_release(c, b->d_scratch, b->scratch_bytes);
 			b->d_scratch = nullptr;
@@ -680,8 +695,9 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 		CU(cudaEventCreate(&ev.second));
 	}
 	CU(cudaEventRecord(ev.first, b->stream));
-	const int rc = pairs ? vp8_launch_pairs(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, b->d_scratch, cluster, b->stream)
-	                     : vp8_launch_wavefront(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, b->stream);
+	const int rc = groups ? vp8_launch_lockstep(kernel_mode, b->d_desc, b->n, b->max_mb_cols, grid, groups, b->d_scratch, b->stream)
+	               : pairs ? vp8_launch_pairs(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, b->d_scratch, cluster, b->stream)
+	                       : vp8_launch_wavefront(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, b->stream);
 	CU(cudaEventRecord(ev.second, b->stream));
 	c->timed.push_back(ev);
 	if (c->timed.size() > 4096) { // nobody is asking: recycle the oldest
@@ -693,7 +709,8 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 	c->last_warps = warps;
 	c->last_grid = grid;
 	c->last_cluster = cluster;
-	c->last_smem = pairs ? vp8_pairs_smem_bytes(warps, b->max_mb_cols) : vp8_wavefront_smem_bytes(kernel_mode, warps, b->max_mb_cols);
+	c->last_groups = groups;
+	c->last_smem = groups ? vp8_lockstep_smem_bytes(groups, b->max_mb_cols) : pairs ? vp8_pairs_smem_bytes(warps, b->max_mb_cols) : vp8_wavefront_smem_bytes(kernel_mode, warps, b->max_mb_cols);
 	return 0;
 }
 
@@ -914,7 +931,7 @@ int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out) {
 		}
 		c->own_stream = true;
 	}
-	if (const char* k = getenv("VP8_GPU_KERNEL")) c->kernel_version = atoi(k) == 1 ? 1 : 2;
+	if (const char* k = getenv("VP8_GPU_KERNEL")) c->kernel_version = std::min(3, std::max(1, atoi(k)));
 	if (const char* w = getenv("VP8_GPU_WARPS")) c->tune_warps = atoi(w);
 	if (const char* w = getenv("VP8_GPU_CLUSTER")) c->tune_cluster = atoi(w);
 	if (const char* w = getenv("VP8_GPU_HOST_THREADS")) c->host_threads = atoi(w);
@@ -978,9 +995,10 @@ int vp8_gpu_set_cluster(vp8_gpu_ctx* c, int ctas_per_image) {
 }
 
 int vp8_gpu_last_cluster(const vp8_gpu_ctx* c) { return c ? c->last_cluster : 0; }
+int vp8_gpu_last_groups(const vp8_gpu_ctx* c) { return c ? c->last_groups : 0; }
 
 int vp8_gpu_set_kernel(vp8_gpu_ctx* c, int version) {
-	if (!c || (version != 1 && version != 2)) return fail(EINVAL, "bad kernel version");
+	if (!c || (version < 1 || version > 3)) return fail(EINVAL, "bad kernel version");
 	c->kernel_version = version;
 	return 0;
 }
@@ -1472,7 +1490,7 @@ static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, 
 		c->trace_retire_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_r0).count();
 		vp8_gpu_batch* b = nullptr;
 		if (timeline) tl_host.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_p0).count());
-		if (c->compact_transport && c->kernel_version == 2) rc = batch_create_compact(c, kf + first, frames + first, cnt, slot, s_up, &b);
+		if (c->compact_transport && c->kernel_version >= 2) rc = batch_create_compact(c, kf + first, frames + first, cnt, slot, s_up, &b);
 		else rc = batch_create(c, kf + first, frames + first, cnt, true, &b, s_up);
 		if (rc) break;
 		ch.b = b;

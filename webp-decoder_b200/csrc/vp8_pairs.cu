@@ -100,6 +100,13 @@ constexpr int kClusterProg = 1024; // progress stamps per image in cluster mode 
 #define VP8_PAIR_MIN_CTAS(NW) ((NW) == 4 ? 7 : (NW) == 8 ? 3 : 1)
 #endif
 
+// compact layout: packed blocks / per-macroblock mask / first-block index live behind the re-purposed coeff pointers;
+// they are re-read from the shared-memory descriptor at each use to keep registers free
+#define G_COMPACT (sd->compact != 0)
+#define G_PACKED reinterpret_cast<const uint8_t*>(sd->coeff_y)
+#define G_MASK reinterpret_cast<const uint32_t*>(sd->coeff_u)
+#define G_FIRST reinterpret_cast<const uint32_t*>(sd->coeff_v)
+
 // CL = false: one CTA per image, unfiltered line buffer and progress stamps in shared memory.
 // CL = true : one thread-block CLUSTER per image (launched with a cluster dimension, so its CTAs are co-scheduled and may
 //             spin on each other): row pairs are dealt round-robin to the warps of all CTAs of the cluster; the unfiltered
@@ -192,601 +199,231 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 			__syncthreads();
 		}
 
-		const int cols = sd->mb_cols, rows = sd->mb_rows;
-		OutPlane oy{sd->out_y, sd->out_stride_y, sd->out_w, sd->out_h,
-		            ((reinterpret_cast<uintptr_t>(sd->out_y) | sd->out_stride_y) & 3) == 0};
-		const uint32_t ocw = (sd->out_w + 1) >> 1, och = (sd->out_h + 1) >> 1;
-		OutPlane ou{sd->out_u, sd->out_stride_uv, ocw, och,
-		            ((reinterpret_cast<uintptr_t>(sd->out_u) | sd->out_stride_uv) & 3) == 0};
-		OutPlane ov{sd->out_v, sd->out_stride_uv, ocw, och,
-		            ((reinterpret_cast<uintptr_t>(sd->out_v) | sd->out_stride_uv) & 3) == 0};
-		const bool words_ok = oy.word_ok && ou.word_ok && ov.word_ok;
-		const bool lf_simple = sd->lf_simple != 0;
-		const uint8_t* const g_ymode = sd->ymode;
-		const uint8_t* const g_seg = sd->segment_id;
-		const uint8_t* const g_hc = sd->has_coeff;
-		// compact layout: packed blocks / per-macroblock mask / first-block index live behind the re-purposed coeff pointers;
-		// they are re-read from the shared-memory descriptor at each use to keep registers free
-#define G_COMPACT (sd->compact != 0)
-#define G_PACKED reinterpret_cast<const uint8_t*>(sd->coeff_y)
-#define G_MASK reinterpret_cast<const uint32_t*>(sd->coeff_u)
-#define G_FIRST reinterpret_cast<const uint32_t*>(sd->coeff_v)
+		int cols, rows;
+		OutPlane oy, ou, ov;
+		bool words_ok, lf_simple;
+		const uint8_t *g_ymode, *g_seg, *g_hc;
+#include "vp8_pairs_image.inc"
 
 		for (int p = c_rank * NW + warp; 2 * p < rows; p += NW * c_size) {
-			const int y = 2 * p + half;
-			const bool row_ok = y < rows;
-			const bool last_row = (y == rows - 1);
-			const size_t mb_row0 = (size_t)y * cols;
-
-			// ---- row start: out-of-frame left neighbours (129) and corner (127 on the top row, else 129)
-			const int16_t* cptr = sd->coeff_y2;
-			int x_pref = 0; // next macroblock column whose coefficients have not been requested yet
-			uint32_t staged_nz = 3; // compact layout: which of the lane's two staged blocks are present (dense layout: both)
-			if (RECON) {
-				ws.lcol[hl] = 129;
-				ws.lcol[16 + hl] = 129;
-				ws.rt_y[(hl + 1) * 24 + 3] = 129;
-				if (hl < 8) ws.rt_u[(hl + 1) * 12 + 3] = 129;
-				else ws.rt_v[(hl - 8 + 1) * 12 + 3] = 129;
-				const uint8_t corner = (y == 0) ? 127 : 129;
-				if (hl == 0) ws.rt_y[3] = corner;
-				if (hl == 1) ws.rt_u[3] = corner;
-				if (hl == 2) ws.rt_v[3] = corner;
-				if (row_ok && !G_COMPACT) {
-					if (tl_luma) cptr = sd->coeff_y + (mb_row0 * 16 + 2 * hl) * 16;
-					else if (hl < 10) cptr = sd->coeff_u + (mb_row0 * 4 + 2 * (hl - 8)) * 16;
-					else if (hl < 12) cptr = sd->coeff_v + (mb_row0 * 4 + 2 * (hl - 10)) * 16;
-					else cptr = sd->coeff_y2 + mb_row0 * 16;
-				}
-				if (half == 0 && row_ok) { // row y starts at step 0: its first macroblock's blocks go on their way now
-					if (G_COMPACT) {
-						staged_nz = fetch_compact(ws, G_PACKED, G_MASK[mb_row0], G_FIRST[mb_row0], bit0, hl);
-					} else if (hl < 13) {
-						cp_async16(&ws.coef[0 * 13 + hl], cptr);
-						cp_async16(&ws.coef[1 * 13 + hl], cptr + 8);
-						if (hl < 12) {
-							cp_async16(&ws.coef[2 * 13 + hl], cptr + 16);
-							cp_async16(&ws.coef[3 * 13 + hl], cptr + 24);
-						}
-					}
-					cptr += cstep;
-					x_pref = 1;
-				}
-				cp_async_commit();
-			}
+			int y, x_pref;
+			bool row_ok, last_row;
+			size_t mb_row0;
+			const int16_t* cptr;
+			uint32_t staged_nz;
+#include "vp8_pairs_row.inc"
 
 			for (int t = 0; t < cols + 2; t++) {
-				const int x = t - 2 * half;
-				const bool v = row_ok && x >= 0 && x < cols; // this half has a macroblock in this step
-				const bool last_col = (x == cols - 1);
-				const size_t mb = mb_row0 + (size_t)(v ? x : 0);
-
-				// ---- per-macroblock syntax
-				int ymode = 0, seg = 0, uvmode = 0, bmode = 0;
-				bool bpred = false, inner = false;
-				if (v) {
-					ymode = g_ymode[mb];
-					bpred = (ymode == 4);
-					if (g_seg) seg = g_seg[mb] & 3;
-					inner = bpred || (g_hc && g_hc[mb]);
-					if (RECON) {
-						uvmode = sd->uv_mode[mb];
-						if (bpred) bmode = min((int)sd->bmode[mb * 16 + hl], 10);
-					}
-				}
-
-				// ---- row y (half 0) waits for MB(x+1, y-1), which another warp produces; row y+1 trails row y by design
-				if (p > 0 && t < cols) {
-					if (lane == 0) {
-						const int target = 2 * p * kStampRow + min(t + 2, cols);
-						while (prog[(2 * p - 1) & prog_mask] < target) __nanosleep(64);
-						if (CL) __threadfence();
-						else __threadfence_block();
-					}
-				}
-				__syncwarp();
-
-				// ---- filtered rows of the row above: requested now, needed only when the filter tile is assembled
-				uint32_t ta_y = 0, ta_c = 0;
-				if (FILTER && v && y > 0) {
-					ta_y = ldcg32(tf_y + (hl >> 2) * line_px + 16 * x + 4 * (hl & 3));
-					ta_c = ldcg32((hl < 8 ? tf_u : tf_v) + ((hl & 7) >> 1) * line_c + 8 * x + 4 * (hl & 1));
-				}
-
-				if (RECON) {
-					// ================================================================== m06: reconstruction
-					// ---- top border (row -1) from the unfiltered line buffer, 127 above the frame
-					if (v && hl < 9) {
-						uint32_t w = 0x7f7f7f7fu;
-						if (y > 0) {
-							if (hl < 5) {
-								if (hl == 4 && last_col) w = 0x01010101u * (ld_line<CL>(tu_y + 16 * x + 12) >> 24);
-								else w = ld_line<CL>(tu_y + 16 * x + 4 * hl);
-							} else if (hl < 7) {
-								w = ld_line<CL>(tu_u + 8 * x + 4 * (hl - 5));
-							} else {
-								w = ld_line<CL>(tu_v + 8 * x + 4 * (hl - 7));
-							}
-						}
-						if (hl < 5) {
-							st32(ws.rt_y + 4 + 4 * hl, w);
-							if (hl == 4) { // above-right of sub-block column 3 always comes from the MB row above
-								st32(ws.rt_y + 4 * 24 + 20, w);
-								st32(ws.rt_y + 8 * 24 + 20, w);
-								st32(ws.rt_y + 12 * 24 + 20, w);
-							}
-						} else if (hl < 7) {
-							st32(ws.rt_u + 4 + 4 * (hl - 5), w);
-						} else {
-							st32(ws.rt_v + 4 + 4 * (hl - 7), w);
-						}
-					}
-
-					// ---- coefficients have landed
-					cp_async_wait_all();
-					__syncwarp();
-
-					const int16_t* dq = sd->dq[seg];
-					// ---- Y2: lane 12 runs the WHT, luma lanes take their DC from it (vp8_recon.c:563-586)
-					if (v && !bpred && hl == 12) {
-						const uint4 c0 = ws.coef[0 * 13 + 12], c1 = ws.coef[1 * 13 + 12];
-						uint4* z = reinterpret_cast<uint4*>(ws.res[0]);
-						if (!(staged_nz & 1) || (c0.x | c0.y | c0.z | c0.w | c1.x | c1.y | c1.z | c1.w) == 0) {
-							z[0] = make_uint4(0, 0, 0, 0);
-							z[1] = make_uint4(0, 0, 0, 0);
-						} else {
-							const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-							const int dcq = dq[4], acq = dq[5];
-							int vv[16], d[16];
-#pragma unroll
-							for (int i = 0; i < 8; i++) {
-								vv[2 * i] = s16(s16(cw[i]) * (i == 0 ? dcq : acq));
-								vv[2 * i + 1] = s16(((int)cw[i] >> 16) * acq);
-							}
-							iwht4x4(vv, d);
-							uint32_t pk[8];
-#pragma unroll
-							for (int i = 0; i < 8; i++) pk[i] = (uint32_t)(d[2 * i] & 0xffff) | ((uint32_t)d[2 * i + 1] << 16);
-							z[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-							z[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-						}
-					}
-					__syncwarp();
-
-					// ---- two 4x4 blocks per lane: dequantise, inverse DCT, then predict + add (i16 luma, chroma) or park the
-					//      residual for the sub-block pass (B_PRED luma)
-					if (v && hl < 12) {
-						const int dcq = tl_luma ? dq[0] : dq[2], acq = tl_luma ? dq[1] : dq[3];
-						uint8_t* tile;
-						const uint8_t* lc;
-						int stride, nwords, mode;
-						if (tl_luma) { tile = ws.rt_y; lc = ws.lcol; stride = 24; nwords = 4; mode = ymode; }
-						else if (hl < 10) { tile = ws.rt_u; lc = ws.lcol + 16; stride = 12; nwords = 2; mode = uvmode; }
-						else { tile = ws.rt_v; lc = ws.lcol + 24; stride = 12; nwords = 2; mode = uvmode; }
-						const bool park = tl_luma && bpred;
-
-						// prediction that does not depend on the block column: left word, DC value
-						uint32_t lw = 0, dcw = 0;
-						int tm_p = 0;
-						if (!park) {
-							lw = ld32(lc + tl_by);
-							tm_p = tile[3];
-							if (mode != 1 && mode != 2 && mode != 3) { // DC (also any out-of-range mode): vp8_recon.c:152-176
-								uint32_t sum = 0;
-								const bool have_a = y > 0, have_l = x > 0;
-								for (int k = 0; k < nwords; k++) {
-									if (have_a) sum += sum4(ld32(tile + 4 + 4 * k));
-									if (have_l) sum += sum4(ld32(lc + 4 * k));
-								}
-								const int lg = (nwords == 4) ? 4 : 3;
-								uint32_t dcv;
-								if (have_a && have_l) dcv = (sum + (1u << lg)) >> (lg + 1);
-								else if (have_a || have_l) dcv = (sum + (1u << (lg - 1))) >> lg;
-								else dcv = 128;
-								dcw = dcv * 0x01010101u;
-							}
-						}
-
-						VP8P_UNROLL(VP8P_BLOCK_UNROLL)
-						for (int k = 0; k < 2; k++) {
-							uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
-							if (staged_nz & (1u << k)) {
-								c0 = ws.coef[(2 * k) * 13 + hl];
-								c1 = ws.coef[(2 * k + 1) * 13 + hl];
-							}
-							const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-							const int bi = 2 * hl + k; // luma block index (raster) when tl_luma
-							int r[16];
-							bool any;
-							{
-								int vv[16];
-								int dc_override = 0;
-								const bool use_override = tl_luma && !bpred;
-								if (use_override) dc_override = ws.res[0][bi];
-								// quick outs on the raw words: nothing coded at all / only the DC slot
-								const uint32_t ac_raw = (cw[0] & 0xffff0000u) | cw[1] | cw[2] | cw[3] | cw[4] | cw[5] | cw[6] | cw[7];
-								if (ac_raw == 0) {
-									const int v0 = use_override ? dc_override : s16(s16(cw[0]) * dcq);
-									const int dc = s16((v0 + 4) >> 3);
-									any = dc != 0;
-#pragma unroll
-									for (int i = 0; i < 16; i++) r[i] = dc;
-								} else {
-#pragma unroll
-									for (int i = 0; i < 8; i++) {
-										vv[2 * i] = s16(s16(cw[i]) * (i == 0 ? dcq : acq));
-										vv[2 * i + 1] = s16(((int)cw[i] >> 16) * acq);
-									}
-									if (use_override) vv[0] = dc_override;
-									idct4x4(vv, r);
-									any = true;
-								}
-							}
-							if (park) {
-								uint32_t pk[8];
-#pragma unroll
-								for (int i = 0; i < 8; i++) pk[i] = (uint32_t)(r[2 * i] & 0xffff) | ((uint32_t)r[2 * i + 1] << 16);
-								uint4* dst = reinterpret_cast<uint4*>(ws.res[bi]);
-								dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-								dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-							} else {
-								const int bx = tl_bx0 + 4 * k;
-								uint32_t pw[4];
-								if (mode == 1) { // V
-									const uint32_t a = ld32(tile + 4 + bx);
-									pw[0] = pw[1] = pw[2] = pw[3] = a;
-								} else if (mode == 2) { // H
-#pragma unroll
-									for (int j = 0; j < 4; j++) pw[j] = ((lw >> (8 * j)) & 255u) * 0x01010101u;
-								} else if (mode == 3) { // TM
-									const uint32_t a = ld32(tile + 4 + bx);
-#pragma unroll
-									for (int j = 0; j < 4; j++) {
-										const int base = (int)((lw >> (8 * j)) & 255u) - tm_p;
-										uint32_t w = 0;
-#pragma unroll
-										for (int i = 0; i < 4; i++) w |= (uint32_t)add_clip255(base, (int)((a >> (8 * i)) & 255u)) << (8 * i);
-										pw[j] = w;
-									}
-								} else {
-									pw[0] = pw[1] = pw[2] = pw[3] = dcw;
-								}
-								uint8_t* dst = tile + (tl_by + 1) * stride + 4 + bx;
-#pragma unroll
-								for (int j = 0; j < 4; j++) {
-									uint32_t w = pw[j];
-									if (any) {
-										uint32_t o = 0;
-#pragma unroll
-										for (int i = 0; i < 4; i++) o |= (uint32_t)add_clip255((int)((w >> (8 * i)) & 255u), r[4 * j + i]) << (8 * i);
-										w = o;
-									}
-									st32(dst + j * stride, w);
-								}
-							}
-						}
-					}
-					__syncwarp();
-
-					// ---- staged coefficients are consumed: request the next macroblock of this half's row
-					if (row_ok && x + 1 == x_pref && x_pref < cols) {
-						if (G_COMPACT) {
-							staged_nz = fetch_compact(ws, G_PACKED, G_MASK[mb_row0 + x_pref], G_FIRST[mb_row0 + x_pref], bit0, hl);
-						} else if (hl < 13) {
-							cp_async16(&ws.coef[0 * 13 + hl], cptr);
-							cp_async16(&ws.coef[1 * 13 + hl], cptr + 8);
-							if (hl < 12) {
-								cp_async16(&ws.coef[2 * 13 + hl], cptr + 16);
-								cp_async16(&ws.coef[3 * 13 + hl], cptr + 24);
-							}
-						}
-						cptr += cstep;
-						x_pref++;
-					}
-					cp_async_commit();
-
-					// ---- B_PRED luma: 16 sub-blocks in raster order, one lane per pixel (both halves at once)
-					const bool bp = v && bpred;
-					if (__any_sync(FULL, bp)) {
-						const uint32_t sp = __ballot_sync(FULL, bp && (bmode <= 1 || bmode == 10));
-						const uint32_t spm = (sp | (sp >> 16)) & 0xffffu; // sub-blocks needing B_DC / B_TM / 128 in either half
-						VP8P_UNROLL(VP8P_BPRED_UNROLL)
-						for (int s = 0; s < 16; s++) {
-							const int tile_c = ((s >> 2) * 4 + 1) * 24 + 4 + (s & 3) * 4; // pixel (0,0) of sub-block s
-							const int mode = __shfl_sync(FULL, bmode, hbit | s);
-							uint32_t tw = 0;
-							int e = 0, rs = 0;
-							if (bp) {
-								tw = *reinterpret_cast<const uint32_t*>(bp_tab + mode * 64);
-								e = bp_edge[tile_c];
-								rs = bp_res[s * 16];
-							}
-							const int a = __shfl_sync(FULL, e, tw);
-							const int b = __shfl_sync(FULL, e, tw >> 8);
-							const int c = __shfl_sync(FULL, e, tw >> 16);
-							int pv = (a + c + 2 + 2 * b) >> 2;
-							if (spm & (1u << s)) {
-								const uint32_t kind = tw >> 24;
-								if (kind == 1) pv = clip255(a + b - c);
-								// B_DC: (A0..A3 + L0..L3 + 4) >> 3; one reduction serves both halves (low / high 16 bits)
-								const int mine = dc_tap ? (e << hbit) : 0;
-								const int both = __reduce_add_sync(FULL, mine);
-								if (kind == 2) pv = (((both >> hbit) & 0xffff) + 4) >> 3;
-								if (kind == 3) pv = 128;
-							}
-							if (bp) bp_out[tile_c] = (uint8_t)add_clip255(pv, rs);
-							__syncwarp();
-						}
-					}
-				} else {
-					// ================================================================== stand-alone m07: load the MB
-					if (v) {
-						const uint8_t* sy = sd->src_y + (size_t)(16 * y) * sd->src_stride_y + 16 * x;
-#pragma unroll
-						for (int j = 0; j < 4; j++) {
-							const int i = hl + 16 * j, row = i >> 2, wc = i & 3;
-							st32(ws.rt_y + (row + 1) * 24 + 4 + 4 * wc, ld32(sy + (size_t)row * sd->src_stride_y + 4 * wc));
-						}
-#pragma unroll
-						for (int j = 0; j < 2; j++) {
-							const int row = hl >> 1, wc = hl & 1;
-							const uint8_t* sp = (j ? sd->src_v : sd->src_u) + (size_t)(8 * y + row) * sd->src_stride_uv + 8 * x + 4 * wc;
-							st32((j ? ws.rt_v : ws.rt_u) + (row + 1) * 12 + 4 + 4 * wc, ld32(sp));
-						}
-					}
-					__syncwarp();
-				}
-
-				// ---- snapshot of the unfiltered tile that the neighbours will need (read phase)
-				uint32_t edge_y = 0, edge_c = 0, bot_w = 0, corner_b = 0;
-				if (RECON && v) {
-					edge_y = ws.rt_y[(hl + 1) * 24 + 4 + 15];
-					edge_c = (hl < 8) ? ws.rt_u[(hl + 1) * 12 + 4 + 7] : ws.rt_v[(hl - 8 + 1) * 12 + 4 + 7];
-					if (hl < 4) bot_w = ld32(ws.rt_y + 16 * 24 + 4 + 4 * hl);
-					else if (hl < 6) bot_w = ld32(ws.rt_u + 8 * 12 + 4 + 4 * (hl - 4));
-					else if (hl < 8) bot_w = ld32(ws.rt_v + 8 * 12 + 4 + 4 * (hl - 6));
-					if (hl == 8) corner_b = ws.rt_y[4 + 15];
-					if (hl == 9) corner_b = ws.rt_u[4 + 7];
-					if (hl == 10) corner_b = ws.rt_v[4 + 7];
-				}
-
-				if (!FILTER) {
-					// ================================================================== unfiltered output (-yuv)
-					if (v) {
-						const bool fast = words_ok && !last_col && !last_row;
-#pragma unroll
-						for (int j = 0; j < 4; j++) {
-							const int i = hl + 16 * j, row = i >> 2, wc = i & 3;
-							const uint32_t w = ld32(ws.rt_y + (row + 1) * 24 + 4 + 4 * wc);
-							if (fast) st32(oy.p + (size_t)(16 * y + row) * oy.stride + 16 * x + 4 * wc, w);
-							else put_word(oy, 16 * x + 4 * wc, 16 * y + row, w);
-						}
-#pragma unroll
-						for (int j = 0; j < 2; j++) {
-							const int row = hl >> 1, wc = hl & 1;
-							const uint32_t w = ld32((j ? ws.rt_v : ws.rt_u) + (row + 1) * 12 + 4 + 4 * wc);
-							if (fast) st32((j ? ov.p : ou.p) + (size_t)(8 * y + row) * ou.stride + 8 * x + 4 * wc, w);
-							else put_word(j ? ov : ou, 8 * x + 4 * wc, 8 * y + row, w);
-						}
-					}
-				} else {
-					// ================================================================== m07: loop filter
-					// ---- assemble the filter tile: left apron = previous tile's right 4 columns (all 20 / 12 rows, so the
-					//      corner above-left travels along), top apron = the prefetched tf words, interior = the reconstruction
-					{
-						uint32_t la0, la1, la2 = 0, in[4], ic[2];
-						la0 = ld32(ws.ft_y + (hl + 4) * 20 + 16);                                  // luma rows 0..15
-						la1 = (hl < 4) ? ld32(ws.ft_y + hl * 20 + 16) : ld32(ws.ft_u + (hl - 4) * 12 + 8); // luma rows -4..-1, U rows -4..7
-						if (hl < 12) la2 = ld32(ws.ft_v + hl * 12 + 8);                            // V rows -4..7
-#pragma unroll
-						for (int j = 0; j < 4; j++) {
-							const int i = hl + 16 * j;
-							in[j] = ld32(ws.rt_y + ((i >> 2) + 1) * 24 + 4 + 4 * (i & 3));
-						}
-						ic[0] = ld32(ws.rt_u + ((hl >> 1) + 1) * 12 + 4 + 4 * (hl & 1));
-						ic[1] = ld32(ws.rt_v + ((hl >> 1) + 1) * 12 + 4 + 4 * (hl & 1));
-						__syncwarp();
-						st32(ws.ft_y + (hl + 4) * 20, la0);
-						if (hl < 4) st32(ws.ft_y + hl * 20, la1);
-						else st32(ws.ft_u + (hl - 4) * 12, la1);
-						if (hl < 12) st32(ws.ft_v + hl * 12, la2);
-						st32(ws.ft_y + (hl >> 2) * 20 + 4 + 4 * (hl & 3), ta_y);
-						st32((hl < 8 ? ws.ft_u : ws.ft_v) + ((hl & 7) >> 1) * 12 + 4 + 4 * (hl & 1), ta_c);
-#pragma unroll
-						for (int j = 0; j < 4; j++) {
-							const int i = hl + 16 * j;
-							st32(ws.ft_y + ((i >> 2) + 4) * 20 + 4 + 4 * (i & 3), in[j]);
-						}
-						st32(ws.ft_u + ((hl >> 1) + 4) * 12 + 4 + 4 * (hl & 1), ic[0]);
-						st32(ws.ft_v + ((hl >> 1) + 4) * 12 + 4 + 4 * (hl & 1), ic[1]);
-						__syncwarp();
-					}
-
-					// ---- edge filters in the reference's order per plane (vp8_loopfilter.c:226-277); both halves in lockstep,
-					//      16 luma lines, then 8 U + 8 V lines
-					const uint8_t* lfp = sd->lf[seg][bpred ? 1 : 0];
-					const int level = lfp[0], interior = lfp[1], hev_thr = lfp[2];
-					const bool do_f = v && level > 0;
-					const int lim_mb = 2 * (level + 2) + interior, lim_in = 2 * level + interior;
-					const bool f_left = do_f && x > 0, f_top = do_f && y > 0, f_in = do_f && inner;
-					uint8_t* const ty = ws.ft_y + 4 * 20 + 4;                                   // luma pixel (0,0)
-					uint8_t* const tc = (hl < 8 ? ws.ft_u : ws.ft_v) + 4 * 12 + 4;              // this lane's chroma plane (0,0)
-					const int cn = hl & 7;
-#if VP8P_LF_COMPACT
-					if (__any_sync(FULL, do_f)) {
-						// 12 passes: (plane, direction, edge) packed 4 bits each: bit 0 chroma, bits 1-2 edge/4, bit 3 between rows.
-						// Per plane the reference's order holds: left MB edge, inner columns, top MB edge, inner rows.
-						const unsigned long long kPasses = 0xECBA98643210ull;
-#pragma unroll 1
-						for (int p = 0; p < 12; p++) {
-							const int d = (int)(kPasses >> (4 * p)) & 15;
-							const bool chroma = d & 1, rows_dir = d & 8;
-							const int e = (d & 6) * 2;
-							uint8_t* const base = chroma ? tc : ty;
-							const int stride = chroma ? 12 : 20, n = chroma ? cn : hl;
-							const bool act = (e == 0 ? (rows_dir ? f_top : f_left) : f_in) && !(lf_simple && chroma);
-							if (__any_sync(FULL, act)) {
-								if (act)
-									lf_line(rows_dir ? base + e * stride + n : base + n * stride + e, rows_dir ? stride : 1,
-									        lf_simple ? EDGE_SIMPLE : (e == 0 ? EDGE_MB : EDGE_INNER), e == 0 ? lim_mb : lim_in, interior, hev_thr);
-								__syncwarp();
-							}
-						}
-					}
-
-#else
-					if (__any_sync(FULL, do_f)) {
-						if (!lf_simple) {
-							if (__any_sync(FULL, f_left)) {
-								if (f_left) lf_across_columns<EDGE_MB>(ty + hl * 20, lim_mb, interior, hev_thr);
-								if (f_left) lf_across_columns<EDGE_MB>(tc + cn * 12, lim_mb, interior, hev_thr);
-								__syncwarp();
-							}
-							const bool any_in = __any_sync(FULL, f_in);
-#if VP8P_LF_LOOP
-							if (any_in) {
-								if (f_in) lf_across_columns<EDGE_INNER>(tc + cn * 12 + 4, lim_in, interior, hev_thr);
-#pragma unroll 1
-								for (int e = 4; e < 16; e += 4) {
-									if (f_in) lf_across_columns<EDGE_INNER>(ty + hl * 20 + e, lim_in, interior, hev_thr);
-									__syncwarp();
-								}
-							}
-							if (__any_sync(FULL, f_top)) {
-								if (f_top) lf_across_rows<EDGE_MB>(ty + hl, 20, lim_mb, interior, hev_thr);
-								if (f_top) lf_across_rows<EDGE_MB>(tc + cn, 12, lim_mb, interior, hev_thr);
-								__syncwarp();
-							}
-							if (any_in) {
-								if (f_in) lf_across_rows<EDGE_INNER>(tc + 4 * 12 + cn, 12, lim_in, interior, hev_thr);
-#pragma unroll 1
-								for (int e = 4; e < 16; e += 4) {
-									if (f_in) lf_across_rows<EDGE_INNER>(ty + e * 20 + hl, 20, lim_in, interior, hev_thr);
-									__syncwarp();
-								}
-							}
-#else
-							if (any_in) {
-								if (f_in) lf_across_columns<EDGE_INNER>(ty + hl * 20 + 4, lim_in, interior, hev_thr);
-								if (f_in) lf_across_columns<EDGE_INNER>(tc + cn * 12 + 4, lim_in, interior, hev_thr);
-								__syncwarp();
-								if (f_in) lf_across_columns<EDGE_INNER>(ty + hl * 20 + 8, lim_in, interior, hev_thr);
-								__syncwarp();
-								if (f_in) lf_across_columns<EDGE_INNER>(ty + hl * 20 + 12, lim_in, interior, hev_thr);
-								__syncwarp();
-							}
-							if (__any_sync(FULL, f_top)) {
-								if (f_top) lf_across_rows<EDGE_MB>(ty + hl, 20, lim_mb, interior, hev_thr);
-								if (f_top) lf_across_rows<EDGE_MB>(tc + cn, 12, lim_mb, interior, hev_thr);
-								__syncwarp();
-							}
-							if (any_in) {
-								if (f_in) lf_across_rows<EDGE_INNER>(ty + 4 * 20 + hl, 20, lim_in, interior, hev_thr);
-								if (f_in) lf_across_rows<EDGE_INNER>(tc + 4 * 12 + cn, 12, lim_in, interior, hev_thr);
-								__syncwarp();
-								if (f_in) lf_across_rows<EDGE_INNER>(ty + 8 * 20 + hl, 20, lim_in, interior, hev_thr);
-								__syncwarp();
-								if (f_in) lf_across_rows<EDGE_INNER>(ty + 12 * 20 + hl, 20, lim_in, interior, hev_thr);
-								__syncwarp();
-							}
-#endif
-						} else {
-							// simple filter: luma only (vp8_loopfilter.c:228-244)
-							if (f_left) lf_across_columns<EDGE_SIMPLE>(ty + hl * 20, lim_mb, 0, 0);
-							__syncwarp();
-#pragma unroll 1
-							for (int e = 4; e < 16; e += 4) {
-								if (f_in) lf_across_columns<EDGE_SIMPLE>(ty + hl * 20 + e, lim_in, 0, 0);
-								__syncwarp();
-							}
-							if (f_top) lf_across_rows<EDGE_SIMPLE>(ty + hl, 20, lim_mb, 0, 0);
-							__syncwarp();
-#pragma unroll 1
-							for (int e = 4; e < 16; e += 4) {
-								if (f_in) lf_across_rows<EDGE_SIMPLE>(ty + e * 20 + hl, 20, lim_in, 0, 0);
-								__syncwarp();
-							}
-						}
-					}
-
-#endif
-					// ---- store what can no longer change: the 16x16 (8x8) block whose origin is 4 pixels up and left of the
-					//      macroblock; the last column / row of macroblocks also flush the strips nobody else will
-					if (v) {
-						const bool fast = words_ok && x > 0 && y > 0 && !last_col && !last_row;
-#pragma unroll
-						for (int j = 0; j < 4; j++) {
-							const int i = hl + 16 * j, row = i >> 2, wc = i & 3; // tile rows -4..11, word columns -1..2
-							const uint32_t w = ld32(ws.ft_y + row * 20 + 4 * wc);
-							if (fast) st32(oy.p + (size_t)(16 * y - 4 + row) * oy.stride + (16 * x - 4 + 4 * wc), w);
-							else put_word(oy, 16 * x - 4 + 4 * wc, 16 * y - 4 + row, w);
-						}
-#pragma unroll
-						for (int j = 0; j < 2; j++) {
-							const int row = hl >> 1, wc = hl & 1;
-							const uint32_t w = ld32((j ? ws.ft_v : ws.ft_u) + row * 12 + 4 * wc);
-							if (fast) st32((j ? ov.p : ou.p) + (size_t)(8 * y - 4 + row) * ou.stride + (8 * x - 4 + 4 * wc), w);
-							else put_word(j ? ov : ou, 8 * x - 4 + 4 * wc, 8 * y - 4 + row, w);
-						}
-						if (last_col) { // right strip: columns 12..15 (4..7), rows -4..11 (-4..3)
-							put_word(oy, 16 * x + 12, 16 * y - 4 + hl, ld32(ws.ft_y + hl * 20 + 16));
-							put_word(hl < 8 ? ou : ov, 8 * x + 4, 8 * y - 4 + cn, ld32((hl < 8 ? ws.ft_u : ws.ft_v) + cn * 12 + 8));
-						}
-						if (last_row) { // bottom strip: rows 12..15 (4..7), columns -4..15 (-4..7)
-							{
-								const int rr = hl >> 2, ww = hl & 3;
-								put_word(oy, 16 * x - 4 + 4 * ww, 16 * y + 12 + rr, ld32(ws.ft_y + (16 + rr) * 20 + 4 * ww));
-								if (last_col && ww == 0) put_word(oy, 16 * x + 12, 16 * y + 12 + rr, ld32(ws.ft_y + (16 + rr) * 20 + 16));
-							}
-							{
-								const int rr = (hl & 7) >> 1, ww = hl & 1;
-								uint8_t* fc = hl < 8 ? ws.ft_u : ws.ft_v;
-								put_word(hl < 8 ? ou : ov, 8 * x - 4 + 4 * ww, 8 * y + 4 + rr, ld32(fc + (8 + rr) * 12 + 4 * ww));
-								if (last_col && ww == 0) put_word(hl < 8 ? ou : ov, 8 * x + 4, 8 * y + 4 + rr, ld32(fc + (8 + rr) * 12 + 8));
-							}
-						}
-						if (!last_row) { // hand the bottom 4 filtered rows to the row below: columns -4..11 (+12..15 on the last column)
-							if (x > 0 || (hl & 3)) stcg32(tf_y + (hl >> 2) * line_px + 16 * x - 4 + 4 * (hl & 3), ld32(ws.ft_y + ((hl >> 2) + 16) * 20 + 4 * (hl & 3)));
-							if (x > 0 || (hl & 1))
-								stcg32((hl < 8 ? tf_u : tf_v) + (cn >> 1) * line_c + 8 * x - 4 + 4 * (hl & 1),
-								       ld32((hl < 8 ? ws.ft_u : ws.ft_v) + ((cn >> 1) + 8) * 12 + 4 * (hl & 1)));
-							if (last_col) {
-								if (hl < 4) stcg32(tf_y + hl * line_px + 16 * x + 12, ld32(ws.ft_y + (hl + 16) * 20 + 16));
-								else if (hl < 12) {
-									const int k = hl - 4;
-									stcg32(((k >> 2) ? tf_v : tf_u) + (k & 3) * line_c + 8 * x + 4, ld32(((k >> 2) ? ws.ft_v : ws.ft_u) + ((k & 3) + 8) * 12 + 8));
-								}
-							}
-						}
-					}
-				}
-
-				// ---- hand the unfiltered borders on (write phase) and publish progress
-				__syncwarp();
-				if (RECON && v) {
-					ws.lcol[hl] = (uint8_t)edge_y;
-					ws.lcol[16 + hl] = (uint8_t)edge_c;
-					ws.rt_y[(hl + 1) * 24 + 3] = (uint8_t)edge_y;
-					if (hl < 8) ws.rt_u[(hl + 1) * 12 + 3] = (uint8_t)edge_c;
-					else ws.rt_v[(hl - 8 + 1) * 12 + 3] = (uint8_t)edge_c;
-					if (hl == 8) ws.rt_y[3] = (uint8_t)corner_b;
-					if (hl == 9) ws.rt_u[3] = (uint8_t)corner_b;
-					if (hl == 10) ws.rt_v[3] = (uint8_t)corner_b;
-					if (!last_row) {
-						if (hl < 4) st_line<CL>(tu_y + 16 * x + 4 * hl, bot_w);
-						else if (hl < 6) st_line<CL>(tu_u + 8 * x + 4 * (hl - 4), bot_w);
-						else if (hl < 8) st_line<CL>(tu_v + 8 * x + 4 * (hl - 6), bot_w);
-					}
-				}
-				__syncwarp();
-				if (hl == 0 && v) {
-					if (CL) __threadfence();
-					else __threadfence_block();
-					prog[y & prog_mask] = (y + 1) * kStampRow + x + 1;
-				}
+#include "vp8_pairs_step.inc"
 			}
 		}
 	}
+}
+
+// ------------------------------------------------------------------------------------------------ lockstep flavour
+// Same warps, same step (vp8_pairs_step.inc), different schedule. The step is ~2500 instructions of mostly straight-line
+// code, far beyond the 32 KB instruction cache of an SM: 28 independent warps stream it from L2 at 28 different places
+// and the SM issues ~0.55 instructions per cycle per scheduler whatever the occupancy (tools/icache_probe.cu reproduces
+// this with plain integer code: 0.56 skewed, 0.83 when the warps of ONE CTA meet at a barrier once per pass). So here
+// ONE CTA per SM carries up to 7 images (a GROUP of NW warps each, private line buffers and stamps), and all its warps
+// meet at one CTA-wide barrier per step: they walk the step's code side by side and share every fetched line.
+//
+// A barrier inside a loop needs every warp to come round the same number of times, so nothing in this loop blocks:
+// a warp whose dependency (stamp of the row above) or next image is not ready yet simply sits the step out, and the
+// loop ends when no warp has work left (__syncthreads_or). Image hand-over inside a group: warps count themselves out
+// (ctl[0]); when all NW have, the group's first warp loads the next descriptor and publishes it (ctl[1]).
+constexpr int kLockMaxGroups = 7;
+#ifndef VP8P_LOCK_PER_SCHEDULER
+#define VP8P_LOCK_PER_SCHEDULER 0 // 1: only the warps that share a scheduler (same index in their group) meet at the barrier
+#endif
+// Barrier + OR-reduction among the `count` threads that use barrier `id`.
+__device__ __forceinline__ bool bar_red_or(int id, int count, bool pred) {
+	uint32_t r;
+	asm volatile(
+	    "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %3, 0;\n\tbar.red.or.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(r)
+	    : "r"(id), "r"(count), "r"((uint32_t)pred)
+	    : "memory");
+	return r != 0;
+}
+
+// Per-image values every warp of a group needs but only now and then: kept in shared memory, not in registers.
+struct LockImage {
+	OutPlane oy, ou, ov;
+	int all_words, simple;
+};
+constexpr int kLockGroupFixed = 256 + 256 + 16 + 96; // progress ring + image descriptor + hand-over counters + LockImage
+static_assert(sizeof(LockImage) <= 96, "LockImage slot");
+__device__ __forceinline__ void lock_image_init(LockImage* gi, const Vp8ImgDesc* sd) {
+	const uint32_t ocw = (sd->out_w + 1) >> 1, och = (sd->out_h + 1) >> 1;
+	gi->oy = OutPlane{sd->out_y, sd->out_stride_y, sd->out_w, sd->out_h, ((reinterpret_cast<uintptr_t>(sd->out_y) | sd->out_stride_y) & 3) == 0};
+	gi->ou = OutPlane{sd->out_u, sd->out_stride_uv, ocw, och, ((reinterpret_cast<uintptr_t>(sd->out_u) | sd->out_stride_uv) & 3) == 0};
+	gi->ov = OutPlane{sd->out_v, sd->out_stride_uv, ocw, och, ((reinterpret_cast<uintptr_t>(sd->out_v) | sd->out_stride_uv) & 3) == 0};
+	gi->all_words = gi->oy.word_ok && gi->ou.word_ok && gi->ov.word_ok;
+	gi->simple = sd->lf_simple != 0;
+}
+
+template <int NW, bool RECON, bool FILTER>
+__global__ void __launch_bounds__(NW * 32 * kLockMaxGroups, 1)
+vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, uint8_t* __restrict__ tf_scratch) {
+	constexpr bool CL = false;
+	constexpr uint32_t FULL = 0xffffffffu;
+	constexpr int prog_mask = kProgRing - 1;
+	static_assert(4 * NW <= kProgRing, "progress ring too small");
+	extern __shared__ __align__(16) uint8_t smem[];
+	uint32_t* btab = reinterpret_cast<uint32_t*>(smem);
+	const int line_c = line_px / 2;
+	const int groups = blockDim.x / (NW * 32);
+	const int lane = threadIdx.x & 31, group = (threadIdx.x >> 5) / NW, warp = (threadIdx.x >> 5) % NW;
+	const int hl = lane & 15, half = lane >> 4, hbit = lane & 16;
+	const int slot = blockIdx.x * groups + group;
+
+	uint8_t* const gs = smem + kBtabWords * 4 + (size_t)group * (kLockGroupFixed + 2 * line_px + NW * 2 * sizeof(HalfWs));
+	volatile int* prog = reinterpret_cast<volatile int*>(gs);
+	Vp8ImgDesc* sd = reinterpret_cast<Vp8ImgDesc*>(gs + 256);
+	volatile int* ctl = reinterpret_cast<volatile int*>(gs + 512); // [0] warps that finished an image (running total), [1] images loaded
+	LockImage* const gi = reinterpret_cast<LockImage*>(gs + 528);
+	uint8_t* tu_y = gs + kLockGroupFixed; // unfiltered bottom rows of the row above
+	uint8_t* tu_u = tu_y + line_px;
+	uint8_t* tu_v = tu_u + line_px / 2;
+	HalfWs& ws = reinterpret_cast<HalfWs*>(gs + kLockGroupFixed + 2 * line_px)[warp * 2 + half];
+	// per-slot scratch in global memory (L2), same layout as the classic kernel: [tf: 8 x line][unused 2 x line][unused stamps]
+	uint8_t* const sc = tf_scratch + (size_t)slot * ((size_t)10 * line_px + kClusterProg * 4);
+	uint8_t* tf_y = sc;
+	uint8_t* tf_u = tf_y + 4 * line_px;
+	uint8_t* tf_v = tf_u + 2 * line_px;
+
+	if (RECON) {
+		for (int i = threadIdx.x; i < kBtabWords; i += blockDim.x) {
+			const int h = i / 176, m = (i % 176) / 16, p = i % 16, base = h * 16;
+			uint32_t a = 0, b = 0, c = 0, kind = 0;
+			if (m == 0) kind = 2;
+			else if (m == 1) { a = 5 - (p >> 2); b = 7 + (p & 3); c = 6; kind = 1; }
+			else if (m == 10) kind = 3;
+			else {
+				const int tap = c_bpred_taps[m * 16 + p], t0 = tap & 15;
+				a = t0; b = t0 + 1; c = (tap & 16) ? t0 : t0 + 2;
+			}
+			btab[i] = (base + a) | ((base + b) << 8) | ((base + c) << 16) | (kind << 24);
+		}
+	}
+	if (warp == 0 && lane < 2) ctl[lane] = 0;
+	__syncthreads();
+
+	// lane roles inside a half, as in vp8_mb_pairs
+	const bool tl_luma = hl < 8, tl_chroma = hl >= 8 && hl < 12;
+	const int tl_by = tl_luma ? (hl >> 1) * 4 : (hl & 1) * 4;
+	const int tl_bx0 = tl_luma ? (hl & 1) * 8 : 0;
+	const int cstep = tl_luma ? 256 : (tl_chroma ? 64 : 16);
+	const int bit0 = tl_luma ? 2 * hl : (hl < 10 ? 16 + 2 * (hl - 8) : (hl < 12 ? 20 + 2 * (hl - 10) : 24));
+	const int px_r = hl >> 2, px_c = hl & 3;
+	const int e_dy = hl <= 2 ? 3 : (hl <= 5 ? 5 - hl : -1);
+	const int e_dx = hl <= 6 ? -1 : (hl == 15 ? 7 : hl - 7);
+	uint8_t* const bp_edge = ws.rt_y + e_dy * 24 + e_dx;
+	uint8_t* const bp_out = ws.rt_y + px_r * 24 + px_c;
+	const int16_t* const bp_res = &ws.res[0][0] + hl;
+	const uint8_t* const bp_tab = reinterpret_cast<const uint8_t*>(btab + half * 176 + hl);
+	const bool dc_tap = (hl >= 2 && hl <= 5) || (hl >= 7 && hl <= 10);
+
+	enum { ST_IMAGE, ST_ROW, ST_STEP, ST_DONE };
+	int state = ST_IMAGE, taken = 0; // taken: images this warp has finished
+	int p = 0, t = 0;
+	int cols = 0, rows = 0;
+	const OutPlane &oy = gi->oy, &ou = gi->ou, &ov = gi->ov;
+#define words_ok (gi->all_words != 0)
+#define lf_simple (gi->simple != 0)
+#define g_ymode (sd->ymode)
+#define g_seg (sd->segment_id)
+#define g_hc (sd->has_coeff)
+	int y = 0, x_pref = 0;
+	bool row_ok = false, last_row = false;
+	size_t mb_row0 = 0;
+	const int16_t* cptr = nullptr;
+	uint32_t staged_nz = 0;
+
+	for (;;) {
+#if VP8P_LOCK_PER_SCHEDULER
+		// warps with the same index in their group sit on the same scheduler (warp id mod 4): they share its instruction
+		// buffer, the four sets are free to drift apart
+		if (!bar_red_or(1 + warp, groups * 32, state != ST_DONE)) break;
+#else
+		if (!__syncthreads_or(state != ST_DONE)) break;
+#endif
+		if (state == ST_DONE) continue;
+		if (state == ST_IMAGE) {
+			const long long img = slot + (long long)taken * (gridDim.x * groups);
+			if (img >= n_images) {
+				state = ST_DONE;
+				continue;
+			}
+			if (ctl[1] <= taken) {
+				// not loaded yet: the group's first warp does it once everybody has left the previous image
+				if (warp == 0 && ctl[0] == NW * taken) {
+					const uint32_t* src = reinterpret_cast<const uint32_t*>(descs + img);
+					uint32_t* dst = reinterpret_cast<uint32_t*>(sd);
+					for (int i = lane; i < (int)(sizeof(Vp8ImgDesc) / 4); i += 32) dst[i] = src[i];
+					for (int i = lane; i < kProgRing; i += 32) prog[i] = 0;
+					__syncwarp();
+					if (lane == 0) {
+						lock_image_init(gi, sd);
+						__threadfence_block();
+						ctl[1] = taken + 1;
+					}
+				}
+				continue;
+			}
+			__threadfence_block();
+			cols = sd->mb_cols;
+			rows = sd->mb_rows;
+			p = warp;
+			state = ST_ROW;
+		}
+		if (state == ST_ROW) {
+			if (2 * p >= rows) { // this warp has no row pair left in the image
+				__syncwarp();
+				if (lane == 0) {
+					__threadfence_block();
+					atomicAdd(const_cast<int*>(ctl), 1);
+				}
+				taken++;
+				state = ST_IMAGE;
+				continue;
+			}
+#include "vp8_pairs_row.inc"
+			t = 0;
+			state = ST_STEP;
+		}
+		// row y (half 0) needs MB(x+1, y-1) of the row above, which another warp of the group produces
+		if (p > 0 && t < cols) {
+			const int target = 2 * p * kStampRow + min(t + 2, cols);
+			const bool there = prog[(2 * p - 1) & prog_mask] >= target;
+			if (!__all_sync(FULL, there)) continue;
+			__threadfence_block();
+		}
+#define VP8P_STEP_NO_SPIN
+		{
+#include "vp8_pairs_step.inc"
+		}
+#undef VP8P_STEP_NO_SPIN
+		if (++t == cols + 2) {
+			p += NW;
+			state = ST_ROW;
+		}
+	}
+#undef words_ok
+#undef lf_simple
+#undef g_ymode
+#undef g_seg
+#undef g_hc
+}
+
+template <int NW, bool RECON, bool FILTER>
+int launch_lockstep_t(const Vp8ImgDesc* descs, int n, int line_px, int grid, int groups, size_t smem, uint8_t* scratch, cudaStream_t st) {
+	auto k = vp8_mb_lockstep<NW, RECON, FILTER>;
+	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return (int)e;
+	k<<<grid, NW * 32 * groups, smem, st>>>(descs, n, line_px, scratch);
+	return (int)cudaGetLastError();
 }
 
 template <int NW, bool RECON, bool FILTER>
@@ -862,4 +499,31 @@ int vp8_launch_pairs(int mode, int warps_per_image, const Vp8ImgDesc* descs_dev,
 int vp8_pairs_max_ctas_per_sm(int mode, int warps_per_image, int max_mb_cols) {
 	const size_t smem = (size_t)vp8_pairs_smem_bytes(warps_per_image, max_mb_cols);
 	VP8_PAIRS_DISPATCH(occupancy_pairs_t, smem)
+}
+
+// ---- lockstep flavour: `groups` images per CTA (1..7), 4 warps each
+int vp8_lockstep_smem_bytes(int groups, int max_mb_cols) {
+	return kBtabWords * 4 + groups * (kLockGroupFixed + 2 * 16 * max_mb_cols + 4 * 2 * (int)sizeof(HalfWs));
+}
+
+int vp8_lockstep_max_groups(int max_mb_cols) {
+	int dev = 0, limit = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+	int g = kLockMaxGroups;
+	while (g > 0 && vp8_lockstep_smem_bytes(g, max_mb_cols) > limit) g--;
+	return g;
+}
+
+int vp8_launch_lockstep(int mode, const Vp8ImgDesc* descs_dev, int n_images, int max_mb_cols, int grid_ctas, int groups, uint8_t* scratch,
+                        void* stream) {
+	if (groups < 1 || groups > kLockMaxGroups) return (int)cudaErrorInvalidValue;
+	const size_t smem = (size_t)vp8_lockstep_smem_bytes(groups, max_mb_cols);
+	const int line_px = 16 * max_mb_cols;
+	cudaStream_t st = (cudaStream_t)stream;
+	switch (mode) {
+		case VP8_K_RECON: return launch_lockstep_t<4, true, false>(descs_dev, n_images, line_px, grid_ctas, groups, smem, scratch, st);
+		case VP8_K_RECON_FILTER: return launch_lockstep_t<4, true, true>(descs_dev, n_images, line_px, grid_ctas, groups, smem, scratch, st);
+		case VP8_K_FILTER: return launch_lockstep_t<4, false, true>(descs_dev, n_images, line_px, grid_ctas, groups, smem, scratch, st);
+		default: return -1;
+	}
 }
