@@ -79,6 +79,23 @@ __device__ __forceinline__ uint32_t fetch_compact(HalfWs& ws, const uint8_t* pac
 	return nz;
 }
 
+// Dense layout (the reference's own arrays): request this lane's blocks of macroblock `mb` (lanes 0..7 two luma blocks,
+// 8..9 U, 10..11 V, 12 the Y2 block).
+__device__ __forceinline__ void fetch_dense(HalfWs& ws, const Vp8ImgDesc* sd, size_t mb, int hl) {
+	if (hl >= 13) return;
+	const int16_t* src;
+	if (hl < 8) src = sd->coeff_y + (mb * 16 + 2 * hl) * 16;
+	else if (hl < 10) src = sd->coeff_u + (mb * 4 + 2 * (hl - 8)) * 16;
+	else if (hl < 12) src = sd->coeff_v + (mb * 4 + 2 * (hl - 10)) * 16;
+	else src = sd->coeff_y2 + mb * 16;
+	cp_async16(&ws.coef[0 * 13 + hl], src);
+	cp_async16(&ws.coef[1 * 13 + hl], src + 8);
+	if (hl < 12) {
+		cp_async16(&ws.coef[2 * 13 + hl], src + 16);
+		cp_async16(&ws.coef[3 * 13 + hl], src + 24);
+	}
+}
+
 constexpr int kClusterProg = 1024; // progress stamps per image in cluster mode (VP8 frames have at most 1024 macroblock rows)
 
 #ifndef VP8P_BPRED_UNROLL
@@ -161,10 +178,9 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 
 	// ---- lane roles inside a half (hl = 0..15)
 	//   transforms / block prediction: hl < 8 luma blocks 2hl, 2hl+1 (same block row); 8,9: U; 10,11: V; 12: Y2
-	const bool tl_luma = hl < 8, tl_chroma = hl >= 8 && hl < 12;
+	const bool tl_luma = hl < 8;
 	const int tl_by = tl_luma ? (hl >> 1) * 4 : (hl & 1) * 4;   // block row offset inside the plane tile
 	const int tl_bx0 = tl_luma ? (hl & 1) * 8 : 0;              // column offset of the lane's first block (second: +4)
-	const int cstep = tl_luma ? 256 : (tl_chroma ? 64 : 16);    // int16 per macroblock in this lane's coefficient stream
 	const int bit0 = tl_luma ? 2 * hl : (hl < 10 ? 16 + 2 * (hl - 8) : (hl < 12 ? 20 + 2 * (hl - 10) : 24)); // compact layout: mask bit of the lane's first block
 	//   B_PRED: lane = pixel of the current sub-block
 	const int px_r = hl >> 2, px_c = hl & 3;
@@ -206,22 +222,24 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 #include "vp8_pairs_image.inc"
 
 		for (int p = c_rank * NW + warp; 2 * p < rows; p += NW * c_size) {
-			int y, x_pref;
+			int y;
 			bool row_ok, last_row;
 			size_t mb_row0;
-			const int16_t* cptr;
 			uint32_t staged_nz;
 #include "vp8_pairs_row.inc"
 
 			for (int t = 0; t < cols + 2; t++) {
-#include "vp8_pairs_step.inc"
+#define VP8P_STEP_ACTIVE true
+#include "vp8_pairs_step_a.inc"
+#include "vp8_pairs_step_b.inc"
+#undef VP8P_STEP_ACTIVE
 			}
 		}
 	}
 }
 
 // ------------------------------------------------------------------------------------------------ lockstep flavour
-// Same warps, same step (vp8_pairs_step.inc), different schedule. The step is ~2500 instructions of mostly straight-line
+// Same warps, same step (vp8_pairs_step_a/_b.inc), different schedule. The step is ~2500 instructions of mostly straight-line
 // code, far beyond the 32 KB instruction cache of an SM: 28 independent warps stream it from L2 at 28 different places
 // and the SM issues ~0.55 instructions per cycle per scheduler whatever the occupancy (tools/icache_probe.cu reproduces
 // this with plain integer code: 0.56 skewed, 0.83 when the warps of ONE CTA meet at a barrier once per pass). So here
@@ -233,9 +251,16 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 // loop ends when no warp has work left (__syncthreads_or). Image hand-over inside a group: warps count themselves out
 // (ctl[0]); when all NW have, the group's first warp loads the next descriptor and publishes it (ctl[1]).
 constexpr int kLockMaxGroups = 7;
+#ifndef VP8P_LOCK_EARLY_LOADS
+#define VP8P_LOCK_EARLY_LOADS 0 // 1: the lockstep kernel issues a step's loads before the barrier of that step
+#endif
+#ifndef VP8P_LOCK_PIN
+#define VP8P_LOCK_PIN 0 // how many thread constants of the lockstep kernel are pinned in registers (0..3)
+#endif
 #ifndef VP8P_LOCK_PER_SCHEDULER
 #define VP8P_LOCK_PER_SCHEDULER 0 // 1: only the warps that share a scheduler (same index in their group) meet at the barrier
 #endif
+#if VP8P_LOCK_PER_SCHEDULER
 // Barrier + OR-reduction among the `count` threads that use barrier `id`.
 __device__ __forceinline__ bool bar_red_or(int id, int count, bool pred) {
 	uint32_t r;
@@ -246,6 +271,7 @@ __device__ __forceinline__ bool bar_red_or(int id, int count, bool pred) {
 	    : "memory");
 	return r != 0;
 }
+#endif
 
 // Per-image values every warp of a group needs but only now and then: kept in shared memory, not in registers.
 struct LockImage {
@@ -274,11 +300,40 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 	uint32_t* btab = reinterpret_cast<uint32_t*>(smem);
 	const int line_c = line_px / 2;
 	const int groups = blockDim.x / (NW * 32);
-	const int lane = threadIdx.x & 31, group = (threadIdx.x >> 5) / NW, warp = (threadIdx.x >> 5) % NW;
-	const int hl = lane & 15, half = lane >> 4, hbit = lane & 16;
+	const int group = (threadIdx.x >> 5) / NW;
 	const int slot = blockIdx.x * groups + group;
 
-	uint8_t* const gs = smem + kBtabWords * 4 + (size_t)group * (kLockGroupFixed + 2 * line_px + NW * 2 * sizeof(HalfWs));
+	// Thread constants are needed all over the ~2500-instruction step. Left alone, the compiler re-derives them from
+	// threadIdx at every use (9 % of all executed instructions in the first build, every chain starting with an S2R), so
+	// PIN_COUNT values are made opaque to it and therefore stay in registers: the lane-role word and shared-memory
+	// addresses (this thread's workspace, its group's block).
+	static_assert(NW <= 4, "roles word holds a 2-bit warp index");
+	uint32_t roles, ws_s, gs_s;
+	{
+		const int lane0 = threadIdx.x & 31, warp0 = (threadIdx.x >> 5) % NW, hl0 = lane0 & 15, half0 = lane0 >> 4;
+		const bool luma0 = hl0 < 8;
+		const int by0 = luma0 ? (hl0 >> 1) * 4 : (hl0 & 1) * 4;
+		const int bx0 = luma0 ? (hl0 & 1) * 8 : 0;
+		const int bit00 = luma0 ? 2 * hl0 : (hl0 < 10 ? 16 + 2 * (hl0 - 8) : (hl0 < 12 ? 20 + 2 * (hl0 - 10) : 24));
+		const int e_dy = hl0 <= 2 ? 3 : (hl0 <= 5 ? 5 - hl0 : -1);
+		const int e_dx = hl0 <= 6 ? -1 : (hl0 == 15 ? 7 : hl0 - 7);
+		roles = hl0 | half0 << 4 | by0 << 5 | bx0 << 9 | bit00 << 13 | (e_dy * 24 + e_dx + 32) << 18 | warp0 << 26;
+		gs_s = (uint32_t)__cvta_generic_to_shared(smem) + kBtabWords * 4 +
+		       group * (kLockGroupFixed + 2 * line_px + NW * 2 * (int)sizeof(HalfWs));
+		ws_s = gs_s + kLockGroupFixed + 2 * line_px + (warp0 * 2 + half0) * (int)sizeof(HalfWs);
+	}
+#if VP8P_LOCK_PIN >= 1
+	asm volatile("" : "+r"(roles));
+#endif
+#if VP8P_LOCK_PIN >= 2
+	asm volatile("" : "+r"(ws_s));
+#endif
+#if VP8P_LOCK_PIN >= 3
+	asm volatile("" : "+r"(gs_s));
+#endif
+	const int lane = roles & 31, hl = roles & 15, half = (roles >> 4) & 1, hbit = roles & 16, warp = (roles >> 26) & 3;
+
+	uint8_t* const gs = reinterpret_cast<uint8_t*>(__cvta_shared_to_generic(gs_s));
 	volatile int* prog = reinterpret_cast<volatile int*>(gs);
 	Vp8ImgDesc* sd = reinterpret_cast<Vp8ImgDesc*>(gs + 256);
 	volatile int* ctl = reinterpret_cast<volatile int*>(gs + 512); // [0] warps that finished an image (running total), [1] images loaded
@@ -286,7 +341,7 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 	uint8_t* tu_y = gs + kLockGroupFixed; // unfiltered bottom rows of the row above
 	uint8_t* tu_u = tu_y + line_px;
 	uint8_t* tu_v = tu_u + line_px / 2;
-	HalfWs& ws = reinterpret_cast<HalfWs*>(gs + kLockGroupFixed + 2 * line_px)[warp * 2 + half];
+	HalfWs& ws = *reinterpret_cast<HalfWs*>(__cvta_shared_to_generic(ws_s));
 	// per-slot scratch in global memory (L2), same layout as the classic kernel: [tf: 8 x line][unused 2 x line][unused stamps]
 	uint8_t* const sc = tf_scratch + (size_t)slot * ((size_t)10 * line_px + kClusterProg * 4);
 	uint8_t* tf_y = sc;
@@ -310,16 +365,13 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 	if (warp == 0 && lane < 2) ctl[lane] = 0;
 	__syncthreads();
 
-	// lane roles inside a half, as in vp8_mb_pairs
-	const bool tl_luma = hl < 8, tl_chroma = hl >= 8 && hl < 12;
-	const int tl_by = tl_luma ? (hl >> 1) * 4 : (hl & 1) * 4;
-	const int tl_bx0 = tl_luma ? (hl & 1) * 8 : 0;
-	const int cstep = tl_luma ? 256 : (tl_chroma ? 64 : 16);
-	const int bit0 = tl_luma ? 2 * hl : (hl < 10 ? 16 + 2 * (hl - 8) : (hl < 12 ? 20 + 2 * (hl - 10) : 24));
+	// lane roles inside a half, as in vp8_mb_pairs, unpacked from the role word where that is cheaper than from hl
+	const bool tl_luma = hl < 8;
+	const int tl_by = (roles >> 5) & 15;
+	const int tl_bx0 = (roles >> 9) & 15;
+	const int bit0 = (roles >> 13) & 31;
 	const int px_r = hl >> 2, px_c = hl & 3;
-	const int e_dy = hl <= 2 ? 3 : (hl <= 5 ? 5 - hl : -1);
-	const int e_dx = hl <= 6 ? -1 : (hl == 15 ? 7 : hl - 7);
-	uint8_t* const bp_edge = ws.rt_y + e_dy * 24 + e_dx;
+	uint8_t* const bp_edge = ws.rt_y + (int)((roles >> 18) & 255) - 32;
 	uint8_t* const bp_out = ws.rt_y + px_r * 24 + px_c;
 	const int16_t* const bp_res = &ws.res[0][0] + hl;
 	const uint8_t* const bp_tab = reinterpret_cast<const uint8_t*>(btab + half * 176 + hl);
@@ -335,13 +387,76 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 #define g_ymode (sd->ymode)
 #define g_seg (sd->segment_id)
 #define g_hc (sd->has_coeff)
-	int y = 0, x_pref = 0;
+	int y = 0;
 	bool row_ok = false, last_row = false;
 	size_t mb_row0 = 0;
-	const int16_t* cptr = nullptr;
 	uint32_t staged_nz = 0;
 
 	for (;;) {
+		// ---- what does this warp do in this round? (nothing here blocks, see above)
+		bool active = false;
+		do {
+			if (state == ST_DONE) break;
+			if (state == ST_IMAGE) {
+				const long long img = slot + (long long)taken * (gridDim.x * groups);
+				if (img >= n_images) {
+					state = ST_DONE;
+					break;
+				}
+				if (ctl[1] <= taken) {
+					// not loaded yet: the group's first warp does it once everybody has left the previous image
+					if (warp == 0 && ctl[0] == NW * taken) {
+						const uint32_t* src = reinterpret_cast<const uint32_t*>(descs + img);
+						uint32_t* dst = reinterpret_cast<uint32_t*>(sd);
+						for (int i = lane; i < (int)(sizeof(Vp8ImgDesc) / 4); i += 32) dst[i] = src[i];
+						for (int i = lane; i < kProgRing; i += 32) prog[i] = 0;
+						__syncwarp();
+						if (lane == 0) {
+							lock_image_init(gi, sd);
+							__threadfence_block();
+							ctl[1] = taken + 1;
+						}
+					}
+					break;
+				}
+				__threadfence_block();
+				cols = sd->mb_cols;
+				rows = sd->mb_rows;
+				p = warp;
+				state = ST_ROW;
+			}
+			if (state == ST_ROW) {
+				if (2 * p >= rows) { // this warp has no row pair left in the image
+					__syncwarp();
+					if (lane == 0) {
+						__threadfence_block();
+						atomicAdd(const_cast<int*>(ctl), 1);
+					}
+					taken++;
+					state = ST_IMAGE;
+					break;
+				}
+#include "vp8_pairs_row.inc"
+				t = 0;
+				state = ST_STEP;
+			}
+			// row y (half 0) needs MB(x+1, y-1) of the row above, which another warp of the group produces
+			if (p > 0 && t < cols) {
+				const int target = 2 * p * kStampRow + min(t + 2, cols);
+				const bool there = prog[(2 * p - 1) & prog_mask] >= target;
+				if (!__all_sync(FULL, there)) break;
+				__threadfence_block();
+			}
+			active = true;
+		} while (0);
+
+		// ---- the step, with all warps of the CTA on the same instruction-cache lines.
+		//      VP8P_LOCK_EARLY_LOADS=1 issues the step's loads before the barrier instead (measured: slower, 15.5 vs 15.0 ms)
+#define VP8P_STEP_NO_SPIN
+#define VP8P_STEP_ACTIVE active
+#if VP8P_LOCK_EARLY_LOADS
+#include "vp8_pairs_step_a.inc"
+#endif
 #if VP8P_LOCK_PER_SCHEDULER
 		// warps with the same index in their group sit on the same scheduler (warp id mod 4): they share its instruction
 		// buffer, the four sets are free to drift apart
@@ -349,66 +464,18 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 #else
 		if (!__syncthreads_or(state != ST_DONE)) break;
 #endif
-		if (state == ST_DONE) continue;
-		if (state == ST_IMAGE) {
-			const long long img = slot + (long long)taken * (gridDim.x * groups);
-			if (img >= n_images) {
-				state = ST_DONE;
-				continue;
+		if (active) {
+#if !VP8P_LOCK_EARLY_LOADS
+#include "vp8_pairs_step_a.inc"
+#endif
+#include "vp8_pairs_step_b.inc"
+			if (++t == cols + 2) {
+				p += NW;
+				state = ST_ROW;
 			}
-			if (ctl[1] <= taken) {
-				// not loaded yet: the group's first warp does it once everybody has left the previous image
-				if (warp == 0 && ctl[0] == NW * taken) {
-					const uint32_t* src = reinterpret_cast<const uint32_t*>(descs + img);
-					uint32_t* dst = reinterpret_cast<uint32_t*>(sd);
-					for (int i = lane; i < (int)(sizeof(Vp8ImgDesc) / 4); i += 32) dst[i] = src[i];
-					for (int i = lane; i < kProgRing; i += 32) prog[i] = 0;
-					__syncwarp();
-					if (lane == 0) {
-						lock_image_init(gi, sd);
-						__threadfence_block();
-						ctl[1] = taken + 1;
-					}
-				}
-				continue;
-			}
-			__threadfence_block();
-			cols = sd->mb_cols;
-			rows = sd->mb_rows;
-			p = warp;
-			state = ST_ROW;
 		}
-		if (state == ST_ROW) {
-			if (2 * p >= rows) { // this warp has no row pair left in the image
-				__syncwarp();
-				if (lane == 0) {
-					__threadfence_block();
-					atomicAdd(const_cast<int*>(ctl), 1);
-				}
-				taken++;
-				state = ST_IMAGE;
-				continue;
-			}
-#include "vp8_pairs_row.inc"
-			t = 0;
-			state = ST_STEP;
-		}
-		// row y (half 0) needs MB(x+1, y-1) of the row above, which another warp of the group produces
-		if (p > 0 && t < cols) {
-			const int target = 2 * p * kStampRow + min(t + 2, cols);
-			const bool there = prog[(2 * p - 1) & prog_mask] >= target;
-			if (!__all_sync(FULL, there)) continue;
-			__threadfence_block();
-		}
-#define VP8P_STEP_NO_SPIN
-		{
-#include "vp8_pairs_step.inc"
-		}
+#undef VP8P_STEP_ACTIVE
 #undef VP8P_STEP_NO_SPIN
-		if (++t == cols + 2) {
-			p += NW;
-			state = ST_ROW;
-		}
 	}
 #undef words_ok
 #undef lf_simple
