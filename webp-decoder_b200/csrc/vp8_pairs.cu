@@ -251,6 +251,9 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 // loop ends when no warp has work left (__syncthreads_or). Image hand-over inside a group: warps count themselves out
 // (ctl[0]); when all NW have, the group's first warp loads the next descriptor and publishes it (ctl[1]).
 constexpr int kLockMaxGroups = 7;
+#ifndef VP8P_LOCK_BARRIER_EVERY
+#define VP8P_LOCK_BARRIER_EVERY 2 // the lockstep kernel's warps meet every N-th step (measured: 1 -> 14.37 ms, 2 -> 14.11, 4 -> 14.32)
+#endif
 #ifndef VP8P_LOCK_EARLY_LOADS
 #define VP8P_LOCK_EARLY_LOADS 0 // 1: the lockstep kernel issues a step's loads before the barrier of that step
 #endif
@@ -377,6 +380,9 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 	const uint8_t* const bp_tab = reinterpret_cast<const uint8_t*>(btab + half * 176 + hl);
 	const bool dc_tap = (hl >= 2 && hl <= 5) || (hl >= 7 && hl <= 10);
 
+#if VP8P_LOCK_BARRIER_EVERY > 1
+	int round_no = 0;
+#endif
 	enum { ST_IMAGE, ST_ROW, ST_STEP, ST_DONE };
 	int state = ST_IMAGE, taken = 0; // taken: images this warp has finished
 	int p = 0, t = 0;
@@ -461,6 +467,8 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 		// warps with the same index in their group sit on the same scheduler (warp id mod 4): they share its instruction
 		// buffer, the four sets are free to drift apart
 		if (!bar_red_or(1 + warp, groups * 32, state != ST_DONE)) break;
+#elif VP8P_LOCK_BARRIER_EVERY > 1
+		if ((++round_no % VP8P_LOCK_BARRIER_EVERY) == 0 && !__syncthreads_or(state != ST_DONE)) break;
 #else
 		if (!__syncthreads_or(state != ST_DONE)) break;
 #endif
