@@ -55,9 +55,10 @@ def test_reference_fuzz_digests(gpu_ctx):
 DEFAULT_KERNEL = 3  # what a fresh context runs (vp8_gpu.h: vp8_gpu_set_kernel)
 
 
-@pytest.mark.parametrize("kernel,warps", [(1, 4), (1, 8), (1, 16), (1, 32), (2, 4), (2, 8), (2, 16), (3, 4), (3, 16)])
+@pytest.mark.parametrize("kernel,warps", [(1, 4), (1, 8), (1, 16), (1, 32), (2, 4), (2, 8), (2, 16), (3, 4), (3, 8), (3, 16)])
 def test_fuzz_vs_oracle_all_kernels_and_warp_shapes(gpu_ctx, oracle, kernel, warps):
-    """Both wavefront kernels (warp per macroblock / half-warp per macroblock) in every CTA shape."""
+    """Every wavefront kernel (warp per macroblock / half-warp per macroblock / the same with the lockstep flavour of its
+    8-warp CTAs) in every CTA shape."""
     gpu_ctx.set_kernel(kernel)
     gpu_ctx.set_tuning(warps, 0)
     try:

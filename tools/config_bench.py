@@ -29,15 +29,17 @@ def timed(kfs, frs, filtered=True, reps=20):
 
 for label, name in (("config1_512x512_noise", "noise_512x512_q75.webp"), ("config3_4k_checker", "checker_3840x2160_q75.webp"),
                     ("config3_4k_rgbgrad", "rgbgrad_3840x2160_q75.webp")):
-    for kern in (2, 1):
+    for kern in (3, 2, 1):
         ctx.set_kernel(kern)
+        ctx.set_cluster(1)  # one CTA: the cluster numbers are in the last section
         i = idx[name]
         ms, b, buf, offs, sizes = timed([pf.kfs[i]], [pf.frames[i]])
         ok = hashlib.sha256(buf[int(offs[0]):int(offs[0]) + int(sizes[0])]).hexdigest() == dg[name]["yuvf"]
         w, h = dg[name]["width"], dg[name]["height"]
         out[f"{label}_kernel{kern}"] = {"latency_us": ms * 1e3, "mpixel_per_s": w * h / ms / 1e3, "launch": ctx.last_launch_config(), "bit_exact": ok}
         b.free()
-ctx.set_kernel(2)
+ctx.set_kernel(3)
+ctx.set_cluster(0)
 # config 4: 1080p batch through -ppm (fused recon+filter, then the RGB kernel)
 sel = [idx[n] for n in names if "1920x1080" in n]
 order = [sel[k % len(sel)] for k in range(1024)]
@@ -70,9 +72,9 @@ print(json.dumps(out, indent=1))
 
 # config 3 again with the image spread over a thread-block cluster (pair kernel, 16 warps per CTA)
 ctx3 = W.Context(0)
-ctx3.set_kernel(2)
 lat = {}
-for name in ("checker_3840x2160_q75.webp", "rgbgrad_3840x2160_q75.webp"):
+for kern, name in ((3, "checker_3840x2160_q75.webp"), (3, "rgbgrad_3840x2160_q75.webp"), (2, "checker_3840x2160_q75.webp")):
+    ctx3.set_kernel(kern)
     for cl in (1, 2, 4, 8):
         ctx3.set_cluster(cl)
         i = idx[name]
@@ -85,6 +87,6 @@ for name in ("checker_3840x2160_q75.webp", "rgbgrad_3840x2160_q75.webp"):
         ms, n = ctx3.kernel_time()
         buf, offs, sizes = ctx3.download_i420(b)
         ok = hashlib.sha256(buf[int(offs[0]):int(offs[0]) + int(sizes[0])]).hexdigest() == dg[name]["yuvf"]
-        lat[f"{name} cluster<= {cl}"] = {"latency_us": ms / n * 1e3, "launch": ctx3.last_launch_config(), "bit_exact": ok}
+        lat[f"kernel {kern} {name} cluster<= {cl}"] = {"latency_us": ms / n * 1e3, "launch": ctx3.last_launch_config(), "bit_exact": ok}
         b.free()
 print(json.dumps({"config3_cluster": lat}, indent=1))

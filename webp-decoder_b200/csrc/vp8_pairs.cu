@@ -129,7 +129,10 @@ constexpr int kClusterProg = 1024; // progress stamps per image in cluster mode 
 //             spin on each other): row pairs are dealt round-robin to the warps of all CTAs of the cluster; the unfiltered
 //             line buffer and the progress stamps live next to the filtered line in the L2-resident scratch and are
 //             published / acquired with gpu-scope fences. This is what lets ONE big frame use several SMs.
-template <int NW, bool RECON, bool FILTER, bool CL>
+// LS = true : same work split, but the warps of the CTA walk the step in lockstep: one CTA-wide barrier per round, and
+//             a warp whose row above is not far enough yet sits the round out instead of spinning (see vp8_mb_lockstep
+//             below for why: warps that stay together share instruction-cache lines).
+template <int NW, bool RECON, bool FILTER, bool CL, bool LS>
 __global__ void __launch_bounds__(NW * 32, CL ? 1 : VP8_PAIR_MIN_CTAS(NW))
 vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, uint8_t* __restrict__ tf_scratch) {
 	extern __shared__ __align__(16) uint8_t smem[];
@@ -221,18 +224,59 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 		const uint8_t *g_ymode, *g_seg, *g_hc;
 #include "vp8_pairs_image.inc"
 
-		for (int p = c_rank * NW + warp; 2 * p < rows; p += NW * c_size) {
-			int y;
-			bool row_ok, last_row;
-			size_t mb_row0;
-			uint32_t staged_nz;
+		if constexpr (!LS) {
+			for (int p = c_rank * NW + warp; 2 * p < rows; p += NW * c_size) {
+				int y;
+				bool row_ok, last_row;
+				size_t mb_row0;
+				uint32_t staged_nz;
 #include "vp8_pairs_row.inc"
 
-			for (int t = 0; t < cols + 2; t++) {
+				for (int t = 0; t < cols + 2; t++) {
 #define VP8P_STEP_ACTIVE true
 #include "vp8_pairs_step_a.inc"
 #include "vp8_pairs_step_b.inc"
 #undef VP8P_STEP_ACTIVE
+				}
+			}
+		} else {
+			// rounds: every warp does at most one step per round, nothing in here blocks, all warps leave together
+			int p = c_rank * NW + warp, t = -1; // t < 0: the row pair has not been started
+			int y = 0;
+			bool row_ok = false, last_row = false;
+			size_t mb_row0 = 0;
+			uint32_t staged_nz = 0;
+			for (;;) {
+				const bool more = 2 * p < rows;
+				bool active = false;
+				if (more) {
+					if (t < 0) {
+#include "vp8_pairs_row.inc"
+						t = 0;
+					}
+					active = true;
+					if (p > 0 && t < cols) { // row y (half 0) needs MB(x+1, y-1) of the row above, which another warp produces
+						const int target = 2 * p * kStampRow + min(t + 2, cols);
+						active = __all_sync(FULL, prog[(2 * p - 1) & prog_mask] >= target);
+						if (active) {
+							if (CL) __threadfence();
+							else __threadfence_block();
+						}
+					}
+				}
+				if (!__syncthreads_or(more)) break;
+				if (active) {
+#define VP8P_STEP_NO_SPIN
+#define VP8P_STEP_ACTIVE true
+#include "vp8_pairs_step_a.inc"
+#include "vp8_pairs_step_b.inc"
+#undef VP8P_STEP_ACTIVE
+#undef VP8P_STEP_NO_SPIN
+					if (++t == cols + 2) {
+						p += NW * c_size;
+						t = -1;
+					}
+				}
 			}
 		}
 	}
@@ -501,17 +545,17 @@ int launch_lockstep_t(const Vp8ImgDesc* descs, int n, int line_px, int grid, int
 	return (int)cudaGetLastError();
 }
 
-template <int NW, bool RECON, bool FILTER>
+template <int NW, bool RECON, bool FILTER, bool LS>
 int launch_pairs_t(const Vp8ImgDesc* descs, int n, int line_px, int grid, size_t smem, uint8_t* scratch, int cluster, cudaStream_t st) {
 	if (cluster <= 1) {
-		auto k = vp8_mb_pairs<NW, RECON, FILTER, false>;
+		auto k = vp8_mb_pairs<NW, RECON, FILTER, false, LS>;
 		cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return (int)e;
 		k<<<grid, NW * 32, smem, st>>>(descs, n, line_px, scratch);
 		return (int)cudaGetLastError();
 	}
 	if (NW != 16) return (int)cudaErrorInvalidValue; // the cluster flavour is only built for 16 warps per CTA
-	auto k = vp8_mb_pairs<16, RECON, FILTER, true>;
+	auto k = vp8_mb_pairs<16, RECON, FILTER, true, false>;
 	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return (int)e;
 	cudaLaunchConfig_t cfg{};
@@ -531,9 +575,9 @@ int launch_pairs_t(const Vp8ImgDesc* descs, int n, int line_px, int grid, size_t
 	return (int)cudaGetLastError();
 }
 
-template <int NW, bool RECON, bool FILTER>
+template <int NW, bool RECON, bool FILTER, bool LS>
 int occupancy_pairs_t(size_t smem) {
-	auto k = vp8_mb_pairs<NW, RECON, FILTER, false>;
+	auto k = vp8_mb_pairs<NW, RECON, FILTER, false, LS>;
 	if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
 	int nb = 0;
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, NW * 32, smem) != cudaSuccess) return 0;
@@ -549,30 +593,38 @@ int vp8_pairs_smem_bytes(int warps_per_image, int max_mb_cols) {
 // one scratch slot per CTA (or per cluster): filtered line (8 B/column), unfiltered line (2 B/column, cluster mode), stamps
 size_t vp8_pairs_scratch_bytes(int slots, int max_mb_cols) { return (size_t)slots * ((size_t)10 * 16 * max_mb_cols + kClusterProg * 4); }
 
-#define VP8_PAIRS_DISPATCH(FN, ...)                                \
-	switch (mode * 100 + warps_per_image) {                        \
-		case 4: return FN<4, true, false>(__VA_ARGS__);             \
-		case 8: return FN<8, true, false>(__VA_ARGS__);             \
-		case 16: return FN<16, true, false>(__VA_ARGS__);           \
-		case 104: return FN<4, true, true>(__VA_ARGS__);            \
-		case 108: return FN<8, true, true>(__VA_ARGS__);            \
-		case 116: return FN<16, true, true>(__VA_ARGS__);           \
-		case 204: return FN<4, false, true>(__VA_ARGS__);           \
-		case 208: return FN<8, false, true>(__VA_ARGS__);           \
-		case 216: return FN<16, false, true>(__VA_ARGS__);          \
-		default: return -1;                                         \
+// lockstep flavour (LS) only where it pays: 8 warps per image, three such CTAs per SM (+5-6 %). 4 warps per image run
+// vp8_mb_lockstep instead; with 16 warps per image (one image per SM or per cluster) the frame's dependency chain is the
+// limit, not the issue rate, and the barrier only lengthens it (one 4K frame: 10.2 -> 11.0 ms, cluster of 4: 5.1 -> 6.0 ms)
+#define VP8_PAIRS_DISPATCH(FN, ...)                                                       \
+	switch ((lockstep ? 1000 : 0) + mode * 100 + warps_per_image) {                       \
+		case 4: return FN<4, true, false, false>(__VA_ARGS__);                             \
+		case 8: return FN<8, true, false, false>(__VA_ARGS__);                             \
+		case 16: return FN<16, true, false, false>(__VA_ARGS__);                           \
+		case 104: return FN<4, true, true, false>(__VA_ARGS__);                            \
+		case 108: return FN<8, true, true, false>(__VA_ARGS__);                            \
+		case 116: return FN<16, true, true, false>(__VA_ARGS__);                           \
+		case 204: return FN<4, false, true, false>(__VA_ARGS__);                           \
+		case 208: return FN<8, false, true, false>(__VA_ARGS__);                           \
+		case 216: return FN<16, false, true, false>(__VA_ARGS__);                          \
+		case 1008: return FN<8, true, false, true>(__VA_ARGS__);                           \
+		case 1108: return FN<8, true, true, true>(__VA_ARGS__);                            \
+		case 1208: return FN<8, false, true, true>(__VA_ARGS__);                           \
+		default: return -1;                                                                \
 	}
 
 int vp8_launch_pairs(int mode, int warps_per_image, const Vp8ImgDesc* descs_dev, int n_images, int max_mb_cols, int grid_ctas,
-                     uint8_t* scratch, int cluster, void* stream) {
+                     uint8_t* scratch, int cluster, int lockstep, void* stream) {
 	const size_t smem = (size_t)vp8_pairs_smem_bytes(warps_per_image, max_mb_cols);
 	const int line_px = 16 * max_mb_cols;
 	cudaStream_t st = (cudaStream_t)stream;
+	if (warps_per_image != 8) lockstep = 0;
 	VP8_PAIRS_DISPATCH(launch_pairs_t, descs_dev, n_images, line_px, grid_ctas, smem, scratch, cluster, st)
 }
 
 int vp8_pairs_max_ctas_per_sm(int mode, int warps_per_image, int max_mb_cols) {
 	const size_t smem = (size_t)vp8_pairs_smem_bytes(warps_per_image, max_mb_cols);
+	const int lockstep = 0;
 	VP8_PAIRS_DISPATCH(occupancy_pairs_t, smem)
 }
 
