@@ -128,3 +128,20 @@ def test_parser_rejects_what_the_reference_rejects(lib):
             P.parse_batch([data], threads=1)
         assert e.value.errno == errno.EINVAL, what
     assert P.webp_size(good) == (16, 16)
+
+
+def test_packed_two_position_loop_filter_arithmetic(tmp_path):
+    """webp-decoder_b200/csrc/vp8_lf2.cuh (the VP8P_LF_SWAR=1 build of the pair kernels) restates the normal loop filter
+    with packed-halfword instructions and biased shifts; its host flavour emulates each instruction per half, and
+    tests/native/lf2_check.cpp compares it with a scalar restatement of vp8_loopfilter.c:24-121 over 1.6 million
+    tap / threshold combinations (two positions per word, different limits in the two halves)."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "lf2_check"
+    src = Path(__file__).resolve().parent / "native" / "lf2_check.cpp"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("ok "), out.stdout + out.stderr

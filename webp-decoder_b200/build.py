@@ -9,7 +9,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 LIB = HERE / "libvp8gpu.so"
 SOURCES = [HERE / "csrc" / "vp8_kernels.cu", HERE / "csrc" / "vp8_pairs.cu", HERE / "csrc" / "vp8_gpu.cu", HERE / "csrc" / "vp8_parse.cpp"]
-HEADERS = [HERE / "csrc" / "vp8_dev.h", HERE / "csrc" / "vp8_common.cuh", HERE / "csrc" / "vp8_tables.h",
+HEADERS = [HERE / "csrc" / "vp8_dev.h", HERE / "csrc" / "vp8_common.cuh", HERE / "csrc" / "vp8_lf2.cuh", HERE / "csrc" / "vp8_tables.h",
            HERE / "csrc" / "vp8_pairs_image.inc", HERE / "csrc" / "vp8_pairs_row.inc", HERE / "csrc" / "vp8_pairs_step_a.inc", HERE / "csrc" / "vp8_pairs_step_b.inc", HERE.parent / "include" / "vp8_gpu.h", HERE.parent / "include" / "vp8_abi.h",
            HERE.parent / "include" / "vp8_parse.h"]
 

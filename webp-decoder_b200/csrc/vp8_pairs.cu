@@ -16,6 +16,14 @@
 //     of shared memory: shared memory per image drops from 10 to 2 bytes per pixel column, which is what lets 7-8
 //     images stay resident per SM although every warp now carries two macroblock workspaces.
 #include "vp8_common.cuh"
+#include "vp8_lf2.cuh"
+
+#ifndef VP8P_LF_SWAR
+#define VP8P_LF_SWAR 0 // 1: normal loop filter with two positions per lane (vp8_lf2.cuh), 0: one position per lane.
+                        // Bit-exact either way; measured equal in the lockstep kernel (14.0 ms: 6 % MORE executed instructions,
+                        // fewer shared-memory round trips) and slower in vp8_mb_pairs (17.7 -> 19.1 ms), see DESIGN.md 4.1c
+#endif
+constexpr int kFtC = VP8P_LF_SWAR ? 20 : 12; // row stride of the chroma filter tiles (20 = the luma tile's: one set of offsets)
 
 namespace {
 
@@ -30,8 +38,8 @@ struct __align__(16) HalfWs {
 	uint8_t lcol[32];
 	int16_t res[16][16];
 	uint8_t ft_y[20 * 20];
-	uint8_t ft_u[12 * 12];
-	uint8_t ft_v[12 * 12];
+	uint8_t ft_u[12 * kFtC]; // 12 rows of 12 pixels; the row stride equals the luma tile's, so that one set of compile-time
+	uint8_t ft_v[12 * kFtC]; // offsets serves every lane of the two-positions-per-lane loop filter
 	uint4 coef[52];
 };
 static_assert(sizeof(HalfWs) % 16 == 0 && offsetof(HalfWs, res) % 16 == 0 && offsetof(HalfWs, coef) % 16 == 0, "HalfWs alignment");
