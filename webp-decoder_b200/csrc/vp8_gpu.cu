@@ -1267,7 +1267,26 @@ __attribute__((target("avx2"))) inline uint32_t pack_mb_avx2(const int16_t* cons
 	*bytes = pos;
 	return m;
 }
+// Same, with non-temporal stores: the arena is written once and read only by the copy engine, so the lines need not be
+// fetched into the cache first (a third less host memory traffic for the packed part). out must be 32-byte aligned.
+__attribute__((target("avx2"))) inline uint32_t pack_mb_avx2_nt(const int16_t* const src[4], uint8_t* out, size_t* bytes) {
+	static const int nblk[4] = {16, 4, 4, 1}, bit[4] = {0, 16, 20, 24};
+	uint32_t m = 0;
+	size_t pos = 0;
+	for (int g = 0; g < 4; g++)
+		for (int b = 0; b < nblk[g]; b++) {
+			const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src[g] + 16 * b));
+			if (!_mm256_testz_si256(v, v)) {
+				_mm256_stream_si256(reinterpret_cast<__m256i*>(out + pos), v);
+				pos += 32;
+				m |= 1u << (bit[g] + b);
+			}
+		}
+	*bytes = pos;
+	return m;
+}
 const bool g_have_avx2 = (__builtin_cpu_init(), __builtin_cpu_supports("avx2") != 0);
+const bool g_nt_stores = !(getenv("VP8_GPU_NT_STORES") && atoi(getenv("VP8_GPU_NT_STORES")) == 0);
 #else
 const bool g_have_avx2 = false;
 #endif
@@ -1301,7 +1320,9 @@ size_t compact_frame(const Vp8DecodedFrame* f, uint8_t* arena, std::atomic<size_
 		const int16_t* const src[4] = {f->coeff_y + i * 256, f->coeff_u + i * 64, f->coeff_v + i * 64, f->coeff_y2 + i * 16};
 		size_t bytes = 0;
 #if defined(__x86_64__)
-		mask[i] = g_have_avx2 ? pack_mb_avx2(src, arena + pos, &bytes) : pack_mb_portable(src, arena + pos, &bytes);
+		mask[i] = !g_have_avx2 ? pack_mb_portable(src, arena + pos, &bytes)
+		          : g_nt_stores ? pack_mb_avx2_nt(src, arena + pos, &bytes)
+		                        : pack_mb_avx2(src, arena + pos, &bytes);
 #else
 		mask[i] = pack_mb_portable(src, arena + pos, &bytes);
 #endif
@@ -1317,6 +1338,9 @@ size_t compact_frame(const Vp8DecodedFrame* f, uint8_t* arena, std::atomic<size_
 	if (f->segmentation_enabled && f->segment_id) memcpy(dst + L.o_seg, f->segment_id, mb);
 	if (f->has_coeff) memcpy(dst + L.o_hc, f->has_coeff, mb);
 	memcpy(dst + L.o_bmode, f->bmode, 16 * mb);
+#if defined(__x86_64__)
+	_mm_sfence(); // the non-temporal stores are globally visible before the copy engine is told to read the arena
+#endif
 	return head;
 }
 
