@@ -104,6 +104,29 @@ def files_for(args):
     return [str(ROOT / "bench_data" / f) for f in FRAMES_1080P]
 
 
+# The contract is ONE JSON line on stdout. Libraries print there too (NCCL announces its version on the first collective
+# when NCCL_DEBUG says so), so the process's stdout is pointed at stderr for the whole run and the line goes out through a
+# saved descriptor.
+_JSON_FD = None
+
+
+def claim_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -128,7 +151,7 @@ def reference_arm(args):
         "e2e": {"value": r["value"], "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -307,7 +330,7 @@ def gpu_arm(args):
             "gpu_launches": launches,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     pf.free()
     ctx.close()
     if world > 1:
@@ -332,9 +355,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not (args.impl == "b200" and args.gpus > 1 and world == 1):  # (the relaunching parent just passes its children's output on)
+        claim_stdout()
     if args.impl == "reference":
         return reference_arm(args)
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: relaunch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
