@@ -192,6 +192,9 @@ def gpu_arm(args):
     ctx.set_kernel(kernel_version)
     if args.warps or args.images_per_sm:
         ctx.set_tuning(args.warps, args.images_per_sm)
+    if world > 1 and not os.environ.get("VP8_GPU_HOST_THREADS"):
+        # the ranks of one node share its cores: each takes its share for the host side of the end-to-end call
+        ctx.set_transport(True, max(1, (os.cpu_count() or 1) // world))
 
     # ---- inputs: parse the distinct frames once (host threads, pinned arenas), replicate to the batch size
     files = files_for(args)
