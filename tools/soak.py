@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Randomised soak of the wavefront kernels against the CPU oracle: random batch sizes, frame sizes, content density,
+launch shapes (warps per image, images per CTA, cluster size) and kernel generations, for a given number of seconds.
+Development aid, run under gpurun:  python tools/soak.py [seconds] [seed]"""
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import webp_decoder_b200 as W  # noqa: E402
+from vp8fix import Oracle, fuzz_frame  # noqa: E402
+
+
+def main():
+    seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    orc, ctx = Oracle(), W.Context(0)
+    t0, rounds, frames_done = time.time(), 0, 0
+    while time.time() - t0 < seconds:
+        n = int(rng.choice([1, 2, 5, 13, 40, 150, 300]))
+        big = rng.random() < 0.2
+        frames = []
+        for i in range(n):
+            w = int(rng.integers(1, 700 if big and n <= 13 else 130))
+            h = int(rng.integers(1, 1300 if big and n <= 13 else 130))
+            frames.append(fuzz_frame(int(rng.integers(1 << 30)), w, h, density=float(rng.choice([0.0, 0.02, 0.3, 0.9])),
+                                     amp=int(rng.choice([5, 40, 400, 2500])), raw=bool(rng.integers(2))))
+        kernel = int(rng.choice([1, 2, 3, 3, 3]))
+        warps = int(rng.choice([0, 0, 4, 8, 16] if kernel > 1 else [0, 4, 8, 16, 32]))
+        per_sm = int(rng.choice([0, 0, 1, 2, 3, 5, 7]))
+        cluster = int(rng.choice([0, 0, 1, 2, 4, 8]))
+        filtered = bool(rng.integers(2))
+        ctx.set_kernel(kernel)
+        ctx.set_tuning(warps, per_sm)
+        ctx.set_cluster(cluster)
+        outs = ctx.decode_i420([f.header() for f in frames], [f.cstruct() for f in frames], filtered=filtered)
+        cfg = ctx.last_launch_config()
+        bad = [i for i, (f, o) in enumerate(zip(frames, outs)) if not np.array_equal(o, orc.decode_i420(f, filtered))]
+        if bad:
+            print(f"MISMATCH round {rounds}: kernel {kernel} warps {warps} per_sm {per_sm} cluster {cluster} filtered {filtered} "
+                  f"launch {cfg}: frames {bad[:8]} of {n}, e.g. {frames[bad[0]].width}x{frames[bad[0]].height}")
+            return 1
+        rounds += 1
+        frames_done += n
+    print(f"soak ok: {rounds} rounds, {frames_done} frames, {time.time() - t0:.0f} s")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
