@@ -744,7 +744,7 @@ __device__ __noinline__ void rgb_group4(const Vp8RgbDesc& d, uint32_t py, uint32
 // rgb_group4, which handles every geometry.
 __global__ void __launch_bounds__(kRgbThreads, 4) vp8_i420_to_rgb(const Vp8RgbDesc* __restrict__ descs) {
 	const Vp8RgbDesc d = descs[blockIdx.y];
-	const uint32_t w = d.width, h = d.height, cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+	const uint32_t w = d.width, h = d.height, ch = (h + 1) >> 1;
 	const uint32_t groups_per_row = (w + 7) / 8;
 	const uint32_t g = blockIdx.x * kRgbThreads + threadIdx.x;
 	if (g >= groups_per_row * h) return;
