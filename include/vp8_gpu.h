@@ -54,6 +54,12 @@ typedef struct vp8_gpu_batch vp8_gpu_batch; /* n frames resident on the device *
 
 /* stream: a cudaStream_t passed as void* (e.g. torch.cuda.current_stream().cuda_stream), or NULL for a
  * private stream. All work of the context is issued on that stream. */
+/* Environment presets read by vp8_gpu_init (each has a setter below; the legacy single-frame entry points, which
+ * create their context themselves, can only be steered this way): VP8_GPU_DEVICE, VP8_GPU_KERNEL (1|2|3),
+ * VP8_GPU_WARPS, VP8_GPU_IMAGES_PER_SM, VP8_GPU_CLUSTER, VP8_GPU_COMPACT (0|1), VP8_GPU_HOST_THREADS,
+ * VP8_GPU_LOCKSTEP_SMALL (0: 8-warp CTAs spin instead of meeting at a barrier), VP8_GPU_NT_STORES (0: host compaction
+ * with ordinary stores), VP8_GPU_TRACE (1: host-time split of a pipelined call on stderr, 2: plus a per-chunk device
+ * timeline). */
 int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out);
 void vp8_gpu_destroy(vp8_gpu_ctx* ctx);
 int vp8_gpu_sync(vp8_gpu_ctx* ctx);
