@@ -37,12 +37,13 @@ def ncu_sass(rep: str, kernel: str):
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hdr_i]
     ci, si = hdr.index("Instructions Executed"), hdr.index("# Samples")
+    wi, xi = hdr.index("L1 Wavefronts Shared"), hdr.index("L1 Wavefronts Shared Excessive")
     stall_cols = {h: i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h}
     insts = []
     for r in rows[hdr_i + 1:]:
         if len(r) <= ci or not r[0].startswith("0x"):
             continue
-        insts.append({"sass": r[1].strip(), "n": int(r[ci] or 0), "smp": int(r[si] or 0),
+        insts.append({"sass": r[1].strip(), "n": int(r[ci] or 0), "smp": int(r[si] or 0), "wf": int(r[wi] or 0), "wfx": int(r[xi] or 0),
                       "stalls": {h: int(r[i] or 0) for h, i in stall_cols.items()}})
     return insts
 
@@ -109,20 +110,26 @@ def main():
     tot_s = sum(i["smp"] for i in insts)
     reg = collections.OrderedDict()
     for ins, ch in zip(insts, chains):
-        r = reg.setdefault(region(ch), {"n": 0, "smp": 0, "static": 0, "stalls": collections.Counter()})
+        r = reg.setdefault(region(ch), {"n": 0, "smp": 0, "static": 0, "wf": 0, "wfx": 0, "stalls": collections.Counter()})
+        r["wf"] += ins["wf"]
+        r["wfx"] += ins["wfx"]
         r["n"] += ins["n"]
         r["smp"] += ins["smp"]
         r["static"] += 1
         r["stalls"].update(ins["stalls"])
     print(f"{len(insts)} SASS instructions, {tot_n / 1e9:.3f} G executed (warp level), {tot_s} stall samples")
     unit = f"{'per unit':>9s}" if args.units else ""
-    print(f"{'static':>6s} {'executed':>9s} {unit} {'samples':>8s}  top stall reasons                          region")
+    tot_wf = sum(i["wf"] for i in insts)
+    tot_wfx = sum(i["wfx"] for i in insts)
+    print(f"shared-memory wavefronts {tot_wf / 1e9:.3f} G, of which bank-conflict replays {tot_wfx / 1e9:.3f} G")
+    print(f"{'static':>6s} {'executed':>9s} {unit} {'samples':>8s} {'smem wf':>8s} {'replays':>8s}  top stall reasons                          region")
     for name, r in reg.items():
         if r["n"] / max(tot_n, 1) < 0.002 and r["smp"] / max(tot_s, 1) < 0.002:
             continue
         top = ", ".join(f"{k[6:]} {v / max(r['smp'], 1) * 100:.0f}%" for k, v in r["stalls"].most_common(3))
         per = f"{r['n'] / args.units:9.1f}" if args.units else ""
-        print(f"{r['static']:6d} {r['n'] / tot_n * 100:8.1f}% {per} {r['smp'] / max(tot_s, 1) * 100:7.1f}%  {top:42s} {name}")
+        print(f"{r['static']:6d} {r['n'] / tot_n * 100:8.1f}% {per} {r['smp'] / max(tot_s, 1) * 100:7.1f}% {r['wf'] / max(tot_wf, 1) * 100:7.1f}% "
+              f"{r['wfx'] / max(r['wf'], 1) * 100:7.1f}%  {top:42s} {name}")
 
 
 if __name__ == "__main__":

@@ -18,6 +18,9 @@
 #include "vp8_common.cuh"
 #include "vp8_lf2.cuh"
 
+#ifndef VP8P_HALF_SKEW
+#define VP8P_HALF_SKEW 64
+#endif
 #ifndef VP8P_LF_SWAR
 #define VP8P_LF_SWAR 0 // 1: normal loop filter with two positions per lane (vp8_lf2.cuh), 0: one position per lane.
                         // Bit-exact either way; measured equal in the lockstep kernel (14.0 ms: 6 % MORE executed instructions,
@@ -41,6 +44,8 @@ struct __align__(16) HalfWs {
 	uint8_t ft_u[12 * kFtC]; // 12 rows of 12 pixels; the row stride equals the luma tile's, so that one set of compile-time
 	uint8_t ft_v[12 * kFtC]; // offsets serves every lane of the two-positions-per-lane loop filter
 	uint4 coef[52];
+	uint8_t skew_[VP8P_HALF_SKEW]; // the two halves of a warp touch the same offsets of their workspaces in the same instruction:
+	                               // with sizeof(HalfWs) = 64 mod 128 they do so on complementary shared-memory banks
 };
 static_assert(sizeof(HalfWs) % 16 == 0 && offsetof(HalfWs, res) % 16 == 0 && offsetof(HalfWs, coef) % 16 == 0, "HalfWs alignment");
 
