@@ -37,11 +37,24 @@ def main():
         ctx.set_kernel(kernel)
         ctx.set_tuning(warps, per_sm)
         ctx.set_cluster(cluster)
-        outs = ctx.decode_i420([f.header() for f in frames], [f.cstruct() for f in frames], filtered=filtered)
+        kfs, ds = [f.header() for f in frames], [f.cstruct() for f in frames]
+        want = [orc.decode_i420(f, filtered) for f in frames]
+        api = str(rng.choice(["batch", "batch", "pipelined", "ppm"]))
+        if api == "batch":
+            outs = ctx.decode_i420(kfs, ds, filtered=filtered)
+        elif api == "pipelined":  # chunked, compact or dense transport, several host threads
+            ctx.set_transport(bool(rng.integers(2)), int(rng.choice([1, 3, 8])))
+            buf = np.empty(ctx.decode_bytes(kfs), np.uint8)
+            offs, szs = ctx.decode_into(kfs, ds, buf, filtered=filtered, chunk=int(rng.choice([1, 3, 16, 64])))
+            outs = [buf[int(o):int(o) + int(z)] for o, z in zip(offs, szs)]
+        else:  # m08 on top of the filtered frames
+            filtered = True
+            want = [np.frombuffer(orc.ppm(orc.rgb(orc.decode_i420(f, True), f.width, f.height), f.width, f.height), np.uint8) for f in frames]
+            outs = [np.frombuffer(p, np.uint8) for p in ctx.decode_ppm(kfs, ds)]
         cfg = ctx.last_launch_config()
-        bad = [i for i, (f, o) in enumerate(zip(frames, outs)) if not np.array_equal(o, orc.decode_i420(f, filtered))]
+        bad = [i for i, (w, o) in enumerate(zip(want, outs)) if not np.array_equal(o, w)]
         if bad:
-            print(f"MISMATCH round {rounds}: kernel {kernel} warps {warps} per_sm {per_sm} cluster {cluster} filtered {filtered} "
+            print(f"MISMATCH round {rounds} ({api}): kernel {kernel} warps {warps} per_sm {per_sm} cluster {cluster} filtered {filtered} "
                   f"launch {cfg}: frames {bad[:8]} of {n}, e.g. {frames[bad[0]].width}x{frames[bad[0]].height}")
             return 1
         rounds += 1
