@@ -311,12 +311,6 @@ constexpr int kLockMaxGroups = 7;
 #ifndef VP8P_LOCK_BARRIER_EVERY
 #define VP8P_LOCK_BARRIER_EVERY 2 // the lockstep kernel's warps meet every N-th step (measured: 1 -> 14.37 ms, 2 -> 14.11, 4 -> 14.32)
 #endif
-#ifndef VP8P_LOCK_EARLY_LOADS
-#define VP8P_LOCK_EARLY_LOADS 0 // 1: the lockstep kernel issues a step's loads before the barrier of that step
-#endif
-#ifndef VP8P_LOCK_PIN
-#define VP8P_LOCK_PIN 0 // how many thread constants of the lockstep kernel are pinned in registers (0..3)
-#endif
 #ifndef VP8P_LOCK_PER_SCHEDULER
 #define VP8P_LOCK_PER_SCHEDULER 0 // 1: only the warps that share a scheduler (same index in their group) meet at the barrier
 #endif
@@ -363,10 +357,9 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 	const int group = (threadIdx.x >> 5) / NW;
 	const int slot = blockIdx.x * groups + group;
 
-	// Thread constants are needed all over the ~2500-instruction step. Left alone, the compiler re-derives them from
-	// threadIdx at every use (9 % of all executed instructions in the first build, every chain starting with an S2R), so
-	// PIN_COUNT values are made opaque to it and therefore stay in registers: the lane-role word and shared-memory
-	// addresses (this thread's workspace, its group's block).
+	// Thread constants are needed all over the ~2500-instruction step; the lane roles travel in one packed word and the two
+	// shared-memory bases as 32-bit addresses, which is the form the compiler re-derives them from most cheaply (making
+	// them opaque to it, i.e. pinning them in registers, was measured and gained nothing).
 	static_assert(NW <= 4, "roles word holds a 2-bit warp index");
 	uint32_t roles, ws_s, gs_s;
 	{
@@ -382,15 +375,6 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 		       group * (kLockGroupFixed + 2 * line_px + NW * 2 * (int)sizeof(HalfWs));
 		ws_s = gs_s + kLockGroupFixed + 2 * line_px + (warp0 * 2 + half0) * (int)sizeof(HalfWs);
 	}
-#if VP8P_LOCK_PIN >= 1
-	asm volatile("" : "+r"(roles));
-#endif
-#if VP8P_LOCK_PIN >= 2
-	asm volatile("" : "+r"(ws_s));
-#endif
-#if VP8P_LOCK_PIN >= 3
-	asm volatile("" : "+r"(gs_s));
-#endif
 	const int lane = roles & 31, hl = roles & 15, half = (roles >> 4) & 1, hbit = roles & 16, warp = (roles >> 26) & 3;
 
 	uint8_t* const gs = reinterpret_cast<uint8_t*>(__cvta_shared_to_generic(gs_s));
@@ -513,13 +497,10 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 			active = true;
 		} while (0);
 
-		// ---- the step, with all warps of the CTA on the same instruction-cache lines.
-		//      VP8P_LOCK_EARLY_LOADS=1 issues the step's loads before the barrier instead (measured: slower, 15.5 vs 15.0 ms)
+		// ---- the step, with all warps of the CTA on the same instruction-cache lines (issuing the step's loads before
+		//      the barrier instead was measured: slower, 15.5 vs 15.0 ms)
 #define VP8P_STEP_NO_SPIN
 #define VP8P_STEP_ACTIVE active
-#if VP8P_LOCK_EARLY_LOADS
-#include "vp8_pairs_step_a.inc"
-#endif
 #if VP8P_LOCK_PER_SCHEDULER
 		// warps with the same index in their group sit on the same scheduler (warp id mod 4): they share its instruction
 		// buffer, the four sets are free to drift apart
@@ -530,9 +511,7 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 		if (!__syncthreads_or(state != ST_DONE)) break;
 #endif
 		if (active) {
-#if !VP8P_LOCK_EARLY_LOADS
 #include "vp8_pairs_step_a.inc"
-#endif
 #include "vp8_pairs_step_b.inc"
 			if (++t == cols + 2) {
 				p += NW;
