@@ -75,6 +75,9 @@ int vp8_gpu_set_tuning(vp8_gpu_ctx* ctx, int warps_per_image, int images_per_sm)
  * instruction-cache lines). All are bit-exact; the environment variable VP8_GPU_KERNEL presets it. */
 int vp8_gpu_set_kernel(vp8_gpu_ctx* ctx, int version);
 int vp8_gpu_last_groups(const vp8_gpu_ctx* ctx); /* images per CTA of the last wavefront launch if it was lockstep, else 0 */
+/* A batch that is not a whole number of lockstep waves is cut into segments (full waves, then the rest in the shape that
+ * suits it), one kernel launch each; the other vp8_gpu_last_* calls describe the first segment. */
+int vp8_gpu_last_segments(const vp8_gpu_ctx* ctx);
 
 /* Small batches of big frames: the pair kernel can spread ONE image over a thread-block cluster of 2, 4 or 8 CTAs
  * (co-scheduled, exchanging line buffers and progress stamps through L2). 0 = automatic (used when the batch would

@@ -174,6 +174,17 @@ def test_lockstep_is_what_big_batches_run_by_default(gpu_ctx, oracle):
         gpu_ctx.set_tuning(0, 0)
 
 
+def test_batch_of_more_than_a_wave_is_cut_into_segments(gpu_ctx, oracle):
+    """148 SMs x 7 images is one lockstep wave; 1100 images = one full wave + 64 images that get their own launch shape."""
+    frames = [fuzz_frame(5000 + s, 32 + 16 * (s % 2), 32 + 16 * (s % 3), density=0.15) for s in range(1100)]
+    outs = gpu_ctx.decode_i420([f.header() for f in frames], [f.cstruct() for f in frames], filtered=True)
+    cfg = gpu_ctx.last_launch_config()
+    sms = cfg["grid"]  # one CTA per SM in the first segment
+    assert cfg["images_per_cta"] == 7 and (cfg["segments"] == 2 or sms * 7 >= 1100), cfg
+    bad = [i for i, (f, o) in enumerate(zip(frames, outs)) if not np.array_equal(o, oracle.decode_i420(f, True))]
+    assert not bad, bad[:8]
+
+
 @pytest.mark.parametrize("ctas", [1, 2, 4, 8])
 def test_cluster_mode_one_image_over_several_ctas(gpu_ctx, oracle, ctas):
     """Few big frames: each image is decoded by a thread-block cluster (row pairs dealt to the warps of 2/4/8 co-scheduled

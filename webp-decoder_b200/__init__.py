@@ -43,7 +43,7 @@ EXPORTS = [
     "vp8_gpu_last_launch_config", "vp8_gpu_frame_params", "vp8_gpu_kernel_time",
     "vp8_gpu_decode_i420", "vp8_gpu_decode_ppm", "vp8_gpu_decode_bytes", "vp8_gpu_set_kernel",
     "vp8_gpu_png_bound", "vp8_gpu_png_frame", "vp8_gpu_set_transport",
-    "vp8_gpu_set_cluster", "vp8_gpu_last_cluster", "vp8_gpu_last_groups",
+    "vp8_gpu_set_cluster", "vp8_gpu_last_cluster", "vp8_gpu_last_groups", "vp8_gpu_last_segments",
 ]
 
 _lib = None
@@ -75,6 +75,7 @@ def load_library() -> C.CDLL:
     L.vp8_gpu_set_cluster.argtypes = [vp, C.c_int]
     L.vp8_gpu_last_cluster.argtypes = [vp]
     L.vp8_gpu_last_groups.argtypes = [vp]
+    L.vp8_gpu_last_segments.argtypes = [vp]
     L.vp8_gpu_host_alloc.argtypes = [sz]
     L.vp8_gpu_host_alloc.restype = vp
     L.vp8_gpu_host_free.argtypes = [vp]
@@ -351,7 +352,8 @@ class Context:
         _check(self._L.vp8_gpu_last_launch_config(self._h, C.byref(w), C.byref(g), C.byref(s)), "launch config")
         return {"warps_per_image": w.value, "grid": g.value, "smem_bytes": s.value,
                 "ctas_per_image": int(self._L.vp8_gpu_last_cluster(self._h)),
-                "images_per_cta": int(self._L.vp8_gpu_last_groups(self._h))}
+                "images_per_cta": int(self._L.vp8_gpu_last_groups(self._h)),
+                "segments": int(self._L.vp8_gpu_last_segments(self._h))}
 
 
 # -------------------------------------------------------------------------------------------- reference-shaped calls

@@ -146,7 +146,7 @@ struct vp8_gpu_ctx {
 	bool bounce_busy[2] = {false, false};
 	std::vector<FreeBlock> cache; // device blocks kept for reuse
 	uint64_t launches = 0, h2d = 0, d2h = 0;
-	int last_warps = 0, last_grid = 0, last_smem = 0;
+	int last_warps = 0, last_grid = 0, last_smem = 0, last_segments = 0;
 	// device-side duration of every wavefront launch since the last vp8_gpu_kernel_time() query
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed; // recorded, not yet read
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spare;
@@ -639,53 +639,87 @@ int pick_warps(const vp8_gpu_ctx* c, int n_images) {
 	return 4;
 }
 
-int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layout) {
-	if (push_descs(c, b, kernel_mode, layout)) return -1;
+// How `n` images (frames of at most max_mb_cols x max_rows macroblocks) are put on the GPU.
+struct LaunchPlan {
+	int warps = 4, grid = 0, cluster = 1, groups = 0;
+	int slots() const { return groups ? grid * groups : cluster > 1 ? grid / cluster : grid; } // images in flight
+};
+
+int plan_launch(const vp8_gpu_ctx* c, int n, int max_mb_cols, int max_rows, int kernel_mode, LaunchPlan* out) {
 	const bool pairs = c->kernel_version >= 2;
-	int warps = pick_warps(c, b->n);
-	if (pairs) warps = std::min(warps, 16); // a pair-kernel warp already carries two macroblock rows
+	LaunchPlan p;
+	p.warps = pick_warps(c, n);
+	if (pairs) p.warps = std::min(p.warps, 16); // a pair-kernel warp already carries two macroblock rows
 	int per_sm = 0;
-	for (;; warps /= 2) {
-		per_sm = pairs ? vp8_pairs_max_ctas_per_sm(kernel_mode, warps, b->max_mb_cols)
-		               : vp8_wavefront_max_ctas_per_sm(kernel_mode, warps, b->max_mb_cols);
-		if (per_sm > 0 || warps == 4) break;
+	for (;; p.warps /= 2) {
+		per_sm = pairs ? vp8_pairs_max_ctas_per_sm(kernel_mode, p.warps, max_mb_cols) : vp8_wavefront_max_ctas_per_sm(kernel_mode, p.warps, max_mb_cols);
+		if (per_sm > 0 || p.warps == 4) break;
 	}
 	if (per_sm <= 0) return fail(EIO, "wavefront kernel does not fit on an SM (frame too wide?)", cudaGetLastError());
+	const int want_per_sm = (n + c->sm_count - 1) / c->sm_count;
 	// 8-warp CTAs fit three to an SM: a batch of four images per SM would need a second wave, while four lockstep groups
 	// of 4 warps take it in one (measured at 1080p: 500 images 11.6 -> 10.1 ms)
-	if (c->kernel_version == 3 && !c->tune_warps && warps == 8 && (b->n + c->sm_count - 1) / c->sm_count > per_sm &&
-	    vp8_lockstep_max_groups(b->max_mb_cols) >= (b->n + c->sm_count - 1) / c->sm_count) {
-		warps = 4;
-		per_sm = vp8_pairs_max_ctas_per_sm(kernel_mode, 4, b->max_mb_cols);
+	if (c->kernel_version == 3 && !c->tune_warps && p.warps == 8 && want_per_sm > per_sm && vp8_lockstep_max_groups(max_mb_cols) >= want_per_sm) {
+		p.warps = 4;
+		per_sm = vp8_pairs_max_ctas_per_sm(kernel_mode, 4, max_mb_cols);
 	}
 	if (c->tune_imgs_per_sm > 0) per_sm = std::min(per_sm, c->tune_imgs_per_sm);
-	int grid = std::min(b->n, per_sm * c->sm_count);
+	p.grid = std::min(n, per_sm * c->sm_count);
 	// Few big frames: spread each over a thread-block cluster so that one image can use several SMs. Worth it only when
 	// 16-warp CTAs are already in use, the GPU would otherwise be mostly idle and the frame has rows to hand out.
-	int cluster = 1;
-	if (pairs && warps == 16 && c->tune_cluster != 1) {
-		int max_rows = 0;
-		for (auto& m : b->meta) max_rows = std::max<int>(max_rows, m.mb_rows);
+	if (pairs && p.warps == 16 && c->tune_cluster != 1) {
 		int want = c->tune_cluster > 1 ? c->tune_cluster : 8;
-		while (want > 1 && (b->n * want > c->sm_count || 32 * (want - 1) >= max_rows)) want /= 2; // every CTA must get rows
-		cluster = want;
-		if (cluster > 1) grid = std::min(b->n, c->sm_count / cluster) * cluster;
+		while (want > 1 && (n * want > c->sm_count || 32 * (want - 1) >= max_rows)) want /= 2; // every CTA must get rows
+		p.cluster = want;
+		if (p.cluster > 1) p.grid = std::min(n, c->sm_count / p.cluster) * p.cluster;
 	}
 	// Many images: the lockstep flavour packs `groups` of them into one CTA per SM (kernel 3 only, where the classic
 	// choice would be 4 warps per image anyway).
-	int groups = 0;
-	if (c->kernel_version == 3 && warps == 4 && cluster == 1) {
-		int g = vp8_lockstep_max_groups(b->max_mb_cols);
+	if (c->kernel_version == 3 && p.warps == 4 && p.cluster == 1) {
+		int g = vp8_lockstep_max_groups(max_mb_cols);
 		if (c->tune_warps == 4 && c->tune_imgs_per_sm > 0) g = std::min(g, c->tune_imgs_per_sm); // explicit: whatever the batch size
-		else g = std::min(g, (b->n + c->sm_count - 1) / c->sm_count);
-		g = std::min(g, b->n);
+		else g = std::min(g, want_per_sm);
+		g = std::min(g, n);
 		if (g >= 2) {
-			groups = g;
-			grid = std::min(c->sm_count, (b->n + groups - 1) / groups);
+			p.groups = g;
+			p.grid = std::min(c->sm_count, (n + g - 1) / g);
 		}
 	}
+	*out = p;
+	return 0;
+}
+
+int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layout) {
+	if (push_descs(c, b, kernel_mode, layout)) return -1;
+	const bool pairs = c->kernel_version >= 2;
+	int max_rows = 0;
+	for (auto& m : b->meta) max_rows = std::max<int>(max_rows, m.mb_rows);
+	// A batch is cut into segments, one launch each. An image takes a group of warps a fixed time, so a lockstep launch is
+	// at its best with a whole number of waves (every slot busy for the same number of images); what is left over after
+	// the full waves gets the shape that suits THAT many images (1100 frames at 1080p: 1036 in lockstep + 64 on
+	// clusters, 15.9 ms instead of two waves of 13.5).
+	struct Segment {
+		int first, count;
+		LaunchPlan plan;
+	};
+	std::vector<Segment> segs;
+	const bool automatic = !c->tune_warps && !c->tune_imgs_per_sm;
+	for (int first = 0; first < b->n;) {
+		Segment sg;
+		sg.first = first;
+		sg.count = b->n - first;
+		if (plan_launch(c, sg.count, b->max_mb_cols, max_rows, kernel_mode, &sg.plan)) return -1;
+		const int slots = sg.plan.slots();
+		if (automatic && sg.plan.groups && sg.count > slots && sg.count % slots != 0) {
+			sg.count = (sg.count / slots) * slots; // full waves only; the rest is planned on its own
+			if (plan_launch(c, sg.count, b->max_mb_cols, max_rows, kernel_mode, &sg.plan)) return -1;
+		}
+		segs.push_back(sg);
+		first += sg.count;
+	}
 	if (pairs) {
-		const size_t need = vp8_pairs_scratch_bytes(groups ? grid * groups : cluster > 1 ? grid / cluster : grid, b->max_mb_cols);
+		size_t need = 0;
+		for (auto& sg : segs) need = std::max(need, vp8_pairs_scratch_bytes(sg.plan.slots(), b->max_mb_cols)); // launches run one after the other
 		if (b->scratch_bytes < need) {
 			dev_release(c, b->d_scratch, b->scratch_bytes);
 			b->d_scratch = nullptr;
@@ -703,10 +737,17 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 		CU(cudaEventCreate(&ev.second));
 	}
 	CU(cudaEventRecord(ev.first, b->stream));
-	const int rc = groups ? vp8_launch_lockstep(kernel_mode, b->d_desc, b->n, b->max_mb_cols, grid, groups, b->d_scratch, b->stream)
-	               : pairs ? vp8_launch_pairs(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, b->d_scratch, cluster,
-	                                          c->kernel_version == 3 && c->lockstep_small, b->stream)
-	                       : vp8_launch_wavefront(kernel_mode, warps, b->d_desc, b->n, b->max_mb_cols, grid, b->stream);
+	int rc = 0;
+	for (auto& sg : segs) {
+		const LaunchPlan& p = sg.plan;
+		const Vp8ImgDesc* descs = b->d_desc + sg.first;
+		rc = p.groups ? vp8_launch_lockstep(kernel_mode, descs, sg.count, b->max_mb_cols, p.grid, p.groups, b->d_scratch, b->stream)
+		     : pairs  ? vp8_launch_pairs(kernel_mode, p.warps, descs, sg.count, b->max_mb_cols, p.grid, b->d_scratch, p.cluster,
+		                                 c->kernel_version == 3 && c->lockstep_small, b->stream)
+		              : vp8_launch_wavefront(kernel_mode, p.warps, descs, sg.count, b->max_mb_cols, p.grid, b->stream);
+		if (rc != 0) break;
+		c->launches++;
+	}
 	CU(cudaEventRecord(ev.second, b->stream));
 	c->timed.push_back(ev);
 	if (c->timed.size() > 4096) { // nobody is asking: recycle the oldest
@@ -714,12 +755,15 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 		c->timed.erase(c->timed.begin());
 	}
 	if (rc != 0) return fail(EIO, "wavefront launch", (cudaError_t)rc);
-	c->launches++;
-	c->last_warps = warps;
-	c->last_grid = grid;
-	c->last_cluster = cluster;
-	c->last_groups = groups;
-	c->last_smem = groups ? vp8_lockstep_smem_bytes(groups, b->max_mb_cols) : pairs ? vp8_pairs_smem_bytes(warps, b->max_mb_cols) : vp8_wavefront_smem_bytes(kernel_mode, warps, b->max_mb_cols);
+	const LaunchPlan& p = segs.front().plan; // what is reported: the shape of the first (biggest) segment
+	c->last_warps = p.warps;
+	c->last_grid = p.grid;
+	c->last_cluster = p.cluster;
+	c->last_groups = p.groups;
+	c->last_segments = (int)segs.size();
+	c->last_smem = p.groups ? vp8_lockstep_smem_bytes(p.groups, b->max_mb_cols)
+	               : pairs  ? vp8_pairs_smem_bytes(p.warps, b->max_mb_cols)
+	                        : vp8_wavefront_smem_bytes(kernel_mode, p.warps, b->max_mb_cols);
 	return 0;
 }
 
@@ -1006,6 +1050,7 @@ int vp8_gpu_set_cluster(vp8_gpu_ctx* c, int ctas_per_image) {
 
 int vp8_gpu_last_cluster(const vp8_gpu_ctx* c) { return c ? c->last_cluster : 0; }
 int vp8_gpu_last_groups(const vp8_gpu_ctx* c) { return c ? c->last_groups : 0; }
+int vp8_gpu_last_segments(const vp8_gpu_ctx* c) { return c ? c->last_segments : 0; }
 
 int vp8_gpu_set_kernel(vp8_gpu_ctx* c, int version) {
 	if (!c || (version < 1 || version > 3)) return fail(EINVAL, "bad kernel version");
