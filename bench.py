@@ -325,7 +325,7 @@ def gpu_arm(args):
                        "launch": cfg, "parity_spot_check_vs_reference_digests": parity},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": ncu_traffic(args.workload, kernel_version), "peak_source": peak_src,
-                         "kernel": {1: "vp8_mb_wavefront", 2: "vp8_mb_pairs", 3: "vp8_mb_lockstep"}[kernel_version],
+                         "kernel": {2: "vp8_mb_pairs", 3: "vp8_mb_lockstep"}[kernel_version],
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": kern_n},
             "cpu_baseline": cpu,
             "host_front_end": host_fe,

@@ -55,7 +55,7 @@ typedef struct vp8_gpu_batch vp8_gpu_batch; /* n frames resident on the device *
 /* stream: a cudaStream_t passed as void* (e.g. torch.cuda.current_stream().cuda_stream), or NULL for a
  * private stream. All work of the context is issued on that stream. */
 /* Environment presets read by vp8_gpu_init (each has a setter below; the legacy single-frame entry points, which
- * create their context themselves, can only be steered this way): VP8_GPU_DEVICE, VP8_GPU_KERNEL (1|2|3),
+ * create their context themselves, can only be steered this way): VP8_GPU_DEVICE, VP8_GPU_KERNEL (2|3),
  * VP8_GPU_WARPS, VP8_GPU_IMAGES_PER_SM, VP8_GPU_CLUSTER, VP8_GPU_COMPACT (0|1), VP8_GPU_HOST_THREADS,
  * VP8_GPU_LOCKSTEP_SMALL (0: 8-warp CTAs spin instead of meeting at a barrier), VP8_GPU_NT_STORES (0: host compaction
  * with ordinary stores), VP8_GPU_TRACE (1: host-time split of a pipelined call on stderr, 2: plus a per-chunk device
@@ -63,16 +63,19 @@ typedef struct vp8_gpu_batch vp8_gpu_batch; /* n frames resident on the device *
 int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out);
 void vp8_gpu_destroy(vp8_gpu_ctx* ctx);
 int vp8_gpu_sync(vp8_gpu_ctx* ctx);
+/* The context keeps freed device blocks (up to 96 blocks / 64 GiB, in power-of-two size classes) so that steady-state
+ * calls never cudaMalloc. vp8_gpu_trim returns all of them to the driver, e.g. before another allocator needs the HBM. */
+int vp8_gpu_trim(vp8_gpu_ctx* ctx);
 const char* vp8_gpu_last_error(void);
 
-/* Tuning: warps cooperating on one image (4, 8, 16 or 32; 0 = pick from the batch size) and resident
+/* Tuning: warps cooperating on one image (4, 8 or 16; 0 = pick from the batch size) and resident
  * images per SM (0 = as many as fit). */
 int vp8_gpu_set_tuning(vp8_gpu_ctx* ctx, int warps_per_image, int images_per_sm);
 
-/* Which wavefront kernel runs m06/m07: 1 = one warp per macroblock (vp8_kernels.cu), 2 = one half-warp per macroblock,
- * two rows per warp (vp8_pairs.cu), 3 = as 2, and batches of several images per SM run its lockstep flavour (one CTA per
- * SM carries up to 7 images and all its warps meet at a barrier once per macroblock step, which keeps them on the same
- * instruction-cache lines). All are bit-exact; the environment variable VP8_GPU_KERNEL presets it. */
+/* Which schedule the wavefront kernel runs big batches in: 3 (default) = several images per SM run vp8_mb_lockstep (one
+ * CTA per SM carries up to 7 images and all its warps meet at a barrier every second macroblock step, which keeps them
+ * on the same instruction-cache lines), 2 = vp8_mb_pairs (one CTA per image) whatever the batch size. Both are bit-exact;
+ * the environment variable VP8_GPU_KERNEL presets it. */
 int vp8_gpu_set_kernel(vp8_gpu_ctx* ctx, int version);
 int vp8_gpu_last_groups(const vp8_gpu_ctx* ctx); /* images per CTA of the last wavefront launch if it was lockstep, else 0 */
 /* A batch that is not a whole number of lockstep waves is cut into segments (full waves, then the rest in the shape that
@@ -96,7 +99,8 @@ void vp8_gpu_host_free(void* p);
 
 /* Stage the ten per-frame arrays of n decoded frames (vp8_tokens.h:52-99) into device memory.
  * kf[i] supplies the visible width/height (vp8_header.h:7-18). Inputs are borrowed for the duration
- * of the call only. */
+ * of the call only: pageable arrays are staged through bounce buffers, pinned ones are read by the copy engine
+ * directly and the call returns once those copies have left the host. */
 int vp8_gpu_upload(vp8_gpu_ctx* ctx, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,
                    vp8_gpu_batch** out);
 void vp8_gpu_batch_free(vp8_gpu_ctx* ctx, vp8_gpu_batch* b);
@@ -130,8 +134,9 @@ int vp8_gpu_download_images(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, Yuv420Image* out
 /* Macroblock-aligned planes of frame i (VP8_GPU_PADDED batches), for inspection. */
 int vp8_gpu_download_padded(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, int i, uint8_t* y, uint8_t* u, uint8_t* v);
 
-/* Whole path in one call, pipelined: the batch is cut into chunks of `chunk` frames (0 = default 128) whose
- * host->device copies, kernels and device->host copies overlap on internal streams. dst (ideally pinned, as the
+/* Whole path in one call, pipelined: the batch is cut into chunks of `chunk` frames (0 = default 64; the first two
+ * chunks are a quarter of that and the third a half, so that the first download starts early) whose host->device
+ * copies, kernels and device->host copies overlap on internal streams. dst (ideally pinned, as the
  * frames' arrays) receives frame i at offsets[i]: the -yuv (filtered=0) / -yuvf bytes, resp. the -ppm bytes.
  * vp8_gpu_decode_bytes gives the capacity needed. Blocking. */
 int vp8_gpu_decode_i420(vp8_gpu_ctx* ctx, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,

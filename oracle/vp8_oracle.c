@@ -5,7 +5,7 @@
  * every function names the reference lines whose results it must reproduce bit for bit.
  *
  * Conventions used throughout (they differ from the reference's on purpose, the GPU kernels
- * share them, and tests/test_oracle_vs_ref.py proves them equivalent):
+ * share them, and tests/test_oracle.py proves them equivalent):
  *   - prediction reads a conceptual frame whose row -1 is all 127 and whose column -1 is 129
  *     (reference vp8_recon.c:395-421, 464-504, 554, 639-640 collapse to exactly this rule);
  *   - the ten 4x4 sub-block predictors are evaluated from one 16-entry edge vector and a

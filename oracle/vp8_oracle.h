@@ -5,7 +5,7 @@
  * TEST INFRASTRUCTURE ONLY: tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg are
  * the only callers. The product library (webp-decoder_b200/csrc) neither links nor loads it.
  *
- * Parity is PINNED: tests/test_oracle_vs_ref.py checks every function below against the real
+ * Parity is PINNED: tests/test_oracle.py checks every function below against the real
  * reference (oracle/_ref/libref_hot.so, built from /root/reference by oracle/Makefile) on the
  * fixture corpus and on struct-level fuzz frames, and tests/golden/ holds digests produced by
  * that reference which are re-checked wherever /root/reference is absent.

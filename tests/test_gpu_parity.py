@@ -55,10 +55,10 @@ def test_reference_fuzz_digests(gpu_ctx):
 DEFAULT_KERNEL = 3  # what a fresh context runs (vp8_gpu.h: vp8_gpu_set_kernel)
 
 
-@pytest.mark.parametrize("kernel,warps", [(1, 4), (1, 8), (1, 16), (1, 32), (2, 4), (2, 8), (2, 16), (3, 4), (3, 8), (3, 16)])
+@pytest.mark.parametrize("kernel,warps", [(2, 4), (2, 8), (2, 16), (3, 4), (3, 8), (3, 16)])
 def test_fuzz_vs_oracle_all_kernels_and_warp_shapes(gpu_ctx, oracle, kernel, warps):
-    """Every wavefront kernel (warp per macroblock / half-warp per macroblock / the same with the lockstep flavour of its
-    8-warp CTAs) in every CTA shape."""
+    """Both schedules of the wavefront kernel (warps spinning on progress stamps / warps of a CTA meeting at a barrier) in
+    every CTA shape."""
     gpu_ctx.set_kernel(kernel)
     gpu_ctx.set_tuning(warps, 0)
     try:
@@ -77,19 +77,6 @@ def test_fuzz_vs_oracle_all_kernels_and_warp_shapes(gpu_ctx, oracle, kernel, war
         gpu_ctx.set_kernel(DEFAULT_KERNEL)
 
 
-def test_first_generation_kernel_still_matches_reference_digests(gpu_ctx, golden, parsed_golden):
-    names = sorted(golden)
-    kfs = [parsed_golden[n][0] for n in names]
-    frs = [parsed_golden[n][1] for n in names]
-    gpu_ctx.set_kernel(1)
-    try:
-        for filtered, key in ((False, "yuv"), (True, "yuvf")):
-            outs = gpu_ctx.decode_i420(kfs, frs, filtered=filtered)
-            assert not [n for n, o in zip(names, outs) if sha(o) != golden[n][key]]
-    finally:
-        gpu_ctx.set_kernel(DEFAULT_KERNEL)
-
-
 def test_edge_geometries(gpu_ctx, oracle):
     """1-pixel frames, single rows/columns of macroblocks, widths that break 4-byte store alignment."""
     dims = [(1, 1), (1, 40), (40, 1), (2, 2), (15, 15), (16, 16), (17, 17), (33, 16), (16, 33), (129, 129), (131, 67),
@@ -104,7 +91,7 @@ def test_edge_geometries(gpu_ctx, oracle):
         assert p == oracle.ppm(oracle.rgb(yuvf, f.width, f.height), f.width, f.height), (f.width, f.height)
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("kernel", [2, 3])
 def test_maximum_frame_dimensions(gpu_ctx, oracle, kernel):
     """VP8 dimensions are 14-bit (vp8_header.c:46-49): the widest (1024 macroblock columns: largest line buffers) and the
     tallest (1024 macroblock rows: longest wavefront, progress ring wrap-around) frames a bitstream can carry."""

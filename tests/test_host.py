@@ -130,18 +130,19 @@ def test_parser_rejects_what_the_reference_rejects(lib):
     assert P.webp_size(good) == (16, 16)
 
 
-def test_packed_two_position_loop_filter_arithmetic(tmp_path):
-    """webp-decoder_b200/csrc/vp8_lf2.cuh (the VP8P_LF_SWAR=1 build of the pair kernels) restates the normal loop filter
-    with packed-halfword instructions and biased shifts; its host flavour emulates each instruction per half, and
-    tests/native/lf2_check.cpp compares it with a scalar restatement of vp8_loopfilter.c:24-121 over 1.6 million
-    tap / threshold combinations (two positions per word, different limits in the two halves)."""
+def test_rgb_tile_arithmetic_on_the_host(tmp_path):
+    """webp-decoder_b200/csrc/vp8_rgb.cuh (the arithmetic of the m08 kernel: U|V packed upsampler over 2x16-pixel tiles,
+    mult_hi as IMAD.HI, fused clip) also compiles for the host with each device instruction emulated;
+    tests/native/rgb_check.cpp runs 263 images (all edge geometries, three content flavours) through it against the
+    oracle's orc_i420_to_rgb and checks the clamped-index identity behind the row-end cases exhaustively."""
     import shutil
     import subprocess
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("no g++")
-    exe = tmp_path / "lf2_check"
-    src = Path(__file__).resolve().parent / "native" / "lf2_check.cpp"
-    subprocess.run([gxx, "-O2", "-std=c++17", "-o", str(exe), str(src)], check=True)
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "rgb_check"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-o", str(exe), str(root / "tests" / "native" / "rgb_check.cpp"), f"-L{root / 'oracle'}",
+                    "-loracle", f"-Wl,-rpath,{root / 'oracle'}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("ok "), out.stdout + out.stderr

@@ -29,7 +29,7 @@ def timed(kfs, frs, filtered=True, reps=20):
 
 for label, name in (("config1_512x512_noise", "noise_512x512_q75.webp"), ("config3_4k_checker", "checker_3840x2160_q75.webp"),
                     ("config3_4k_rgbgrad", "rgbgrad_3840x2160_q75.webp")):
-    for kern in (3, 2, 1):
+    for kern in (3, 2):
         ctx.set_kernel(kern)
         ctx.set_cluster(1)  # one CTA: the cluster numbers are in the last section
         i = idx[name]

@@ -51,7 +51,7 @@ def report(name, got, want, w, h, limit=6):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--kernel", type=int, default=1, help="1 = warp per macroblock, 2 = half-warp per macroblock, 3 = 2 + lockstep")
+    ap.add_argument("--kernel", type=int, default=3, help="2 = vp8_mb_pairs for every batch size, 3 = lockstep flavour for big batches")
     args = ap.parse_args()
     orc = Oracle()
     ctx = W.Context(0)
@@ -89,7 +89,7 @@ def main():
         w, h = fr.width, fr.height
         print(f"[{name}] {w}x{h} lf_level={fr.params['lf_level']} simple={fr.params['lf_use_simple']} seg={fr.params['segmentation_enabled']}")
         kf, d = fr.header(), fr.cstruct()
-        for warps in ((4,) if args.quick else ((4, 8, 32) if args.kernel == 1 else (4, 8, 16))):
+        for warps in ((4,) if args.quick else (4, 8, 16)):
             ctx.set_tuning(warps, 0)
             want_u = orc.decode_i420(fr, False)
             got_u = ctx.decode_i420([kf], [d], filtered=False)[0]

@@ -29,8 +29,8 @@ def main():
             h = int(rng.integers(1, 1300 if big and n <= 13 else 130))
             frames.append(fuzz_frame(int(rng.integers(1 << 30)), w, h, density=float(rng.choice([0.0, 0.02, 0.3, 0.9])),
                                      amp=int(rng.choice([5, 40, 400, 2500])), raw=bool(rng.integers(2))))
-        kernel = int(rng.choice([1, 2, 3, 3, 3]))
-        warps = int(rng.choice([0, 0, 4, 8, 16] if kernel > 1 else [0, 4, 8, 16, 32]))
+        kernel = int(rng.choice([2, 3, 3, 3]))
+        warps = int(rng.choice([0, 0, 4, 8, 16]))
         per_sm = int(rng.choice([0, 0, 1, 2, 3, 5, 7]))
         cluster = int(rng.choice([0, 0, 1, 2, 4, 8]))
         filtered = bool(rng.integers(2))

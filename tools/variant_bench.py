@@ -10,7 +10,7 @@ for name,sel in [("mix",[0,1,2,3]),("noise",[0]),("rgbgrad",[1]),("checker",[2])
     order=[sel[i%len(sel)] for i in range(1024)]
     kfs=[pf.kfs[i] for i in order]; frs=[pf.frames[i] for i in order]
     b=ctx.upload(kfs,frs)
-    for kern in (3,2,1):
+    for kern in (3,2):
         ctx.set_kernel(kern)
         for mode in ("fused","recon_only","staged"):
             for it in range(3):

@@ -35,7 +35,7 @@ EXPORTS = [
     "yuv420_alloc", "yuv420_free", "vp8_reconstruct_keyframe_yuv", "vp8_reconstruct_keyframe_yuv_filtered",
     "vp8_loopfilter_apply_keyframe", "yuv420_write_ppm_fd", "yuv420_write_png_fd",
     # batch interface
-    "vp8_gpu_init", "vp8_gpu_destroy", "vp8_gpu_sync", "vp8_gpu_last_error", "vp8_gpu_set_tuning",
+    "vp8_gpu_init", "vp8_gpu_destroy", "vp8_gpu_sync", "vp8_gpu_trim", "vp8_gpu_last_error", "vp8_gpu_set_tuning",
     "vp8_gpu_host_alloc", "vp8_gpu_host_free", "vp8_gpu_upload", "vp8_gpu_batch_free", "vp8_gpu_recon",
     "vp8_gpu_filter", "vp8_gpu_rgb", "vp8_gpu_run", "vp8_gpu_i420_bytes", "vp8_gpu_ppm_bytes",
     "vp8_gpu_download_i420", "vp8_gpu_download_ppm", "vp8_gpu_download_images", "vp8_gpu_download_padded",
@@ -68,6 +68,7 @@ def load_library() -> C.CDLL:
     L.vp8_gpu_destroy.argtypes = [vp]
     L.vp8_gpu_destroy.restype = None
     L.vp8_gpu_sync.argtypes = [vp]
+    L.vp8_gpu_trim.argtypes = [vp]
     L.vp8_gpu_last_error.restype = C.c_char_p
     L.vp8_gpu_set_tuning.argtypes = [vp, C.c_int, C.c_int]
     L.vp8_gpu_set_kernel.argtypes = [vp, C.c_int]
@@ -226,6 +227,10 @@ class Context:
 
     def sync(self):
         _check(self._L.vp8_gpu_sync(self._h), "vp8_gpu_sync")
+
+    def trim(self):
+        """Returns the context's cached device blocks to the driver."""
+        _check(self._L.vp8_gpu_trim(self._h), "vp8_gpu_trim")
 
     # ---- staging -----------------------------------------------------------------------------------------
     def _ptr_arrays(self, kfs, frames):

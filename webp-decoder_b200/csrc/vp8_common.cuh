@@ -1,4 +1,4 @@
-// vp8_common.cuh - device helpers shared by the wavefront kernels (vp8_kernels.cu, vp8_pairs.cu):
+// vp8_common.cuh - device helpers of the wavefront kernels (vp8_pairs.cu):
 // B_PRED tap table, integer transforms, loop-filter arithmetic, cropped stores.
 #pragma once
 #include <cuda_runtime.h>
@@ -6,13 +6,6 @@
 #include <stdint.h>
 
 #include "vp8_dev.h"
-
-#ifndef VP8_LF_GENERIC
-#define VP8_LF_GENERIC 0 // 1: one byte-addressed filter body looped over the 8 edges (smaller code, more instructions)
-#endif
-#ifndef VP8_BPRED_LOOP
-#define VP8_BPRED_LOOP 0 // 1: B_PRED steps as a 5 x 2 loop instead of 10 unrolled steps
-#endif
 
 namespace {
 
@@ -42,29 +35,6 @@ constexpr int kProgRing = 64;      // progress stamps, ring over macroblock rows
 constexpr int kStampRow = 4096;    // stamp = (row+1)*kStampRow + macroblocks done in that row
 constexpr int kBtabWords = 2 * 11 * 16;
 constexpr int kSmemFixed = 256 + 256 + kBtabWords * 4; // progress ring + image descriptor + B_PRED lane table
-
-// Per-warp shared-memory workspace.
-//   rt_*: reconstruction tile with a 1-pixel top/left border (what intra prediction reads).
-//         luma row r in [-1,15] at (r+1)*24, column c in [-1,19] at 4+c (columns 16..19 = above-right);
-//         chroma row r in [-1,7] at (r+1)*12, column c in [-1,7] at 4+c.
-//   ft_*: filter tile with 4-pixel top/left aprons. luma row r in [-4,15] at (r+4)*20, column c at 4+c;
-//         chroma row r in [-4,7] at (r+4)*12, column c at 4+c.
-//   coef: the macroblock's 25 coefficient blocks as landed by cp.async: 16-byte half h of block i at [h*25+i]
-//         (blocks 0..15 luma, 16..19 U, 20..23 V, 24 Y2), so that lane i reads both halves without bank conflicts.
-struct __align__(16) WarpWs {
-	uint8_t rt_y[17 * 24];
-	uint8_t rt_u[9 * 12];
-	uint8_t rt_v[9 * 12];
-	uint8_t lcol[32];     // unfiltered left neighbours packed: y[16] u[8] v[8]
-	int16_t res[16][16];  // luma residuals of a B_PRED macroblock; res[0] doubles as the WHT output
-	uint8_t ft_y[20 * 20];
-	uint8_t ft_u[12 * 12];
-	uint8_t ft_v[12 * 12];
-	uint4 coef[50];
-	uint8_t pad_[32];
-};
-static_assert(sizeof(WarpWs) % 16 == 0, "WarpWs alignment");
-static_assert(offsetof(WarpWs, res) % 16 == 0 && offsetof(WarpWs, coef) % 16 == 0, "vector slots must be 16-byte aligned");
 
 struct OutPlane {
 	uint8_t* p;
@@ -163,50 +133,6 @@ __device__ __forceinline__ void iwht4x4(const int (&v)[16], int (&r)[16]) {
 
 // ------------------------------------------------------------------------------------------------ loop filter
 enum { EDGE_MB = 0, EDGE_INNER = 1, EDGE_SIMPLE = 2 };
-
-// One position across an edge: q points at q0, `step` is the byte distance between the pixels p3..q3 (1 across a
-// vertical edge, the tile stride across a horizontal one). A single body serves every edge of every plane so that
-// the kernel stays inside the instruction cache; `kind` is warp-uniform.
-// Thresholds: reference vp8_loopfilter.c:24-56; kernels :58-104; dispatch :106-164.
-__device__ __forceinline__ void lf_line(uint8_t* q, int step, int kind, int lim, int interior, int hev_thr) {
-	int p1 = q[-2 * step], p0 = q[-step], q0 = q[0], q1 = q[step];
-	if (2 * absdiff(p0, q0) + (absdiff(p1, q1) >> 1) > lim) return;
-	int p2 = 0, q2 = 0;
-	bool hev = false;
-	if (kind != EDGE_SIMPLE) {
-		const int p3 = q[-4 * step], q3 = q[3 * step];
-		p2 = q[-3 * step];
-		q2 = q[2 * step];
-		const int dp = absdiff(p1, p0), dq = absdiff(q1, q0);
-		int m = __vimax3_s32(absdiff(p3, p2), absdiff(p2, p1), dp);
-		m = __vimax3_s32(m, absdiff(q3, q2), absdiff(q2, q1));
-		if (max(m, dq) > interior) return;
-		hev = max(dp, dq) > hev_thr;
-		if (kind == EDGE_MB && !hev) {
-			const int w = sclamp(sclamp(p1 - q1) + 3 * (q0 - p0));
-			const int a = (27 * w + 63) >> 7, b = (18 * w + 63) >> 7, c = (9 * w + 63) >> 7;
-			q[-step] = (uint8_t)add_clip255(p0, a);
-			q[0] = (uint8_t)add_clip255(q0, -a);
-			q[-2 * step] = (uint8_t)add_clip255(p1, b);
-			q[step] = (uint8_t)add_clip255(q1, -b);
-			q[-3 * step] = (uint8_t)add_clip255(p2, c);
-			q[2 * step] = (uint8_t)add_clip255(q2, -c);
-			return;
-		}
-	}
-	const bool outer = (kind != EDGE_INNER) || hev;
-	int a = 3 * (q0 - p0);
-	if (outer) a += sclamp(p1 - q1);
-	a = sclamp(a);
-	const int f1 = min(a + 4, 127) >> 3, f2 = min(a + 3, 127) >> 3; // a >= -128 already
-	q[0] = (uint8_t)add_clip255(q0, -f1);
-	q[-step] = (uint8_t)add_clip255(p0, f2);
-	if (!outer) {
-		const int h = (f1 + 1) >> 1;
-		q[step] = (uint8_t)add_clip255(q1, -h);
-		q[-2 * step] = (uint8_t)add_clip255(p1, h);
-	}
-}
 
 // One position across an edge, in registers. Returns true when pixels changed.
 // Thresholds: reference vp8_loopfilter.c:24-56; kernels :58-104; dispatch :106-164.

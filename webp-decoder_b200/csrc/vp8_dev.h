@@ -57,8 +57,7 @@ struct Vp8RgbDesc {
 	uint8_t* rgb;
 	uint32_t width, height;
 	uint32_t stride_y, stride_uv;
-	uint32_t first_block; // prefix sum of blocks over the batch
-	uint32_t pad_;
+	uint32_t pad_[2];
 };
 
 enum Vp8KernelMode {
@@ -67,12 +66,8 @@ enum Vp8KernelMode {
 	VP8_K_FILTER = 2,       // m07 only: padded unfiltered planes in, filtered planes out (in place allowed)
 };
 
-// Launchers (vp8_kernels.cu). warps_per_image in {4, 8, 16, 32}. Return cudaError_t as int.
-int vp8_launch_wavefront(int mode, int warps_per_image, const Vp8ImgDesc* descs_dev, int n_images, int max_mb_cols,
-                         int grid_ctas, void* stream);
-int vp8_wavefront_smem_bytes(int mode, int warps_per_image, int max_mb_cols);
-int vp8_wavefront_max_ctas_per_sm(int mode, int warps_per_image, int max_mb_cols);
-// Second-generation kernel (vp8_pairs.cu): half-warp per macroblock, two rows per warp. warps_per_image in {4, 8, 16}.
+// Launchers. Return cudaError_t as int.
+// Wavefront kernel (vp8_pairs.cu): half-warp per macroblock, two rows per warp. warps_per_image in {4, 8, 16}.
 // scratch: vp8_pairs_scratch_bytes(grid, max_mb_cols) bytes of device memory private to this launch.
 // cluster > 1 (2, 4 or 8; needs warps_per_image == 16): every image is processed by a thread-block cluster of that many
 // CTAs; grid_ctas must be a multiple of it and scratch sized for grid_ctas / cluster slots.
@@ -88,4 +83,6 @@ int vp8_launch_lockstep(int mode, const Vp8ImgDesc* descs_dev, int n_images, int
                         void* stream);
 int vp8_lockstep_smem_bytes(int groups, int max_mb_cols);
 int vp8_lockstep_max_groups(int max_mb_cols); // how many groups fit in the shared memory of one SM for this frame width (0: none)
-int vp8_launch_rgb(const Vp8RgbDesc* descs_dev, int n_images, uint32_t total_blocks, void* stream);
+// m08 (vp8_rgb.cu). tiles_per_image: host array, vp8_rgb_tiles() of every image.
+int vp8_launch_rgb(const Vp8RgbDesc* descs_dev, int n_images, const uint32_t* tiles_per_image, void* stream);
+uint32_t vp8_rgb_tiles(uint32_t width, uint32_t height);

@@ -2,7 +2,7 @@
 //
 // The only compute done on the host is per-frame header arithmetic (a few dozen integers: dequantisation
 // factors and loop-filter levels per segment) and file framing (PPM header, PNG container). Every pixel is
-// produced by the kernels in vp8_kernels.cu; there is no CPU fallback.
+// produced by the kernels in vp8_pairs.cu and vp8_rgb.cu; there is no CPU fallback.
 #include <cuda_runtime.h>
 #include <errno.h>
 #include <stdint.h>
@@ -50,6 +50,8 @@ int fail(int err, const char* what, cudaError_t ce = cudaSuccess) {
 constexpr size_t kAlign = 256;
 constexpr size_t kBounceBytes = 32u << 20;
 constexpr int kPpmSlot = 32; // header slot in front of each RGB image; RGB starts 32 bytes into the slot
+constexpr uint64_t kArenaMagic = 0x564138415245414eull; // stats_opaque[21] of frames whose arrays vp8_parse carved from ONE block
+                                                        // ([22] = base address, [23] = bytes); same constant in vp8_parse.cpp
 
 inline size_t align_up(size_t v, size_t a = kAlign) { return (v + a - 1) / a * a; }
 
@@ -137,8 +139,8 @@ struct vp8_gpu_ctx {
 	int tune_warps = 0, tune_imgs_per_sm = 0;
 	int tune_cluster = 0; // CTAs per image in cluster mode: 0 = automatic, 1 = never, 2/4/8 = at most that many
 	int last_cluster = 1;
-	int kernel_version = 3; // 1: vp8_mb_wavefront (warp per macroblock), 2: vp8_mb_pairs (half-warp per macroblock),
-	                        // 3: as 2, and big batches run its lockstep flavour (several images per CTA, barrier per step)
+	int kernel_version = 3; // 2: vp8_mb_pairs for every batch size, 3: big batches run vp8_mb_lockstep (several images
+	                        // per CTA, barrier every second step)
 	bool lockstep_small = true; // kernel 3: 8-warp CTAs also walk their steps in lockstep (VP8_GPU_LOCKSTEP_SMALL=0: no)
 	int last_groups = 0;    // images per CTA of the last launch when it was the lockstep flavour, else 0
 	uint8_t* bounce[2] = {nullptr, nullptr};
@@ -152,6 +154,15 @@ struct vp8_gpu_ctx {
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spare;
 	cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr}; // chunk pipeline of vp8_gpu_decode_*
 	cudaEvent_t pipe_ev = nullptr;
+	cudaEvent_t up_ev = nullptr;                        // "the input copies of this upload have left the host"
+	// descriptors travel from a small ring of pinned slots: a pageable source would make the runtime stage the copy
+	// synchronously, i.e. behind everything already queued on that stream (the host stalled behind chunk k's
+	// upload before it could start on chunk k+1)
+	static constexpr int kDescSlots = 8;
+	uint8_t* desc_stage[kDescSlots] = {};
+	size_t desc_stage_bytes[kDescSlots] = {};
+	cudaEvent_t desc_ev[kDescSlots] = {};
+	int desc_next = 0;
 	uint8_t* cstage[3] = {nullptr, nullptr, nullptr};   // pinned staging of compacted chunks, one per pipeline slot
 	size_t cstage_bytes[3] = {0, 0, 0};
 	int host_threads = 0;                               // workers compacting frames (0 = all cores, at most 32)
@@ -276,6 +287,7 @@ struct Uploader {
 	int cur = 0;
 	size_t fill = 0;          // bytes staged in bounce[cur]
 	uint8_t* dev_at = nullptr; // device address matching bounce[cur][0]
+	bool direct = false;      // some copy was queued straight from caller memory
 
 	int flush() {
 		if (fill) {
@@ -298,8 +310,9 @@ struct Uploader {
 	int put(uint8_t* dev, const void* src, size_t bytes) {
 		if (!bytes) return 0;
 		c->h2d += bytes;
-		if (is_pinned(src)) {
+		if (is_pinned(src) && is_pinned((const uint8_t*)src + bytes - 1)) {
 			CU(cudaMemcpyAsync(dev, src, bytes, cudaMemcpyHostToDevice, st));
+			direct = true; // the copy engine reads the caller's memory until the stream gets there
 			return 0;
 		}
 		if (ensure_bounce(c)) return -1;
@@ -455,7 +468,7 @@ int validate_frame(const Vp8KeyFrameHeader* kf, const Vp8DecodedFrame* f, bool n
 
 // Lay out and upload the per-frame arrays. With need_coeffs == false only what the loop filter reads is staged.
 int batch_create(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* fr, int n, bool need_coeffs,
-                 vp8_gpu_batch** out, cudaStream_t st = nullptr) {
+                 vp8_gpu_batch** out, cudaStream_t st = nullptr, bool caller_waits = false) {
 	if (!c || !kf || !fr || !out || n <= 0) return fail(EINVAL, "bad arguments");
 	for (int i = 0; i < n; i++)
 		if (validate_frame(kf[i], fr[i], need_coeffs)) return -1;
@@ -496,7 +509,11 @@ int batch_create(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8De
 		}
 		for (int k = 0; k < 4; k++)
 			if (sz[k] && ((src[k] - lo) & 15)) aligned = false; // cp.async needs 16-byte aligned coefficient blocks
-		if (need_coeffs && aligned && (size_t)(hi - lo) <= payload + payload / 64 + 4096) {
+		// Only an arena that says so itself counts as one block (vp8_parse.cpp marks its frames); address proximity alone
+		// would also accept the reference's ten adjacent callocs and then copy malloc headers, or fault on an unmapped hole.
+		const bool one_block = f->stats_opaque[21] == kArenaMagic && (const uint8_t*)(uintptr_t)f->stats_opaque[22] <= lo &&
+		                       hi <= (const uint8_t*)(uintptr_t)f->stats_opaque[22] + f->stats_opaque[23];
+		if (need_coeffs && aligned && one_block && payload) {
 			m.span_src = lo;
 			m.span_off = in;
 			m.span_bytes = (size_t)(hi - lo);
@@ -562,7 +579,38 @@ int batch_create(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8De
 		batch_destroy(c, b);
 		return -1;
 	}
+	// Inputs are borrowed for the duration of the call: copies queued straight from the caller's pinned arrays must have
+	// left the host before we return (a pipelined caller owns the frames for its whole call and waits itself).
+	if (up.direct && !caller_waits) {
+		if (!c->up_ev && cudaEventCreateWithFlags(&c->up_ev, cudaEventDisableTiming) != cudaSuccess) c->up_ev = nullptr;
+		cudaError_t e = c->up_ev ? cudaEventRecord(c->up_ev, b->stream) : cudaErrorUnknown;
+		e = e == cudaSuccess ? cudaEventSynchronize(c->up_ev) : cudaStreamSynchronize(b->stream);
+		if (e != cudaSuccess) {
+			batch_destroy(c, b);
+			return fail(EIO, "waiting for the input copies", e);
+		}
+	}
 	*out = b;
+	return 0;
+}
+
+// Host -> device copy of a small descriptor table through the context's pinned ring (asynchronous for real).
+int push_table(vp8_gpu_ctx* c, void* dev, const void* src, size_t bytes, cudaStream_t st) {
+	const int k = c->desc_next;
+	c->desc_next = (k + 1) % vp8_gpu_ctx::kDescSlots;
+	if (!c->desc_ev[k]) CU(cudaEventCreateWithFlags(&c->desc_ev[k], cudaEventDisableTiming));
+	else CU(cudaEventSynchronize(c->desc_ev[k])); // the copy that last used this slot (kDescSlots tables ago) is long done
+	if (c->desc_stage_bytes[k] < bytes) {
+		if (c->desc_stage[k]) cudaFreeHost(c->desc_stage[k]);
+		c->desc_stage[k] = nullptr;
+		c->desc_stage_bytes[k] = 0;
+		const size_t cap = std::max<size_t>(bytes, 64 << 10);
+		CU(cudaHostAlloc((void**)&c->desc_stage[k], cap, cudaHostAllocDefault));
+		c->desc_stage_bytes[k] = cap;
+	}
+	memcpy(c->desc_stage[k], src, bytes);
+	CU(cudaMemcpyAsync(dev, c->desc_stage[k], bytes, cudaMemcpyHostToDevice, st));
+	CU(cudaEventRecord(c->desc_ev[k], st));
 	return 0;
 }
 
@@ -623,8 +671,7 @@ int push_descs(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layout) {
 		d.lf_simple = m.lf_simple;
 		d.compact = m.compact ? 1 : 0;
 	}
-	// pageable source: the runtime stages it before returning, so the vector may die right after
-	CU(cudaMemcpyAsync(b->d_desc, h.data(), sizeof(Vp8ImgDesc) * b->n, cudaMemcpyHostToDevice, b->stream));
+	if (push_table(c, b->d_desc, h.data(), sizeof(Vp8ImgDesc) * b->n, b->stream)) return -1;
 	b->desc_key = kernel_mode * 2 + layout;
 	return 0;
 }
@@ -646,13 +693,11 @@ struct LaunchPlan {
 };
 
 int plan_launch(const vp8_gpu_ctx* c, int n, int max_mb_cols, int max_rows, int kernel_mode, LaunchPlan* out) {
-	const bool pairs = c->kernel_version >= 2;
 	LaunchPlan p;
-	p.warps = pick_warps(c, n);
-	if (pairs) p.warps = std::min(p.warps, 16); // a pair-kernel warp already carries two macroblock rows
+	p.warps = std::min(pick_warps(c, n), 16); // a warp carries two macroblock rows
 	int per_sm = 0;
 	for (;; p.warps /= 2) {
-		per_sm = pairs ? vp8_pairs_max_ctas_per_sm(kernel_mode, p.warps, max_mb_cols) : vp8_wavefront_max_ctas_per_sm(kernel_mode, p.warps, max_mb_cols);
+		per_sm = vp8_pairs_max_ctas_per_sm(kernel_mode, p.warps, max_mb_cols);
 		if (per_sm > 0 || p.warps == 4) break;
 	}
 	if (per_sm <= 0) return fail(EIO, "wavefront kernel does not fit on an SM (frame too wide?)", cudaGetLastError());
@@ -667,7 +712,7 @@ int plan_launch(const vp8_gpu_ctx* c, int n, int max_mb_cols, int max_rows, int 
 	p.grid = std::min(n, per_sm * c->sm_count);
 	// Few big frames: spread each over a thread-block cluster so that one image can use several SMs. Worth it only when
 	// 16-warp CTAs are already in use, the GPU would otherwise be mostly idle and the frame has rows to hand out.
-	if (pairs && p.warps == 16 && c->tune_cluster != 1) {
+	if (p.warps == 16 && c->tune_cluster != 1) {
 		int want = c->tune_cluster > 1 ? c->tune_cluster : 8;
 		while (want > 1 && (n * want > c->sm_count || 32 * (want - 1) >= max_rows)) want /= 2; // every CTA must get rows
 		p.cluster = want;
@@ -691,7 +736,6 @@ int plan_launch(const vp8_gpu_ctx* c, int n, int max_mb_cols, int max_rows, int 
 
 int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layout) {
 	if (push_descs(c, b, kernel_mode, layout)) return -1;
-	const bool pairs = c->kernel_version >= 2;
 	int max_rows = 0;
 	for (auto& m : b->meta) max_rows = std::max<int>(max_rows, m.mb_rows);
 	// A batch is cut into segments, one launch each. An image takes a group of warps a fixed time, so a lockstep launch is
@@ -717,16 +761,14 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 		segs.push_back(sg);
 		first += sg.count;
 	}
-	if (pairs) {
-		size_t need = 0;
-		for (auto& sg : segs) need = std::max(need, vp8_pairs_scratch_bytes(sg.plan.slots(), b->max_mb_cols)); // launches run one after the other
-		if (b->scratch_bytes < need) {
-			dev_release(c, b->d_scratch, b->scratch_bytes);
-			b->d_scratch = nullptr;
-			b->scratch_bytes = 0;
-			if (dev_alloc(c, need, (void**)&b->d_scratch)) return -1;
-			b->scratch_bytes = need;
-		}
+	size_t need = 0;
+	for (auto& sg : segs) need = std::max(need, vp8_pairs_scratch_bytes(sg.plan.slots(), b->max_mb_cols)); // launches run one after the other
+	if (b->scratch_bytes < need) {
+		dev_release(c, b->d_scratch, b->scratch_bytes);
+		b->d_scratch = nullptr;
+		b->scratch_bytes = 0;
+		if (dev_alloc(c, need, (void**)&b->d_scratch)) return -1;
+		b->scratch_bytes = need;
 	}
 	std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
 	if (!c->spare.empty()) {
@@ -742,9 +784,8 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 		const LaunchPlan& p = sg.plan;
 		const Vp8ImgDesc* descs = b->d_desc + sg.first;
 		rc = p.groups ? vp8_launch_lockstep(kernel_mode, descs, sg.count, b->max_mb_cols, p.grid, p.groups, b->d_scratch, b->stream)
-		     : pairs  ? vp8_launch_pairs(kernel_mode, p.warps, descs, sg.count, b->max_mb_cols, p.grid, b->d_scratch, p.cluster,
-		                                 c->kernel_version == 3 && c->lockstep_small, b->stream)
-		              : vp8_launch_wavefront(kernel_mode, p.warps, descs, sg.count, b->max_mb_cols, p.grid, b->stream);
+		              : vp8_launch_pairs(kernel_mode, p.warps, descs, sg.count, b->max_mb_cols, p.grid, b->d_scratch, p.cluster,
+		                                 c->kernel_version == 3 && c->lockstep_small, b->stream);
 		if (rc != 0) break;
 		c->launches++;
 	}
@@ -761,9 +802,7 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 	c->last_cluster = p.cluster;
 	c->last_groups = p.groups;
 	c->last_segments = (int)segs.size();
-	c->last_smem = p.groups ? vp8_lockstep_smem_bytes(p.groups, b->max_mb_cols)
-	               : pairs  ? vp8_pairs_smem_bytes(p.warps, b->max_mb_cols)
-	                        : vp8_wavefront_smem_bytes(kernel_mode, p.warps, b->max_mb_cols);
+	c->last_smem = p.groups ? vp8_lockstep_smem_bytes(p.groups, b->max_mb_cols) : vp8_pairs_smem_bytes(p.warps, b->max_mb_cols);
 	return 0;
 }
 
@@ -820,13 +859,13 @@ int rgb_of_host_image(vp8_gpu_ctx* c, const Yuv420Image* img, std::vector<uint8_
 	for (uint32_t r = 0; r < ch && !rc; r++) rc = up.put(dv + (size_t)r * cw, img->v + (size_t)r * img->stride_uv, cw);
 	if (!rc) rc = up.flush();
 	if (!rc) {
-		Vp8RgbDesc d{dy, du, dv, d_rgb, w, h, w, cw, 0, 0};
+		Vp8RgbDesc d{dy, du, dv, d_rgb, w, h, w, cw, {0, 0}};
 		cudaError_t e = cudaMemcpyAsync(d_desc, &d, sizeof(d), cudaMemcpyHostToDevice, c->stream);
 		if (e != cudaSuccess) rc = fail(EIO, "descriptor upload", e);
 	}
 	if (!rc) {
-		const uint32_t groups = ((w + 7) / 8) * h;
-		const int lrc = vp8_launch_rgb(d_desc, 1, (groups + 255) / 256, c->stream);
+		const uint32_t tiles = vp8_rgb_tiles(w, h);
+		const int lrc = vp8_launch_rgb(d_desc, 1, &tiles, c->stream);
 		if (lrc) rc = fail(EIO, "rgb launch", (cudaError_t)lrc);
 		else c->launches++;
 	}
@@ -984,7 +1023,7 @@ int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out) {
 		}
 		c->own_stream = true;
 	}
-	if (const char* k = getenv("VP8_GPU_KERNEL")) c->kernel_version = std::min(3, std::max(1, atoi(k)));
+	if (const char* k = getenv("VP8_GPU_KERNEL")) c->kernel_version = std::min(3, std::max(2, atoi(k)));
 	if (const char* w = getenv("VP8_GPU_WARPS")) c->tune_warps = atoi(w);
 	if (const char* w = getenv("VP8_GPU_CLUSTER")) c->tune_cluster = atoi(w);
 	if (const char* w = getenv("VP8_GPU_HOST_THREADS")) c->host_threads = atoi(w);
@@ -1014,9 +1053,22 @@ void vp8_gpu_destroy(vp8_gpu_ctx* c) {
 	for (auto& p : c->cstage)
 		if (p) cudaFreeHost(p);
 	if (c->pipe_ev) cudaEventDestroy(c->pipe_ev);
+	if (c->up_ev) cudaEventDestroy(c->up_ev);
+	for (int i = 0; i < vp8_gpu_ctx::kDescSlots; i++) {
+		if (c->desc_stage[i]) cudaFreeHost(c->desc_stage[i]);
+		if (c->desc_ev[i]) cudaEventDestroy(c->desc_ev[i]);
+	}
 	delete c->pool;
 	if (c->own_stream) cudaStreamDestroy(c->stream);
 	delete c;
+}
+
+int vp8_gpu_trim(vp8_gpu_ctx* c) {
+	if (!c) return fail(EINVAL, "null context");
+	CU(cudaSetDevice(c->device));
+	for (auto& b : c->cache) cudaFree(b.p);
+	c->cache.clear();
+	return 0;
 }
 
 int vp8_gpu_sync(vp8_gpu_ctx* c) {
@@ -1053,7 +1105,7 @@ int vp8_gpu_last_groups(const vp8_gpu_ctx* c) { return c ? c->last_groups : 0; }
 int vp8_gpu_last_segments(const vp8_gpu_ctx* c) { return c ? c->last_segments : 0; }
 
 int vp8_gpu_set_kernel(vp8_gpu_ctx* c, int version) {
-	if (!c || (version < 1 || version > 3)) return fail(EINVAL, "bad kernel version");
+	if (!c || (version != 2 && version != 3)) return fail(EINVAL, "bad kernel version");
 	c->kernel_version = version;
 	return 0;
 }
@@ -1129,7 +1181,7 @@ int vp8_gpu_rgb(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
 	if (!b->d_rgb && dev_alloc(c, b->rgb_bytes, (void**)&b->d_rgb)) return -1;
 	if (!b->d_rgbdesc && dev_alloc(c, sizeof(Vp8RgbDesc) * b->n, (void**)&b->d_rgbdesc)) return -1;
 	std::vector<Vp8RgbDesc> h(b->n);
-	uint32_t max_blocks = 0;
+	std::vector<uint32_t> tiles(b->n);
 	for (int i = 0; i < b->n; i++) {
 		const FrameMeta& m = b->meta[i];
 		Vp8RgbDesc& d = h[i];
@@ -1151,11 +1203,10 @@ int vp8_gpu_rgb(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
 			d.stride_uv = m.mb_cols * 8;
 		}
 		d.rgb = b->d_rgb + m.rgb_off + kPpmSlot;
-		const uint32_t groups = ((m.width + 7) / 8) * m.height;
-		max_blocks = std::max(max_blocks, (groups + 255) / 256);
+		tiles[i] = vp8_rgb_tiles(m.width, m.height);
 	}
-	CU(cudaMemcpyAsync(b->d_rgbdesc, h.data(), sizeof(Vp8RgbDesc) * b->n, cudaMemcpyHostToDevice, b->stream));
-	const int rc = vp8_launch_rgb(b->d_rgbdesc, b->n, max_blocks, b->stream);
+	if (push_table(c, b->d_rgbdesc, h.data(), sizeof(Vp8RgbDesc) * b->n, b->stream)) return -1;
+	const int rc = vp8_launch_rgb(b->d_rgbdesc, b->n, tiles.data(), b->stream);
 	if (rc) return fail(EIO, "rgb launch", (cudaError_t)rc);
 	c->launches++;
 	b->have_rgb = true;
@@ -1569,8 +1620,8 @@ static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, 
 		c->trace_retire_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_r0).count();
 		vp8_gpu_batch* b = nullptr;
 		if (timeline) tl_host.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_p0).count());
-		if (c->compact_transport && c->kernel_version >= 2) rc = batch_create_compact(c, kf + first, frames + first, cnt, slot, s_up, &b);
-		else rc = batch_create(c, kf + first, frames + first, cnt, true, &b, s_up);
+		if (c->compact_transport) rc = batch_create_compact(c, kf + first, frames + first, cnt, slot, s_up, &b);
+		else rc = batch_create(c, kf + first, frames + first, cnt, true, &b, s_up, true);
 		if (rc) break;
 		ch.b = b;
 		mark(s_up);

@@ -1,10 +1,23 @@
-// vp8_pairs.cu - second-generation wavefront kernel: every HALF-warp is a macroblock engine.
+// vp8_pairs.cu - the macroblock wavefront kernels: m06 reconstruction (dequantisation, inverse WHT / DCT, intra
+// prediction, residual add; reference vp8_recon.c:423-684) fused with the m07 in-loop deblocking filter
+// (vp8_loopfilter.c:201-283) and the crop to the visible frame (vp8_recon.c:693-707). Every HALF-warp is a macroblock
+// engine.
 //
-// Same arithmetic, same single pass over HBM and the same shared-memory line-buffer scheme as vp8_mb_wavefront
-// (vp8_kernels.cu, read that header first); what changes is the lane mapping, chosen from the ncu profile of that
-// kernel (profiles/README.md: instruction-issue bound, ~70 % of lanes active, every per-macroblock overhead paid once
-// per warp):
+// Single pass over HBM: nothing but coefficients / modes is read and nothing but final pixels is written.
+//   * MB(x, y) needs MB(x-1, y), MB(x, y-1) and MB(x+1, y-1) - for prediction (vp8_recon.c:464-504 reads row y-1 up to
+//     column x+19) and for the loop filter alike (MB(x+1, y-1)'s left-edge filter rewrites the corner MB(x, y)'s top-edge
+//     filter reads) - so the rows of an image form a diagonal wavefront; the only synchronisation is one progress stamp
+//     per macroblock row, no inter-CTA dependency outside cluster mode;
+//   * the unfiltered bottom pixel row of every macroblock (what the row below predicts from) lives in a line buffer
+//     (tu_*), the unfiltered right column stays in the engine's own tile;
+//   * the loop filter runs on a 20x20 (+2x 12x12) tile whose 4-pixel top/left aprons are the already filtered
+//     neighbours: the left apron is the engine's previous tile, the top apron the last four filtered rows of the
+//     macroblock row above (tf_*);
+//   * a macroblock's pixels are stored only once they can no longer change: the block of rows -4..11 / columns -4..11
+//     relative to the macroblock (the right 4 columns and bottom 4 rows wait for the neighbours' edge filters).
 //
+// Lane mapping (chosen from the ncu profile of the first kernel, one warp per macroblock - profiles/README.md:
+// instruction-issue bound, ~70 % of lanes active, every per-macroblock overhead paid once per warp):
 //   * a warp walks TWO macroblock rows in staggered lockstep: lanes 0..15 do MB(t, y), lanes 16..31 do MB(t-2, y+1).
 //     Row y+1 trails row y by two macroblocks, which is exactly its dependency (left, top, top-right), so the pair
 //     needs no flag between its rows; only every second row boundary spins on a progress stamp.
@@ -16,17 +29,10 @@
 //     of shared memory: shared memory per image drops from 10 to 2 bytes per pixel column, which is what lets 7-8
 //     images stay resident per SM although every warp now carries two macroblock workspaces.
 #include "vp8_common.cuh"
-#include "vp8_lf2.cuh"
 
 #ifndef VP8P_HALF_SKEW
 #define VP8P_HALF_SKEW 64
 #endif
-#ifndef VP8P_LF_SWAR
-#define VP8P_LF_SWAR 0 // 1: normal loop filter with two positions per lane (vp8_lf2.cuh), 0: one position per lane.
-                        // Bit-exact either way; measured equal in the lockstep kernel (14.0 ms: 6 % MORE executed instructions,
-                        // fewer shared-memory round trips) and slower in vp8_mb_pairs (17.7 -> 19.1 ms), see DESIGN.md 4.1c
-#endif
-constexpr int kFtC = VP8P_LF_SWAR ? 20 : 12; // row stride of the chroma filter tiles (20 = the luma tile's: one set of offsets)
 
 namespace {
 
@@ -41,8 +47,8 @@ struct __align__(16) HalfWs {
 	uint8_t lcol[32];
 	int16_t res[16][16];
 	uint8_t ft_y[20 * 20];
-	uint8_t ft_u[12 * kFtC]; // 12 rows of 12 pixels; the row stride equals the luma tile's, so that one set of compile-time
-	uint8_t ft_v[12 * kFtC]; // offsets serves every lane of the two-positions-per-lane loop filter
+	uint8_t ft_u[12 * 12];
+	uint8_t ft_v[12 * 12];
 	uint4 coef[52];
 	uint8_t skew_[VP8P_HALF_SKEW]; // the two halves of a warp touch the same offsets of their workspaces in the same instruction:
 	                               // with sizeof(HalfWs) = 64 mod 128 they do so on complementary shared-memory banks
@@ -111,21 +117,6 @@ __device__ __forceinline__ void fetch_dense(HalfWs& ws, const Vp8ImgDesc* sd, si
 
 constexpr int kClusterProg = 1024; // progress stamps per image in cluster mode (VP8 frames have at most 1024 macroblock rows)
 
-#ifndef VP8P_BPRED_UNROLL
-#define VP8P_BPRED_UNROLL 16 // sub-block steps unrolled per loop iteration (16 = fully unrolled)
-#endif
-#ifndef VP8P_BLOCK_UNROLL
-#define VP8P_BLOCK_UNROLL 2 // 2: both 4x4 blocks of a lane unrolled, 1: looped
-#endif
-#ifndef VP8P_LF_COMPACT
-#define VP8P_LF_COMPACT 0 // 1: ONE byte-addressed filter body looped over the 12 edge passes (smallest code)
-#endif
-#ifndef VP8P_LF_LOOP
-#define VP8P_LF_LOOP 0 // 1: inner edges 4/8/12 as a loop, 0: unrolled
-#endif
-#define VP8P_STR2(x) #x
-#define VP8P_STR(x) VP8P_STR2(x)
-#define VP8P_UNROLL(n) _Pragma(VP8P_STR(unroll n))
 #ifndef VP8_PAIR_MIN_CTAS
 #define VP8_PAIR_MIN_CTAS(NW) ((NW) == 4 ? 7 : (NW) == 8 ? 3 : 1)
 #endif
@@ -308,24 +299,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 // loop ends when no warp has work left (__syncthreads_or). Image hand-over inside a group: warps count themselves out
 // (ctl[0]); when all NW have, the group's first warp loads the next descriptor and publishes it (ctl[1]).
 constexpr int kLockMaxGroups = 7;
-#ifndef VP8P_LOCK_BARRIER_EVERY
-#define VP8P_LOCK_BARRIER_EVERY 2 // the lockstep kernel's warps meet every N-th step (measured: 1 -> 14.37 ms, 2 -> 14.11, 4 -> 14.32)
-#endif
-#ifndef VP8P_LOCK_PER_SCHEDULER
-#define VP8P_LOCK_PER_SCHEDULER 0 // 1: only the warps that share a scheduler (same index in their group) meet at the barrier
-#endif
-#if VP8P_LOCK_PER_SCHEDULER
-// Barrier + OR-reduction among the `count` threads that use barrier `id`.
-__device__ __forceinline__ bool bar_red_or(int id, int count, bool pred) {
-	uint32_t r;
-	asm volatile(
-	    "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %3, 0;\n\tbar.red.or.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-	    : "=r"(r)
-	    : "r"(id), "r"(count), "r"((uint32_t)pred)
-	    : "memory");
-	return r != 0;
-}
-#endif
+constexpr int kLockBarrierEvery = 2; // the lockstep kernel's warps meet every N-th step (measured: 1 -> 14.37 ms, 2 -> 14.11, 4 -> 14.32)
 
 // Per-image values every warp of a group needs but only now and then: kept in shared memory, not in registers.
 struct LockImage {
@@ -421,9 +395,7 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 	const uint8_t* const bp_tab = reinterpret_cast<const uint8_t*>(btab + half * 176 + hl);
 	const bool dc_tap = (hl >= 2 && hl <= 5) || (hl >= 7 && hl <= 10);
 
-#if VP8P_LOCK_BARRIER_EVERY > 1
 	int round_no = 0;
-#endif
 	enum { ST_IMAGE, ST_ROW, ST_STEP, ST_DONE };
 	int state = ST_IMAGE, taken = 0; // taken: images this warp has finished
 	int p = 0, t = 0;
@@ -501,15 +473,7 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 		//      the barrier instead was measured: slower, 15.5 vs 15.0 ms)
 #define VP8P_STEP_NO_SPIN
 #define VP8P_STEP_ACTIVE active
-#if VP8P_LOCK_PER_SCHEDULER
-		// warps with the same index in their group sit on the same scheduler (warp id mod 4): they share its instruction
-		// buffer, the four sets are free to drift apart
-		if (!bar_red_or(1 + warp, groups * 32, state != ST_DONE)) break;
-#elif VP8P_LOCK_BARRIER_EVERY > 1
-		if ((++round_no % VP8P_LOCK_BARRIER_EVERY) == 0 && !__syncthreads_or(state != ST_DONE)) break;
-#else
-		if (!__syncthreads_or(state != ST_DONE)) break;
-#endif
+		if ((++round_no % kLockBarrierEvery) == 0 && !__syncthreads_or(state != ST_DONE)) break;
 		if (active) {
 #include "vp8_pairs_step_a.inc"
 #include "vp8_pairs_step_b.inc"

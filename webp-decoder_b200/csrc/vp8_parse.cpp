@@ -252,6 +252,10 @@ int parse_payload(const uint8_t* d, size_t n, Vp8KeyFrameHeader* kf, Vp8DecodedF
 	out->ymode = cv.take<uint8_t>(mb);
 	out->uv_mode = cv.take<uint8_t>(mb);
 	out->stats_opaque[24] = own ? 0x6f776e6564ull : 0; // "owned" marker for vp8_parse_free
+	// the arrays above are ONE block: lets vp8_gpu_upload move a frame with a single transfer (vp8_gpu.cu, kArenaMagic)
+	out->stats_opaque[21] = 0x564138415245414eull;
+	out->stats_opaque[22] = (uint64_t)(uintptr_t)arena;
+	out->stats_opaque[23] = (uint64_t)need;
 	auto bail = [&](int e) {
 		if (own) free(arena);
 		memset(out, 0, sizeof(*out));
