@@ -20,6 +20,7 @@
 #define VP8_GPU_H
 
 #include "vp8_abi.h"
+#include "vp8_parse.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -88,9 +89,11 @@ int vp8_gpu_last_segments(const vp8_gpu_ctx* ctx);
 int vp8_gpu_set_cluster(vp8_gpu_ctx* ctx, int ctas_per_image);
 int vp8_gpu_last_cluster(const vp8_gpu_ctx* ctx); /* CTAs per image of the last wavefront launch */
 
-/* Transport of the pipelined calls (vp8_gpu_decode_*): compact != 0 (default) ships each frame without its all-zero
- * 4x4 blocks (per-macroblock presence mask + packed blocks, built by host_threads workers; 0 = all cores), which is
- * what the host->device link is bound by; compact == 0 ships the dense arrays as they are. */
+/* Transport of vp8_gpu_decode_i420 / _ppm (dense Vp8DecodedFrames in): compact != 0 (default) ships each frame without
+ * its all-zero 4x4 blocks (per-macroblock presence mask + packed blocks, built by host_threads workers; 0 = all cores,
+ * at most 32), which is what the host->device link is bound by; compact == 0 ships the dense arrays as they are (pure
+ * DMA of three times the bytes: the better choice when only a few host threads per GPU are available). host_threads is
+ * also the number of parser threads of vp8_gpu_decode_webp. */
 int vp8_gpu_set_transport(vp8_gpu_ctx* ctx, int compact, int host_threads);
 
 /* Pinned host memory: frames whose arrays live here are copied to the device without staging. */
@@ -145,6 +148,34 @@ int vp8_gpu_decode_ppm(vp8_gpu_ctx* ctx, const Vp8KeyFrameHeader* const* kf, con
                        uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk);
 size_t vp8_gpu_decode_bytes(const Vp8KeyFrameHeader* const* kf, int n, int ppm);
 
+/* The same pipelined call for frames that are compact already (vp8_parse_webp_compact / vp8_parse_batch_compact,
+ * include/vp8_parse.h): nothing is re-scanned or repacked on the host. Frames in pinned memory are read by the copy
+ * engine where they are - one transfer per run of frames that sit back to back, which is how vp8_parse_batch_compact
+ * lays a batch out - pageable ones are gathered through pinned staging. ppm != 0: -ppm bytes (filtered is implied),
+ * else the -yuv / -yuvf bytes. Output layout and capacity as vp8_gpu_decode_i420 / _ppm (vp8_gpu_decode_bytes). */
+int vp8_gpu_decode_compact(vp8_gpu_ctx* ctx, const Vp8CompactFrame* const* frames, int n, int filtered, int ppm, uint8_t* dst,
+                           size_t cap, size_t* offsets, size_t* sizes, int chunk);
+
+/* .webp bytes in, pixels out: the host threads of the context (vp8_gpu_set_transport) run the serial part - container,
+ * header, bool decoder and token parsing, one image per thread (the reference's m01 + m02 + m05, main.c:630-664) - straight
+ * into the pinned arena of the chunk while the GPU works on the chunks before it. Same acceptance rules as
+ * vp8_parse_webp; a file that fails to parse fails the call with its errno. vp8_gpu_decode_webp_bytes gives the
+ * capacity needed (0 if a file is not a simple lossy WebP key frame). */
+int vp8_gpu_decode_webp(vp8_gpu_ctx* ctx, const uint8_t* const* files, const size_t* file_sizes, int n, int filtered, int ppm,
+                        uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk);
+size_t vp8_gpu_decode_webp_bytes(const uint8_t* const* files, const size_t* file_sizes, int n, int ppm);
+
+/* Where a pipelined call of this context spent its host time (milliseconds, last call): total, host work on the chunks
+ * (compaction of dense frames / gather / parsing), waiting for staging slots and retiring chunks. */
+int vp8_gpu_last_call_profile(const vp8_gpu_ctx* ctx, double* total_ms, double* host_work_ms, double* wait_ms);
+
+/* Several GPUs share one host: bind the calling thread (and the context's worker threads created afterwards) to the
+ * CPUs that are local to the context's GPU (sysfs local_cpulist of its PCI device), so that pinned staging and the
+ * workers' traffic stay on that NUMA node. share > 1: take only the (index % share)-th slice of that CPU list, for
+ * `share` contexts (ranks) whose GPUs hang off the same node. Returns the number of CPUs bound to, 0 if the topology
+ * could not be read (nothing is changed then), -1 on error. */
+int vp8_gpu_bind_host(vp8_gpu_ctx* ctx, int index, int share);
+
 /* m09 framing of an RGB24 image (what vp8_gpu_download_ppm / vp8_gpu_decode_ppm return behind the PPM header): the exact
  * bytes reference yuv420_write_png_fd emits (yuv2rgb_png.c:208-364). out must hold vp8_gpu_png_bound bytes; returns the
  * length, 0 on error. Host-side (stored deflate, slice-by-8 CRC-32, blocked Adler-32). */
@@ -160,6 +191,8 @@ int vp8_gpu_last_launch_config(const vp8_gpu_ctx* ctx, int* warps_per_image, int
 /* Sum of the device-side durations (CUDA events on the context's stream) of the wavefront launches issued since
  * the previous call, and how many there were. Waits for them to finish. */
 int vp8_gpu_kernel_time(vp8_gpu_ctx* ctx, double* total_ms, int* launches);
+/* Same for the m08 (RGB) launches of vp8_gpu_rgb / vp8_gpu_decode_ppm. */
+int vp8_gpu_rgb_time(vp8_gpu_ctx* ctx, double* total_ms, int* launches);
 
 /* Host-side per-frame parameter derivation, exported so tests can pin it against the oracle:
  * dq[4][6] = {y1dc,y1ac,uvdc,uvac,y2dc,y2ac} per segment (vp8_recon.c:57-76);

@@ -3,10 +3,15 @@
 
 TEST/MEASUREMENT INFRASTRUCTURE ONLY (bench.py's cpu_baseline leg and `bench.py --impl reference`).
 
-Each worker process loads the UNMODIFIED reference (oracle/_ref/libref_decode.so, built from /root/reference by
-oracle/Makefile), decodes the tokens of every input once with the reference's own m01..m05 (untimed, as the GPU
-arm's inputs are also already parsed), then times `vp8_reconstruct_keyframe_yuv_filtered` (or `_yuv`, or
-`..._filtered` + `yuv420_write_ppm_fd` to /dev/null) over its share of a bounded number of frames.
+Each worker process loads the UNMODIFIED reference (oracle/_ref/libref_decode[_v3].so, built from /root/reference by
+oracle/Makefile; the x86-64-v3 build when this host's CPU has AVX2/BMI2/FMA) and runs one of two loops over its share of
+a bounded number of frames:
+  stage  the tokens of every input are decoded once with the reference's own m01..m05 (untimed, as the GPU arm's inputs
+         are also already parsed), then `vp8_reconstruct_keyframe_yuv_filtered` (or `_yuv`, or `..._filtered` +
+         `yuv420_write_ppm_fd` to /dev/null) is timed: stage-matched with the GPU kernel / e2e numbers;
+  whole  the reference decoder's whole in-memory path per frame, as main.c:630-702 (cmd_yuvf) runs it: container +
+         header + `vp8_decode_decoded_frame` (bool decoder, tokens) + reconstruction + loop filter (+ PPM), .webp bytes in
+         memory to pixels in memory: the counterpart of the GPU arm's e2e_from_webp.
 One process per core; throughput = pixels of all workers / slowest worker's time.
 If oracle/_ref is absent the oracle port (oracle/liboracle.so) is timed instead and `kind` says "port".
 Prints one JSON object.
@@ -26,26 +31,58 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "tests"))
 
 
+def ref_library():
+    """(path, flags) of the reference build this host should run."""
+    import vp8fix
+    v3 = vp8fix.REF_DIR / "libref_decode_v3.so"
+    try:
+        flags = set(next(l for l in open("/proc/cpuinfo") if l.startswith("flags")).split())
+    except (OSError, StopIteration):
+        flags = set()
+    if v3.exists() and {"avx2", "bmi2", "fma"} <= flags:
+        return v3, "gcc -O3 -march=x86-64-v3 (portable stand-in for -march=native: built off the box)"
+    return vp8fix.REF_DIR / "libref_decode.so", "gcc -O3 (x86-64 baseline)"
+
+
 def _worker(args):
-    files, mode, reps, kind = args
+    files, mode, reps, kind, whole = args
     import numpy as np  # noqa: F401
+    import vp8fix
     from vp8fix import Oracle, Reference
     if kind == "reference":
-        ref = Reference()
+        ref = Reference(ref_library()[0])
         frames = [ref.parse_webp(Path(f).read_bytes()) for f in files]
         L = ref.lib
-        from vp8fix import Yuv420Image
+        from vp8fix import ByteSpan, DecodedFrame, KeyFrameHeader, Yuv420Image, u8p
         fn = L.vp8_reconstruct_keyframe_yuv if mode == "yuv" else L.vp8_reconstruct_keyframe_yuv_filtered
         structs = [(fr.header(), fr.cstruct()) for fr in frames]
         devnull = os.open(os.devnull, os.O_WRONLY)
         img = Yuv420Image()
+        if whole:
+            spans = []
+            for f in files:
+                data = Path(f).read_bytes()
+                size = int.from_bytes(data[16:20], "little")
+                payload = (C.c_uint8 * size).from_buffer_copy(data[20:20 + size])
+                spans.append((payload, ByteSpan(C.cast(payload, u8p), size)))
 
-        def one(i):
-            h, d = structs[i]
-            assert fn(C.byref(h), C.byref(d), C.byref(img)) == 0
-            if mode == "ppm":
-                assert L.yuv420_write_ppm_fd(devnull, C.byref(img)) == 0
-            L.yuv420_free(C.byref(img))
+            def one(i):
+                kf, d = KeyFrameHeader(), DecodedFrame()
+                span = spans[i][1]
+                assert L.vp8_parse_keyframe_header(span, C.byref(kf)) == 0
+                assert L.vp8_decode_decoded_frame(span, C.byref(d)) == 0
+                assert fn(C.byref(kf), C.byref(d), C.byref(img)) == 0
+                if mode == "ppm":
+                    assert L.yuv420_write_ppm_fd(devnull, C.byref(img)) == 0
+                L.yuv420_free(C.byref(img))
+                L.vp8_decoded_frame_free(C.byref(d))
+        else:
+            def one(i):
+                h, d = structs[i]
+                assert fn(C.byref(h), C.byref(d), C.byref(img)) == 0
+                if mode == "ppm":
+                    assert L.yuv420_write_ppm_fd(devnull, C.byref(img)) == 0
+                L.yuv420_free(C.byref(img))
     else:
         # port: frames still come from the reference-free product parser (input provider only)
         sys.path.insert(0, str(ROOT))
@@ -55,10 +92,18 @@ def _worker(args):
         pf = P.parse_batch([Path(f).read_bytes() for f in files], threads=1)
         frames = [ParsedAsFrame(pf.kfs[i], pf.frames[i]) for i in range(len(files))]
 
+        datas = [Path(f).read_bytes() for f in files]
+
         def one(i):
-            out = orc.decode_i420(frames[i], mode != "yuv")
+            fr = frames[i]
+            if whole:  # the product parser stands in for m01..m05 when the reference is absent
+                one_pf = P.parse_batch([datas[i]], threads=1)
+                fr = ParsedAsFrame(one_pf.kfs[0], one_pf.frames[0])
+            out = orc.decode_i420(fr, mode != "yuv")
             if mode == "ppm":
-                orc.rgb(out, frames[i].width, frames[i].height)
+                orc.rgb(out, fr.width, fr.height)
+            if whole:
+                one_pf.free()
     one(0)  # warm the caches and the page tables
     t0 = time.perf_counter()
     px = 0
@@ -69,25 +114,27 @@ def _worker(args):
     return px, time.perf_counter() - t0, reps * len(frames)
 
 
-def run(files, mode="yuvf", procs=None, seconds=12.0):
+def run(files, mode="yuvf", procs=None, seconds=12.0, whole=False):
     from vp8fix import Reference
     kind = "reference" if Reference.available() else "port"
-    procs = procs or os.cpu_count() or 1
+    procs = procs or len(os.sched_getaffinity(0)) or 1
     ctx = mp.get_context("spawn")
     with ctx.Pool(procs) as pool:
         # calibrate with one repetition on every core at once (contention included), then size the sample
-        cal = pool.map(_worker, [(files, mode, 1, kind)] * procs)
+        cal = pool.map(_worker, [(files, mode, 1, kind, whole)] * procs)
         per_rep = max(t for _, t, _ in cal)
         reps = max(1, int(seconds / max(per_rep, 1e-3)))
-        res = pool.map(_worker, [(files, mode, reps, kind)] * procs)
+        res = pool.map(_worker, [(files, mode, reps, kind, whole)] * procs)
     px = sum(r[0] for r in res)
     slowest = max(r[1] for r in res)
     frames = sum(r[2] for r in res)
     return {
         "value": px / slowest / 1e6, "unit": "Mpixel/s", "cores": procs, "kind": kind,
+        "flags": ref_library()[1] if kind == "reference" else "gcc -O2 (oracle/Makefile)",
         "frames_per_s": frames / slowest,
         "sample": f"{frames} frames ({reps} passes over {len(files)} distinct inputs on each of {procs} processes), "
-                  f"{slowest:.1f} s, mode -{mode}, token decode excluded",
+                  f"{slowest:.1f} s, mode -{mode}, " + ("whole decoder: .webp bytes in memory -> pixels in memory (m01..m07)" if whole
+                                                         else "token decode excluded"),
     }
 
 
@@ -97,5 +144,6 @@ if __name__ == "__main__":
     ap.add_argument("--mode", default="yuvf", choices=["yuv", "yuvf", "ppm"])
     ap.add_argument("--procs", type=int, default=0)
     ap.add_argument("--seconds", type=float, default=12.0)
+    ap.add_argument("--whole", action="store_true", help="time the whole decoder (.webp bytes -> pixels), not just m06+m07")
     a = ap.parse_args()
-    print(json.dumps(run(a.files, a.mode, a.procs or None, a.seconds)))
+    print(json.dumps(run(a.files, a.mode, a.procs or None, a.seconds, a.whole)))

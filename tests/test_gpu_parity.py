@@ -341,6 +341,76 @@ def test_pipelined_decode_matches_digests(lib, gpu_ctx, golden, parsed_golden):
         gpu_ctx.decode_into(kfs, frs, np.empty(10, np.uint8))
 
 
+@pytest.mark.parametrize("storage", ["pinned", "pageable", "separate"])
+def test_compact_frames_pipelined_decode(lib, gpu_ctx, golden, storage):
+    """vp8_gpu_decode_compact: frames the parser emitted in the compact wire format (no dense arrays anywhere, nothing
+    re-scanned on the host). pinned: one contiguous pinned buffer, read by the copy engine in runs; pageable: the same
+    layout in pageable memory, gathered through staging; separate: one allocation per frame."""
+    from webp_decoder_b200 import parse as P
+    names = sorted(golden)
+    datas = [(GOLDEN / "webp" / n).read_bytes() for n in names]
+    cf = P.parse_batch_compact(datas, threads=4, pinned=(storage == "pinned"), contiguous=(storage != "separate"))
+    frs = cf.frame_list()
+    kfs = [cf.kfs[i] for i in range(cf.n)]
+    h2d0 = gpu_ctx.h2d_bytes
+    for ppm, key, filtered in ((False, "yuvf", True), (False, "yuv", False), (True, "ppm", True)):
+        need = gpu_ctx.decode_bytes(kfs, ppm=ppm)
+        out = lib.PinnedBuffer(need)
+        for chunk in (9, 0):
+            out.array[:] = 0x55
+            offs, sizes = gpu_ctx.decode_compact_into(frs, out.array, filtered=filtered, ppm=ppm, chunk=chunk)
+            bad = [n for n, o, s in zip(names, offs, sizes) if sha(out.array[int(o):int(o) + int(s)]) != golden[n][key]]
+            assert not bad, (storage, key, chunk, len(bad), bad[:4])
+        out.close()
+    assert gpu_ctx.h2d_bytes > h2d0
+    # a frame that is not standalone / inconsistent is refused
+    broken = P.CompactFrame.from_buffer_copy(frs[0])
+    broken.bytes += 32
+    with pytest.raises(OSError):
+        gpu_ctx.decode_compact_into([broken], np.empty(1 << 20, np.uint8))
+    cf.free()
+
+
+@pytest.mark.parametrize("threads,chunk", [(1, 5), (3, 16), (0, 0)])
+def test_webp_bytes_to_pixels_in_one_call(lib, gpu_ctx, golden, threads, chunk):
+    """vp8_gpu_decode_webp: .webp bytes in, -yuv/-yuvf/-ppm bytes out; host threads parse chunk k straight into the pinned
+    arena while the GPU works on the chunks before it. Same bytes as the reference decoder's files."""
+    names = sorted(golden)
+    files = lib.WebpFiles([(GOLDEN / "webp" / n).read_bytes() for n in names])
+    gpu_ctx.set_transport(True, threads)
+    try:
+        for ppm, key, filtered in ((False, "yuvf", True), (False, "yuv", False), (True, "ppm", True)):
+            need = gpu_ctx.decode_webp_bytes(files, ppm=ppm)
+            out = lib.PinnedBuffer(need)
+            out.array[:] = 0x33
+            offs, sizes = gpu_ctx.decode_webp_into(files, out.array, filtered=filtered, ppm=ppm, chunk=chunk)
+            bad = [n for n, o, s in zip(names, offs, sizes) if sha(out.array[int(o):int(o) + int(s)]) != golden[n][key]]
+            assert not bad, (key, len(bad), bad[:4])
+            out.close()
+        prof = gpu_ctx.last_call_profile()
+        assert prof["total_ms"] > 0 and prof["host_work_ms"] > 0
+    finally:
+        gpu_ctx.set_transport(True, 0)
+    # a broken file fails the whole call with the parser's errno
+    junk = lib.WebpFiles([(GOLDEN / "webp" / names[0]).read_bytes(), b"RIFF\x04\x00\x00\x00WEBP"])
+    assert gpu_ctx.decode_webp_bytes(junk) == 0
+    with pytest.raises(OSError):
+        gpu_ctx.decode_webp_into(junk, np.empty(1 << 20, np.uint8))
+
+
+def test_host_binding_reports_local_cpus(gpu_ctx):
+    """vp8_gpu_bind_host: the GPU's local CPU list from sysfs (0 = topology unreadable: nothing changed)."""
+    import os
+    before = os.sched_getaffinity(0)
+    try:
+        n = gpu_ctx.bind_host(0, 1)
+        assert n >= 0
+        if n:
+            assert len(os.sched_getaffinity(0)) == n
+    finally:
+        os.sched_setaffinity(0, before)
+
+
 @pytest.mark.parametrize("chunk", [1, 2, 5, 16, 1000])
 def test_pipelined_chunk_schedule_and_arena_granules(gpu_ctx, oracle, chunk):
     """The pipelined call ramps its chunk sizes (chunk/4, chunk/4, chunk/2, chunk ..., short last chunk) and several

@@ -146,3 +146,69 @@ def test_rgb_tile_arithmetic_on_the_host(tmp_path):
                     "-loracle", f"-Wl,-rpath,{root / 'oracle'}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("ok "), out.stdout + out.stderr
+
+
+def _dense_to_compact(pf, i):
+    """What the compact wire format of parsed frame i must hold, from its dense arrays (numpy restatement of
+    include/vp8_parse.h: mask bit b = block b non-zero; 0..15 luma, 16..19 U, 20..23 V, 24 Y2; blocks in bit order)."""
+    mb = pf.frames[i].mb_total
+    blocks = np.concatenate([pf.array(i, "coeff_y").reshape(mb, 16, 16), pf.array(i, "coeff_u").reshape(mb, 4, 16),
+                             pf.array(i, "coeff_v").reshape(mb, 4, 16), pf.array(i, "coeff_y2").reshape(mb, 1, 16)], axis=1)
+    nz = (blocks != 0).any(axis=2)
+    mask = (nz.astype(np.uint64) << np.arange(25, dtype=np.uint64)).sum(axis=1).astype(np.uint32)
+    counts = nz.sum(axis=1)
+    first = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.uint32)
+    return mask, first, blocks[nz]
+
+
+@pytest.mark.parametrize("contiguous", [False, True])
+def test_compact_parser_equals_dense_parser(lib, golden, contiguous):
+    """vp8_parse_webp_compact / vp8_parse_batch_compact emit the wire format directly while decoding tokens; it must say
+    exactly what compacting the dense arrays of the same file says (which the GPU tests pin against the reference), and
+    carry the same scalars and modes."""
+    from webp_decoder_b200 import parse as P
+    from vp8fix import GOLDEN
+    names = sorted(golden)[::3]
+    datas = [(GOLDEN / "webp" / n).read_bytes() for n in names]
+    pf = P.parse_batch(datas, threads=4)
+    cf = P.parse_batch_compact(datas, threads=4, contiguous=contiguous)
+    scalars = ["mb_cols", "mb_rows", "mb_total", "q_index", "y1_dc_delta_q", "y2_dc_delta_q", "y2_ac_delta_q", "uv_dc_delta_q", "uv_ac_delta_q",
+               "segmentation_enabled", "segmentation_abs", "lf_use_simple", "lf_level", "lf_sharpness", "lf_delta_enabled"]
+    prev_end = None
+    for i, n in enumerate(names):
+        d, c = pf.frames[i], cf.frames[i]
+        for s in scalars:
+            assert getattr(d, s) == getattr(c.f, s), (n, s)
+        for s in ("seg_quant_idx", "seg_lf_level", "lf_ref_delta", "lf_mode_delta"):
+            assert list(getattr(d, s)) == list(getattr(c.f, s)), (n, s)
+        assert (c.width, c.height) == (pf.kfs[i].width, pf.kfs[i].height) == (cf.kfs[i].width, cf.kfs[i].height)
+        mb = d.mb_total
+        for name, per in (("ymode", 1), ("uv_mode", 1), ("segment_id", 1), ("has_coeff", 1), ("bmode", 16)):
+            got = np.ctypeslib.as_array(getattr(c.f, name), shape=(mb * per,))
+            assert np.array_equal(got, pf.array(i, name)), (n, name)
+        mask, first, blocks = cf.head(i)
+        wmask, wfirst, wblocks = _dense_to_compact(pf, i)
+        assert np.array_equal(mask, wmask), n
+        assert np.array_equal(first, wfirst), n
+        assert c.n_blocks == len(wblocks) and np.array_equal(blocks, wblocks), n
+        assert c.bytes == (28 * mb + 31) // 32 * 32 + 32 * c.n_blocks and c.head_off == 0
+        if contiguous:  # back to back in index order, 256-byte aligned: one transfer per chunk
+            assert c.base % 256 == 0 and (prev_end is None or c.base == prev_end), n
+            prev_end = c.base + (c.bytes + 255) // 256 * 256
+    if contiguous:
+        assert cf.used == prev_end - cf.frames[0].base
+    # replication gives every copy its own bytes and self-consistent pointers
+    rep = P.parse_batch_compact(datas[:3], threads=2, contiguous=True, replicate=3)
+    for k in range(9):
+        m0, f0, b0 = cf.head(k % 3)
+        m1, f1, b1 = rep.head(k)
+        assert np.array_equal(m0, m1) and np.array_equal(f0, f1) and np.array_equal(b0, b1)
+        assert rep.frames[k].f.ymode and C.addressof(rep.frames[k].f.ymode.contents) == rep.frames[k].base + 8 * rep.frames[k].f.mb_total
+    assert len({rep.frames[k].base for k in range(9)}) == 9
+    pf.free()
+
+
+def test_compact_parser_rejects_what_the_dense_one_rejects(lib):
+    from webp_decoder_b200 import parse as P
+    with pytest.raises(OSError):
+        P.parse_batch_compact([b"RIFF\x04\x00\x00\x00WEBP"], threads=1)

@@ -304,8 +304,8 @@ class Reference(Checker):
     def available():
         return (REF_DIR / "libref_decode.so").exists()
 
-    def __init__(self):
-        L = self.lib = C.CDLL(str(REF_DIR / "libref_decode.so"))
+    def __init__(self, lib_path=None):
+        L = self.lib = C.CDLL(str(lib_path or REF_DIR / "libref_decode.so"))
         for fn in ("vp8_reconstruct_keyframe_yuv", "vp8_reconstruct_keyframe_yuv_filtered"):
             getattr(L, fn).argtypes = [C.POINTER(KeyFrameHeader), C.POINTER(DecodedFrame), C.POINTER(Yuv420Image)]
         L.vp8_loopfilter_apply_keyframe.argtypes = [C.POINTER(Yuv420Image), C.POINTER(DecodedFrame)]

@@ -40,10 +40,11 @@ EXPORTS = [
     "vp8_gpu_filter", "vp8_gpu_rgb", "vp8_gpu_run", "vp8_gpu_i420_bytes", "vp8_gpu_ppm_bytes",
     "vp8_gpu_download_i420", "vp8_gpu_download_ppm", "vp8_gpu_download_images", "vp8_gpu_download_padded",
     "vp8_gpu_batch_size", "vp8_gpu_launch_count", "vp8_gpu_h2d_bytes", "vp8_gpu_d2h_bytes",
-    "vp8_gpu_last_launch_config", "vp8_gpu_frame_params", "vp8_gpu_kernel_time",
+    "vp8_gpu_last_launch_config", "vp8_gpu_frame_params", "vp8_gpu_kernel_time", "vp8_gpu_rgb_time",
     "vp8_gpu_decode_i420", "vp8_gpu_decode_ppm", "vp8_gpu_decode_bytes", "vp8_gpu_set_kernel",
     "vp8_gpu_png_bound", "vp8_gpu_png_frame", "vp8_gpu_set_transport",
     "vp8_gpu_set_cluster", "vp8_gpu_last_cluster", "vp8_gpu_last_groups", "vp8_gpu_last_segments",
+    "vp8_gpu_decode_compact", "vp8_gpu_decode_webp", "vp8_gpu_decode_webp_bytes", "vp8_gpu_last_call_profile", "vp8_gpu_bind_host",
 ]
 
 _lib = None
@@ -102,12 +103,19 @@ def load_library() -> C.CDLL:
         getattr(L, fn).restype = C.c_uint64
     L.vp8_gpu_last_launch_config.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.vp8_gpu_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.vp8_gpu_rgb_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.vp8_gpu_frame_params.argtypes = [vp, vp, vp]
     L.vp8_gpu_frame_params.restype = None
     L.vp8_gpu_decode_i420.argtypes = [vp, pp, pp, C.c_int, C.c_int, vp, sz, vp, vp, C.c_int]
     L.vp8_gpu_decode_ppm.argtypes = [vp, pp, pp, C.c_int, vp, sz, vp, vp, C.c_int]
     L.vp8_gpu_decode_bytes.argtypes = [pp, C.c_int, C.c_int]
     L.vp8_gpu_decode_bytes.restype = sz
+    L.vp8_gpu_decode_compact.argtypes = [vp, pp, C.c_int, C.c_int, C.c_int, vp, sz, vp, vp, C.c_int]
+    L.vp8_gpu_decode_webp.argtypes = [vp, pp, vp, C.c_int, C.c_int, C.c_int, vp, sz, vp, vp, C.c_int]
+    L.vp8_gpu_decode_webp_bytes.argtypes = [pp, vp, C.c_int, C.c_int]
+    L.vp8_gpu_decode_webp_bytes.restype = sz
+    L.vp8_gpu_last_call_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.vp8_gpu_bind_host.argtypes = [vp, C.c_int, C.c_int]
     L.yuv420_alloc.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.yuv420_free.argtypes = [vp]
     L.yuv420_free.restype = None
@@ -165,6 +173,16 @@ class PinnedBuffer:
             self.close()
         except Exception:
             pass
+
+
+class WebpFiles:
+    """n .webp byte strings laid out for the C-ABI (pointer and size arrays); keeps the bytes alive."""
+
+    def __init__(self, datas):
+        self.n = len(datas)
+        self._bufs = [(C.c_uint8 * len(d)).from_buffer_copy(d) for d in datas]
+        self.ptrs = (C.c_void_p * self.n)(*[C.addressof(b) for b in self._bufs])
+        self.sizes = (C.c_size_t * self.n)(*[len(d) for d in datas])
 
 
 class Batch:
@@ -311,6 +329,35 @@ class Context:
         _check(rc, "vp8_gpu_decode")
         return offs, sizes
 
+    def decode_compact_into(self, frames, out: np.ndarray, filtered: bool = True, ppm: bool = False, chunk: int = 0):
+        """vp8_gpu_decode_compact: frames = list of parse.CompactFrame structs (vp8_parse_*_compact output)."""
+        n = len(frames)
+        fp = (C.c_void_p * n)(*[_addr(f) for f in frames])
+        offs, sizes = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        _check(self._L.vp8_gpu_decode_compact(self._h, fp, n, int(bool(filtered)), int(bool(ppm)), out.ctypes.data, out.nbytes,
+                                              offs.ctypes.data, sizes.ctypes.data, chunk), "vp8_gpu_decode_compact")
+        return offs, sizes
+
+    def decode_webp_into(self, files: "WebpFiles", out: np.ndarray, filtered: bool = True, ppm: bool = False, chunk: int = 0):
+        """vp8_gpu_decode_webp: .webp bytes in (a WebpFiles pack), -yuv/-yuvf or -ppm bytes out; host threads parse
+        chunk k while the GPU works on the chunks before it."""
+        offs, sizes = np.zeros(files.n, np.uint64), np.zeros(files.n, np.uint64)
+        _check(self._L.vp8_gpu_decode_webp(self._h, files.ptrs, files.sizes, files.n, int(bool(filtered)), int(bool(ppm)), out.ctypes.data,
+                                           out.nbytes, offs.ctypes.data, sizes.ctypes.data, chunk), "vp8_gpu_decode_webp")
+        return offs, sizes
+
+    def decode_webp_bytes(self, files: "WebpFiles", ppm: bool = False) -> int:
+        return int(self._L.vp8_gpu_decode_webp_bytes(files.ptrs, files.sizes, files.n, int(bool(ppm))))
+
+    def last_call_profile(self):
+        t, h, w = C.c_double(), C.c_double(), C.c_double()
+        _check(self._L.vp8_gpu_last_call_profile(self._h, C.byref(t), C.byref(h), C.byref(w)), "vp8_gpu_last_call_profile")
+        return {"total_ms": t.value, "host_work_ms": h.value, "wait_ms": w.value}
+
+    def bind_host(self, index: int = 0, share: int = 1) -> int:
+        """Bind this thread (and the context's future worker threads) to the CPUs local to the GPU."""
+        return int(self._L.vp8_gpu_bind_host(self._h, index, share))
+
     # ---- convenience -------------------------------------------------------------------------------------
     def decode_i420(self, kfs, frames, filtered: bool = True):
         """List of tight I420 byte arrays, one per frame (what `decoder -yuv` / `-yuvf` writes)."""
@@ -350,6 +397,12 @@ class Context:
         """(total_ms, launches) of the wavefront launches since the previous call, timed with CUDA events."""
         ms, n = C.c_double(), C.c_int()
         _check(self._L.vp8_gpu_kernel_time(self._h, C.byref(ms), C.byref(n)), "vp8_gpu_kernel_time")
+        return ms.value, n.value
+
+    def rgb_time(self):
+        """(total_ms, launches) of the m08 RGB launches since the previous call."""
+        ms, n = C.c_double(), C.c_int()
+        _check(self._L.vp8_gpu_rgb_time(self._h, C.byref(ms), C.byref(n)), "vp8_gpu_rgb_time")
         return ms.value, n.value
 
     def last_launch_config(self):

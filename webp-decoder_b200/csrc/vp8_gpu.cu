@@ -4,7 +4,9 @@
 // factors and loop-filter levels per segment) and file framing (PPM header, PNG container). Every pixel is
 // produced by the kernels in vp8_pairs.cu and vp8_rgb.cu; there is no CPU fallback.
 #include <cuda_runtime.h>
+#include <ctype.h>
 #include <errno.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,6 +28,7 @@
 
 #include "../../include/vp8_gpu.h"
 #include "vp8_dev.h"
+#include "vp8_parse_internal.h"
 
 namespace {
 
@@ -151,6 +154,7 @@ struct vp8_gpu_ctx {
 	int last_warps = 0, last_grid = 0, last_smem = 0, last_segments = 0;
 	// device-side duration of every wavefront launch since the last vp8_gpu_kernel_time() query
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed; // recorded, not yet read
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed_rgb; // same for the m08 launches
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spare;
 	cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr}; // chunk pipeline of vp8_gpu_decode_*
 	cudaEvent_t pipe_ev = nullptr;
@@ -1043,7 +1047,7 @@ void vp8_gpu_destroy(vp8_gpu_ctx* c) {
 		if (c->bounce[i]) cudaFreeHost(c->bounce[i]);
 		if (c->bounce_ev[i]) cudaEventDestroy(c->bounce_ev[i]);
 	}
-	for (auto* v : {&c->timed, &c->spare})
+	for (auto* v : {&c->timed, &c->timed_rgb, &c->spare})
 		for (auto& ev : *v) {
 			cudaEventDestroy(ev.first);
 			cudaEventDestroy(ev.second);
@@ -1206,9 +1210,24 @@ int vp8_gpu_rgb(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
 		tiles[i] = vp8_rgb_tiles(m.width, m.height);
 	}
 	if (push_table(c, b->d_rgbdesc, h.data(), sizeof(Vp8RgbDesc) * b->n, b->stream)) return -1;
+	std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+	if (!c->spare.empty()) {
+		ev = c->spare.back();
+		c->spare.pop_back();
+	} else {
+		CU(cudaEventCreate(&ev.first));
+		CU(cudaEventCreate(&ev.second));
+	}
+	CU(cudaEventRecord(ev.first, b->stream));
 	const int rc = vp8_launch_rgb(b->d_rgbdesc, b->n, tiles.data(), b->stream);
+	CU(cudaEventRecord(ev.second, b->stream));
+	c->timed_rgb.push_back(ev);
+	if (c->timed_rgb.size() > 4096) {
+		c->spare.push_back(c->timed_rgb.front());
+		c->timed_rgb.erase(c->timed_rgb.begin());
+	}
 	if (rc) return fail(EIO, "rgb launch", (cudaError_t)rc);
-	c->launches++;
+	c->launches += (b->n + 65534) / 65535;
 	b->have_rgb = true;
 	return 0;
 }
@@ -1305,26 +1324,14 @@ int vp8_gpu_download_images(vp8_gpu_ctx* c, vp8_gpu_batch* b, Yuv420Image* out) 
 
 // ------------------------------------------------------------------------------------------------ compact transport
 // Most 4x4 blocks of a real frame carry no coefficient at all. The dense arrays of Vp8DecodedFrame (800 bytes per
-// macroblock) are what the host->device link is bound by, so the pipelined path ships a compact frame instead:
-//   [mb_mask u32 x mb][mb_first u32 x mb][ymode][uv_mode][segment_id][has_coeff][bmode 16 x mb][pad to 32][packed blocks]
-// mb_mask bit b = block b present (0..15 luma, 16..19 U, 20..23 V, 24 Y2); mb_first = index of the macroblock's first packed
-// 32-byte block. vp8_mb_pairs reads this layout directly, so there is no expansion pass and HBM reads shrink as well.
-struct CompactLayout {
-	size_t o_mask, o_first, o_ymode, o_uv, o_seg, o_hc, o_bmode, o_packed, worst;
-};
-CompactLayout compact_layout(size_t mb) {
-	CompactLayout L;
-	L.o_mask = 0;
-	L.o_first = 4 * mb;
-	L.o_ymode = 8 * mb;
-	L.o_uv = 9 * mb;
-	L.o_seg = 10 * mb;
-	L.o_hc = 11 * mb;
-	L.o_bmode = 12 * mb;
-	L.o_packed = align_up(28 * mb, 32);
-	L.worst = align_up(L.o_packed + 800 * mb);
-	return L;
-}
+// macroblock) are what the host->device link is bound by, so the pipelined path ships compact frames instead (layout:
+// vp8_parse_internal.h). vp8_mb_pairs / vp8_mb_lockstep read that layout directly, so there is no expansion pass and
+// HBM reads shrink as well. Three producers fill a chunk's arena:
+//   (a) compact_frame(): host threads drop the all-zero blocks of dense Vp8DecodedFrames (the reference's contract);
+//   (b) frames the parser already emitted compact (vp8_parse_webp_compact): moved as they are, no host pass at all
+//       when they sit in pinned memory;
+//   (c) .webp bytes: host threads parse straight into the pinned arena (vp8_parse_webp_shared).
+using vp8c::kGranule;
 
 // One macroblock: appends its non-zero 4x4 blocks (32 bytes each) at out, returns the presence mask; *bytes = appended.
 // Branch-free: every block is stored at the running position and the position only moves on when it was non-zero, so
@@ -1387,21 +1394,15 @@ const bool g_nt_stores = !(getenv("VP8_GPU_NT_STORES") && atoi(getenv("VP8_GPU_N
 const bool g_have_avx2 = false;
 #endif
 
-// A chunk's frames are compacted by several host threads into ONE arena, which then crosses the link as one transfer
-// (64 per-frame transfers took 3x as long while the device->host engine was busy: profiles/README.md). Threads take
-// space from a shared cursor: the frame's fixed-size head in one piece, the packed blocks in 64 KiB granules, so no
+// (a) A chunk's dense frames are compacted by several host threads into ONE arena, which then crosses the link as one
+// transfer (64 per-frame transfers took 3x as long while the device->host engine was busy: profiles/README.md). Threads
+// take space from a shared cursor: the frame's fixed-size head in one piece, the packed blocks in 64 KiB granules, so no
 // thread needs to know another frame's size. mb_first counts 32-byte blocks from the start of the ARENA, the kernel's
 // packed-block base is the arena itself, and a macroblock's blocks (at most 800 bytes) never straddle a granule.
-constexpr size_t kGranule = 64 << 10;
-size_t compact_bound(size_t mb) {
-	const CompactLayout L = compact_layout(mb);
-	return L.o_packed + (800 * mb / (kGranule - 800) + 2) * kGranule;
-}
-
-// Returns the arena offset of the frame's head ([mb_mask][mb_first][modes...], CompactLayout without the packed part).
+// Returns the arena offset of the frame's head.
 size_t compact_frame(const Vp8DecodedFrame* f, uint8_t* arena, std::atomic<size_t>& cursor) {
 	const size_t mb = (size_t)f->mb_cols * f->mb_rows;
-	const CompactLayout L = compact_layout(mb);
+	const vp8c::Layout L = vp8c::layout(mb);
 	const size_t head = cursor.fetch_add(L.o_packed);
 	uint8_t* dst = arena + head;
 	uint32_t* mask = reinterpret_cast<uint32_t*>(dst + L.o_mask);
@@ -1440,94 +1441,117 @@ size_t compact_frame(const Vp8DecodedFrame* f, uint8_t* arena, std::atomic<size_
 	return head;
 }
 
-// A batch whose input arena holds compact frames: compacted by host threads into the pinned staging slot, then one
-// transfer of the bytes in use.
-int batch_create_compact(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* fr, int n, int slot,
-                         cudaStream_t st, vp8_gpu_batch** out) {
+// What the pipeline needs to know about frame i before its chunk is built.
+struct FrameGeom {
+	uint32_t width, height;
+};
+
+// Shell of a batch whose input arena holds compact frames: geometry, output layout, nothing uploaded yet.
+vp8_gpu_batch* compact_batch_shell(const FrameGeom* g, int n, cudaStream_t st) {
 	vp8_gpu_batch* b = new (std::nothrow) vp8_gpu_batch;
-	if (!b) return fail(ENOMEM, "batch");
+	if (!b) return nullptr;
 	b->n = n;
 	b->stream = st;
 	b->meta.resize(n);
-	size_t in = 0, tight = 0, rgb = 0;
+	size_t tight = 0, rgb = 0;
 	for (int i = 0; i < n; i++) {
 		FrameMeta& m = b->meta[i];
-		const Vp8DecodedFrame* f = fr[i];
-		m.width = kf[i]->width;
-		m.height = kf[i]->height;
-		m.mb_cols = f->mb_cols;
-		m.mb_rows = f->mb_rows;
-		const size_t mb = (size_t)m.mb_cols * m.mb_rows;
-		m.has_seg = f->segmentation_enabled && f->segment_id;
-		m.has_hc = f->has_coeff != nullptr;
+		m.width = g[i].width;
+		m.height = g[i].height;
+		m.mb_cols = (m.width + 15) / 16;
+		m.mb_rows = (m.height + 15) / 16;
 		m.compact = true;
-		in += compact_bound(mb);
 		const size_t cw = (m.width + 1) / 2, ch = (m.height + 1) / 2;
 		m.tight_off = tight;
 		tight += align_up((size_t)m.width * m.height + 2 * cw * ch);
 		m.pad_off[0] = m.pad_off[1] = m.pad_off[2] = 0;
 		m.rgb_off = rgb;
 		rgb += align_up(kPpmSlot + (size_t)m.width * m.height * 3);
-		frame_params(f, m.dq, m.lf);
-		m.lf_simple = f->lf_use_simple;
-		m.any_filter = false;
-		for (int s = 0; s < (m.has_seg ? 4 : 1); s++)
-			for (int k = 0; k < 2; k++) m.any_filter |= m.lf[s][k][0] != 0;
 		b->max_mb_cols = std::max<int>(b->max_mb_cols, m.mb_cols);
 	}
-	if (in / 32 > 0xffffffffull) {
-		delete b;
-		return fail(EINVAL, "compact chunk exceeds the 32-bit block index; use a smaller chunk");
-	}
-	b->in_bytes = in;
 	b->tight_bytes = tight;
 	b->pad_bytes = 0;
 	b->rgb_bytes = rgb;
-	// pinned staging slot, grown on demand
-	if (c->cstage_bytes[slot] < in) {
-		if (c->cstage[slot]) cudaFreeHost(c->cstage[slot]);
-		c->cstage[slot] = nullptr;
-		c->cstage_bytes[slot] = 0;
-		cudaError_t e = cudaHostAlloc((void**)&c->cstage[slot], in, cudaHostAllocDefault);
-		if (e != cudaSuccess) {
-			delete b;
-			return fail(ENOMEM, "pinned staging for compact transport", e);
-		}
-		c->cstage_bytes[slot] = in;
-	}
-	if (dev_alloc(c, in, (void**)&b->d_in) || dev_alloc(c, sizeof(Vp8ImgDesc) * n, (void**)&b->d_desc)) {
-		batch_destroy(c, b);
-		return -1;
-	}
-	// compaction on host threads, one frame per thread at a time
-	const auto t_c0 = std::chrono::steady_clock::now();
-	uint8_t* stage = c->cstage[slot];
-	std::atomic<size_t> cursor{0};
+	return b;
+}
+
+// Per-frame parameters of a compact batch entry from the frame's scalars; head / packed = offsets inside the device arena.
+void compact_meta(FrameMeta& m, const Vp8DecodedFrame* f, size_t head, size_t packed) {
+	const vp8c::Layout L = vp8c::layout((size_t)m.mb_cols * m.mb_rows);
+	m.has_seg = f->segmentation_enabled != 0;
+	m.has_hc = true;
+	m.in_off[0] = packed;            // packed blocks: mb_first counts from here
+	m.in_off[1] = head + L.o_mask;   // mb_mask
+	m.in_off[2] = head + L.o_first;  // mb_first
+	m.in_off[3] = 0;                 // (coeff_y2 slot unused)
+	m.in_off[4] = head + L.o_bmode;
+	m.in_off[5] = head + L.o_ymode;
+	m.in_off[6] = head + L.o_uv;
+	m.in_off[7] = head + L.o_seg;
+	m.in_off[8] = head + L.o_hc;
+	frame_params(f, m.dq, m.lf);
+	m.lf_simple = f->lf_use_simple;
+	m.any_filter = false;
+	for (int s = 0; s < (m.has_seg ? 4 : 1); s++)
+		for (int k = 0; k < 2; k++) m.any_filter |= m.lf[s][k][0] != 0;
+}
+
+int stage_reserve(vp8_gpu_ctx* c, int slot, size_t bytes) {
+	if (c->cstage_bytes[slot] >= bytes) return 0;
+	if (c->cstage[slot]) cudaFreeHost(c->cstage[slot]);
+	c->cstage[slot] = nullptr;
+	c->cstage_bytes[slot] = 0;
+	cudaError_t e = cudaHostAlloc((void**)&c->cstage[slot], bytes, cudaHostAllocDefault);
+	if (e != cudaSuccess) return fail(ENOMEM, "pinned staging for compact transport", e);
+	c->cstage_bytes[slot] = bytes;
+	return 0;
+}
+
+int pool_threads(vp8_gpu_ctx* c, int jobs) {
 	int threads = c->host_threads > 0 ? c->host_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
-	threads = std::min(threads, n);
-	std::atomic<int> next{0};
-	auto work = [&]() {
-		for (int i; (i = next.fetch_add(1)) < n;) {
-			const size_t head = compact_frame(fr[i], stage, cursor);
-			const CompactLayout L = compact_layout((size_t)fr[i]->mb_cols * fr[i]->mb_rows);
-			FrameMeta& m = b->meta[i];
-			m.in_off[0] = 0;                 // packed blocks: mb_first indexes the whole arena
-			m.in_off[1] = head + L.o_mask;   // mb_mask
-			m.in_off[2] = head + L.o_first;  // mb_first
-			m.in_off[3] = 0;                 // (coeff_y2 slot unused)
-			m.in_off[4] = head + L.o_bmode;
-			m.in_off[5] = head + L.o_ymode;
-			m.in_off[6] = head + L.o_uv;
-			m.in_off[7] = head + L.o_seg;
-			m.in_off[8] = head + L.o_hc;
-		}
-	};
+	threads = std::max(1, std::min(threads, jobs));
 	if (threads > 1 && (!c->pool || c->pool->size() < threads - 1)) {
 		delete c->pool;
 		c->pool = new WorkerPool(threads - 1);
 	}
+	return threads;
+}
+
+void pool_run(vp8_gpu_ctx* c, int threads, const std::function<void()>& work) {
 	if (threads > 1) c->pool->run(work, threads - 1);
 	else work();
+}
+
+// (a) dense frames in: compacted by host threads into the pinned staging slot, then one transfer of the bytes in use.
+int batch_create_compact(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* fr, int n, int slot,
+                         cudaStream_t st, vp8_gpu_batch** out) {
+	std::vector<FrameGeom> g(n);
+	size_t in = 0;
+	for (int i = 0; i < n; i++) {
+		g[i] = {kf[i]->width, kf[i]->height};
+		in += vp8c::shared_bound((size_t)fr[i]->mb_cols * fr[i]->mb_rows);
+	}
+	if (in / 32 > 0xffffffffull) return fail(EINVAL, "compact chunk exceeds the 32-bit block index; use a smaller chunk");
+	vp8_gpu_batch* b = compact_batch_shell(g.data(), n, st);
+	if (!b) return fail(ENOMEM, "batch");
+	b->in_bytes = in;
+	if (stage_reserve(c, slot, in) || dev_alloc(c, in, (void**)&b->d_in) || dev_alloc(c, sizeof(Vp8ImgDesc) * n, (void**)&b->d_desc)) {
+		batch_destroy(c, b);
+		return -1;
+	}
+	const auto t_c0 = std::chrono::steady_clock::now();
+	uint8_t* stage = c->cstage[slot];
+	std::atomic<size_t> cursor{0};
+	std::atomic<int> next{0};
+	const int threads = pool_threads(c, n);
+	pool_run(c, threads, [&]() {
+		for (int i; (i = next.fetch_add(1)) < n;) {
+			const size_t head = compact_frame(fr[i], stage, cursor);
+			compact_meta(b->meta[i], fr[i], head, 0);
+			b->meta[i].has_seg = fr[i]->segmentation_enabled && fr[i]->segment_id;
+			b->meta[i].has_hc = fr[i]->has_coeff != nullptr;
+		}
+	});
 	c->trace_compact_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_c0).count();
 	const size_t used = cursor.load();
 	cudaError_t e = cudaMemcpyAsync(b->d_in, stage, used, cudaMemcpyHostToDevice, st);
@@ -1540,20 +1564,131 @@ int batch_create_compact(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, con
 	return 0;
 }
 
-// Chunked pipeline: chunk k's host->device copies, kernels and device->host copy run on internal stream k % 3, so the
+int validate_compact(const Vp8CompactFrame* f) {
+	if (!f || !f->base || !f->bytes || !f->width || !f->height) return fail(EINVAL, "not a standalone compact frame");
+	const size_t mb = (size_t)f->f.mb_cols * f->f.mb_rows;
+	if (f->f.mb_cols != (f->width + 15u) / 16u || f->f.mb_rows != (f->height + 15u) / 16u || f->f.mb_cols > 1024 || f->f.mb_rows > 1024)
+		return fail(EINVAL, "macroblock grid does not match the frame size");
+	const vp8c::Layout L = vp8c::layout(mb);
+	if (f->packed_off != f->head_off + L.o_packed || f->bytes != L.o_packed + (size_t)32 * f->n_blocks || ((uintptr_t)(f->base + f->head_off) & 31))
+		return fail(EINVAL, "compact frame layout");
+	return 0;
+}
+
+// (b) frames that are compact already. Device layout = the frames back to back, 256-byte aligned. Runs of frames that are
+// back to back in PINNED host memory as well (vp8_parse_batch_compact lays them out like that) go with one transfer per run
+// and no host pass; anything else is gathered into the pinned staging slot by the worker threads first.
+int batch_create_precompact(vp8_gpu_ctx* c, const Vp8CompactFrame* const* fr, int n, int slot, cudaStream_t st, vp8_gpu_batch** out) {
+	std::vector<FrameGeom> g(n);
+	std::vector<size_t> off(n + 1, 0);
+	bool direct = true;
+	for (int i = 0; i < n; i++) {
+		g[i] = {fr[i]->width, fr[i]->height};
+		off[i + 1] = off[i] + align_up(fr[i]->bytes);
+		const uint8_t* p = fr[i]->base + fr[i]->head_off;
+		direct = direct && is_pinned(p) && is_pinned(p + fr[i]->bytes - 1);
+	}
+	const size_t in = off[n];
+	if (in / 32 > 0xffffffffull) return fail(EINVAL, "compact chunk exceeds the 32-bit block index; use a smaller chunk");
+	vp8_gpu_batch* b = compact_batch_shell(g.data(), n, st);
+	if (!b) return fail(ENOMEM, "batch");
+	b->in_bytes = in;
+	if ((!direct && stage_reserve(c, slot, in)) || dev_alloc(c, in, (void**)&b->d_in) || dev_alloc(c, sizeof(Vp8ImgDesc) * n, (void**)&b->d_desc)) {
+		batch_destroy(c, b);
+		return -1;
+	}
+	for (int i = 0; i < n; i++) compact_meta(b->meta[i], &fr[i]->f, off[i], off[i] + vp8c::layout((size_t)fr[i]->f.mb_cols * fr[i]->f.mb_rows).o_packed);
+	cudaError_t e = cudaSuccess;
+	if (direct) {
+		for (int i = 0; i < n && e == cudaSuccess;) {
+			const uint8_t* src = fr[i]->base + fr[i]->head_off;
+			int j = i + 1;
+			while (j < n && fr[j]->base + fr[j]->head_off == src + (off[j] - off[i])) j++;
+			const size_t bytes = off[j - 1] - off[i] + fr[j - 1]->bytes;
+			e = cudaMemcpyAsync(b->d_in + off[i], src, bytes, cudaMemcpyHostToDevice, st);
+			c->h2d += bytes;
+			i = j;
+		}
+	} else {
+		const auto t_c0 = std::chrono::steady_clock::now();
+		uint8_t* stage = c->cstage[slot];
+		std::atomic<int> next{0};
+		const int threads = pool_threads(c, n);
+		pool_run(c, threads, [&]() {
+			for (int i; (i = next.fetch_add(1)) < n;) memcpy(stage + off[i], fr[i]->base + fr[i]->head_off, fr[i]->bytes);
+		});
+		c->trace_compact_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_c0).count();
+		const size_t used = off[n - 1] + fr[n - 1]->bytes;
+		e = cudaMemcpyAsync(b->d_in, stage, used, cudaMemcpyHostToDevice, st);
+		c->h2d += used;
+	}
+	if (e != cudaSuccess) {
+		batch_destroy(c, b);
+		return fail(EIO, "compact chunk upload", e);
+	}
+	*out = b;
+	return 0;
+}
+
+// (c) .webp bytes in: the worker threads parse straight into the pinned staging slot (one image per thread at a time).
+int batch_create_webp(vp8_gpu_ctx* c, const uint8_t* const* files, const size_t* sizes, const FrameGeom* g, int n, int slot, cudaStream_t st,
+                      vp8_gpu_batch** out) {
+	size_t in = 0;
+	for (int i = 0; i < n; i++) in += vp8c::shared_bound((size_t)((g[i].width + 15) / 16) * ((g[i].height + 15) / 16));
+	if (in / 32 > 0xffffffffull) return fail(EINVAL, "compact chunk exceeds the 32-bit block index; use a smaller chunk");
+	vp8_gpu_batch* b = compact_batch_shell(g, n, st);
+	if (!b) return fail(ENOMEM, "batch");
+	b->in_bytes = in;
+	if (stage_reserve(c, slot, in) || dev_alloc(c, in, (void**)&b->d_in) || dev_alloc(c, sizeof(Vp8ImgDesc) * n, (void**)&b->d_desc)) {
+		batch_destroy(c, b);
+		return -1;
+	}
+	const auto t_c0 = std::chrono::steady_clock::now();
+	uint8_t* stage = c->cstage[slot];
+	std::atomic<size_t> cursor{0};
+	std::atomic<int> next{0}, bad{0}, bad_errno{0};
+	const int threads = pool_threads(c, n);
+	pool_run(c, threads, [&]() {
+		for (int i; (i = next.fetch_add(1)) < n;) {
+			Vp8KeyFrameHeader kf;
+			Vp8CompactFrame cf;
+			if (vp8_parse_webp_shared(files[i], sizes[i], &kf, &cf, stage, in, &cursor) || kf.width != g[i].width || kf.height != g[i].height) {
+				if (!bad.fetch_add(1)) bad_errno = errno ? errno : EINVAL;
+				continue;
+			}
+			compact_meta(b->meta[i], &cf.f, cf.head_off, cf.packed_off);
+		}
+	});
+	c->trace_compact_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_c0).count();
+	if (bad.load()) {
+		batch_destroy(c, b);
+		return fail(bad_errno.load(), "a .webp file of the chunk failed to parse");
+	}
+	const size_t used = cursor.load();
+	cudaError_t e = cudaMemcpyAsync(b->d_in, stage, used, cudaMemcpyHostToDevice, st);
+	if (e != cudaSuccess) {
+		batch_destroy(c, b);
+		return fail(EIO, "compact chunk upload", e);
+	}
+	c->h2d += used;
+	*out = b;
+	return 0;
+}
+
+// Chunked pipeline: chunk k's host->device copies, kernels and device->host copy run on internal streams, so the
 // copy engines (one per direction) and the SMs work on different chunks at the same time. Blocking: returns when
 // dst holds every frame. Output layout = the layout of one big batch (frame i at offsets[i], 256-byte aligned).
-static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,
-                            int filtered, bool want_ppm, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk) {
-	if (!c || !kf || !frames || !dst || n <= 0) return fail(EINVAL, "bad arguments");
-	for (int i = 0; i < n; i++)
-		if (validate_frame(kf[i], frames[i], true)) return -1;
+// make_chunk(first, count, staging slot, upload stream, &batch) builds and uploads one chunk.
+using ChunkMaker = std::function<int(int, int, int, cudaStream_t, vp8_gpu_batch**)>;
+
+static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const ChunkMaker& make_chunk, int filtered, bool want_ppm,
+                            uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk) {
 	CU(cudaSetDevice(c->device));
 	if (chunk <= 0) chunk = 64;
 	// global layout
 	std::vector<size_t> off(n + 1, 0);
 	for (int i = 0; i < n; i++) {
-		const size_t w = kf[i]->width, h = kf[i]->height;
+		const size_t w = geom[i].width, h = geom[i].height;
 		off[i + 1] = off[i] + (want_ppm ? align_up(kPpmSlot + w * h * 3) : align_up(w * h + 2 * ((w + 1) / 2) * ((h + 1) / 2)));
 	}
 	if (cap < off[n]) return fail(EINVAL, "destination too small");
@@ -1620,8 +1755,7 @@ static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, 
 		c->trace_retire_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_r0).count();
 		vp8_gpu_batch* b = nullptr;
 		if (timeline) tl_host.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_p0).count());
-		if (c->compact_transport) rc = batch_create_compact(c, kf + first, frames + first, cnt, slot, s_up, &b);
-		else rc = batch_create(c, kf + first, frames + first, cnt, true, &b, s_up, true);
+		rc = make_chunk(first, cnt, slot, s_up, &b);
 		if (rc) break;
 		ch.b = b;
 		mark(s_up);
@@ -1664,14 +1798,15 @@ static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, 
 			cudaEventElapsedTime(&up, tl[0], tl[1 + i]);
 			cudaEventElapsedTime(&run, tl[0], tl[2 + i]);
 			cudaEventElapsedTime(&down, tl[0], tl[3 + i]);
-			fprintf(stderr, "[vp8gpu] chunk %2zu: host starts compaction at %6.1f ms | upload done %6.1f | kernels done %6.1f | download done %6.1f\n",
+			fprintf(stderr, "[vp8gpu] chunk %2zu: host starts on it at %6.1f ms | upload done %6.1f | kernels done %6.1f | download done %6.1f\n",
 			        i / 3, tl_host[i / 3], up, run, down);
 		}
 	}
 	for (auto e : tl) cudaEventDestroy(e);
+	c->trace_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_p0).count();
 	if (getenv("VP8_GPU_TRACE")) {
 		const auto now = std::chrono::steady_clock::now();
-		fprintf(stderr, "[vp8gpu] pipelined call: total %.1f ms, host compaction %.1f ms, waiting on slots/retiring chunks %.1f ms, final drain %.1f ms, "
+		fprintf(stderr, "[vp8gpu] pipelined call: total %.1f ms, host work on chunks (compaction / gather / parse) %.1f ms, waiting on slots/retiring chunks %.1f ms, final drain %.1f ms, "
 		        "%d cudaMalloc + %d cudaFree %.1f ms\n",
 		        std::chrono::duration<double, std::milli>(now - t_p0).count(), c->trace_compact_ms, c->trace_retire_ms,
 		        std::chrono::duration<double, std::milli>(now - t_e0).count(), c->trace_mallocs, c->trace_frees, c->trace_malloc_ms);
@@ -1681,7 +1816,7 @@ static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, 
 		return -1;
 	}
 	for (int i = 0; i < n; i++) {
-		const size_t w = kf[i]->width, h = kf[i]->height;
+		const size_t w = geom[i].width, h = geom[i].height;
 		if (want_ppm) {
 			char hdr[32];
 			const int hl = ppm_header(hdr, (uint32_t)w, (uint32_t)h);
@@ -1696,14 +1831,144 @@ static int decode_pipelined(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, 
 	return 0;
 }
 
+// The reference's contract: dense Vp8DecodedFrames in host memory. Which transport carries them is a host question: the
+// compact one needs every frame's 6.7 MB (1080p) read by host threads, the dense one is pure DMA of three times the
+// bytes. With few host threads per GPU (eight ranks sharing one host) the copy engine wins.
+static int decode_dense(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n, int filtered,
+                        bool want_ppm, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk) {
+	if (!c || !kf || !frames || !dst || n <= 0) return fail(EINVAL, "bad arguments");
+	std::vector<FrameGeom> g(n);
+	for (int i = 0; i < n; i++) {
+		if (validate_frame(kf[i], frames[i], true)) return -1;
+		g[i] = {kf[i]->width, kf[i]->height};
+	}
+	const bool compact = c->compact_transport;
+	return decode_pipelined(
+	    c, g.data(), n,
+	    [&](int first, int cnt, int slot, cudaStream_t s_up, vp8_gpu_batch** out) {
+		    return compact ? batch_create_compact(c, kf + first, frames + first, cnt, slot, s_up, out)
+		                   : batch_create(c, kf + first, frames + first, cnt, true, out, s_up, true);
+	    },
+	    filtered, want_ppm, dst, cap, offsets, sizes, chunk);
+}
+
 int vp8_gpu_decode_i420(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n, int filtered,
                         uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk) {
-	return decode_pipelined(c, kf, frames, n, filtered, false, dst, cap, offsets, sizes, chunk);
+	return decode_dense(c, kf, frames, n, filtered, false, dst, cap, offsets, sizes, chunk);
 }
 
 int vp8_gpu_decode_ppm(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n, uint8_t* dst,
                        size_t cap, size_t* offsets, size_t* sizes, int chunk) {
-	return decode_pipelined(c, kf, frames, n, 1, true, dst, cap, offsets, sizes, chunk);
+	return decode_dense(c, kf, frames, n, 1, true, dst, cap, offsets, sizes, chunk);
+}
+
+int vp8_gpu_decode_compact(vp8_gpu_ctx* c, const Vp8CompactFrame* const* frames, int n, int filtered, int ppm, uint8_t* dst, size_t cap,
+                           size_t* offsets, size_t* sizes, int chunk) {
+	if (!c || !frames || !dst || n <= 0) return fail(EINVAL, "bad arguments");
+	std::vector<FrameGeom> g(n);
+	for (int i = 0; i < n; i++) {
+		if (validate_compact(frames[i])) return -1;
+		g[i] = {frames[i]->width, frames[i]->height};
+	}
+	return decode_pipelined(
+	    c, g.data(), n,
+	    [&](int first, int cnt, int slot, cudaStream_t s_up, vp8_gpu_batch** out) { return batch_create_precompact(c, frames + first, cnt, slot, s_up, out); },
+	    ppm ? 1 : filtered, ppm != 0, dst, cap, offsets, sizes, chunk);
+}
+
+int vp8_gpu_decode_webp(vp8_gpu_ctx* c, const uint8_t* const* files, const size_t* file_sizes, int n, int filtered, int ppm, uint8_t* dst,
+                        size_t cap, size_t* offsets, size_t* sizes, int chunk) {
+	if (!c || !files || !file_sizes || !dst || n <= 0) return fail(EINVAL, "bad arguments");
+	std::vector<FrameGeom> g(n);
+	for (int i = 0; i < n; i++) {
+		uint32_t w = 0, h = 0;
+		if (vp8_parse_webp_size(files[i], file_sizes[i], &w, &h)) return fail(errno ? errno : EINVAL, "not a simple lossy WebP key frame");
+		g[i] = {w, h};
+	}
+	return decode_pipelined(
+	    c, g.data(), n,
+	    [&](int first, int cnt, int slot, cudaStream_t s_up, vp8_gpu_batch** out) {
+		    return batch_create_webp(c, files + first, file_sizes + first, g.data() + first, cnt, slot, s_up, out);
+	    },
+	    ppm ? 1 : filtered, ppm != 0, dst, cap, offsets, sizes, chunk);
+}
+
+size_t vp8_gpu_decode_webp_bytes(const uint8_t* const* files, const size_t* file_sizes, int n, int ppm) {
+	size_t total = 0;
+	for (int i = 0; files && file_sizes && i < n; i++) {
+		uint32_t w = 0, h = 0;
+		if (vp8_parse_webp_size(files[i], file_sizes[i], &w, &h)) return 0;
+		total += ppm ? align_up(kPpmSlot + (size_t)w * h * 3) : align_up((size_t)w * h + 2 * (size_t)((w + 1) / 2) * ((h + 1) / 2));
+	}
+	return total;
+}
+
+int vp8_gpu_last_call_profile(const vp8_gpu_ctx* c, double* total_ms, double* host_work_ms, double* wait_ms) {
+	if (!c) return fail(EINVAL, "null context");
+	if (total_ms) *total_ms = c->trace_total_ms;
+	if (host_work_ms) *host_work_ms = c->trace_compact_ms;
+	if (wait_ms) *wait_ms = c->trace_retire_ms;
+	return 0;
+}
+
+// "0-15,32-47" -> CPU numbers
+static std::vector<int> parse_cpulist(const char* txt) {
+	std::vector<int> cpus;
+	for (const char* p = txt; *p;) {
+		while (*p == ',' || *p == ' ' || *p == '\n') p++;
+		if (*p < '0' || *p > '9') break;
+		char* e;
+		long a = strtol(p, &e, 10), b = a;
+		if (*e == '-') b = strtol(e + 1, &e, 10);
+		for (long k = a; k <= b && k < 4096; k++) cpus.push_back((int)k);
+		p = e;
+	}
+	return cpus;
+}
+
+int vp8_gpu_bind_host(vp8_gpu_ctx* c, int index, int share) {
+	if (!c || index < 0 || share < 0) return fail(EINVAL, "bad arguments");
+	char bus[32] = {0};
+	if (cudaDeviceGetPCIBusId(bus, sizeof(bus), c->device) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	for (char* p = bus; *p; p++) *p = (char)tolower(*p);
+	char path[128];
+	snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+	FILE* f = fopen(path, "r");
+	if (!f) return 0;
+	char line[4096] = {0};
+	const bool got = fgets(line, sizeof(line), f) != nullptr;
+	fclose(f);
+	if (!got) return 0;
+	std::vector<int> cpus = parse_cpulist(line);
+	// only CPUs this process may run on (container cpusets)
+	cpu_set_t allowed;
+	CPU_ZERO(&allowed);
+	if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+		std::vector<int> keep;
+		for (int k : cpus)
+			if (k < CPU_SETSIZE && CPU_ISSET(k, &allowed)) keep.push_back(k);
+		cpus.swap(keep);
+	}
+	if (cpus.empty()) return 0;
+	if (share > 1) {
+		const size_t per = cpus.size() / (size_t)share;
+		if (per >= 1) {
+			const size_t at = (size_t)(index % share) * per;
+			cpus = std::vector<int>(cpus.begin() + at, cpus.begin() + at + per);
+		}
+	}
+	cpu_set_t set;
+	CPU_ZERO(&set);
+	for (int k : cpus)
+		if (k < CPU_SETSIZE) CPU_SET(k, &set);
+	if (sched_setaffinity(0, sizeof(set), &set) != 0) return 0;
+	// workers inherit the affinity of the thread that creates them: start over
+	delete c->pool;
+	c->pool = nullptr;
+	return (int)cpus.size();
 }
 
 size_t vp8_gpu_decode_bytes(const Vp8KeyFrameHeader* const* kf, int n, int ppm) {
@@ -1741,11 +2006,11 @@ int vp8_gpu_last_launch_config(const vp8_gpu_ctx* c, int* warps, int* grid, int*
 
 void vp8_gpu_frame_params(const Vp8DecodedFrame* f, int16_t dq[4][6], uint8_t lf[4][2][4]) { frame_params(f, dq, lf); }
 
-int vp8_gpu_kernel_time(vp8_gpu_ctx* c, double* total_ms, int* launches) {
+static int drain_timed(vp8_gpu_ctx* c, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& list, double* total_ms, int* launches) {
 	if (!c) return fail(EINVAL, "null context");
 	double sum = 0;
 	int n = 0;
-	for (auto& ev : c->timed) {
+	for (auto& ev : list) {
 		CU(cudaEventSynchronize(ev.second));
 		float ms = 0;
 		CU(cudaEventElapsedTime(&ms, ev.first, ev.second));
@@ -1753,11 +2018,14 @@ int vp8_gpu_kernel_time(vp8_gpu_ctx* c, double* total_ms, int* launches) {
 		n++;
 		c->spare.push_back(ev);
 	}
-	c->timed.clear();
+	list.clear();
 	if (total_ms) *total_ms = sum;
 	if (launches) *launches = n;
 	return 0;
 }
+
+int vp8_gpu_kernel_time(vp8_gpu_ctx* c, double* total_ms, int* launches) { return c ? drain_timed(c, c->timed, total_ms, launches) : fail(EINVAL, "null context"); }
+int vp8_gpu_rgb_time(vp8_gpu_ctx* c, double* total_ms, int* launches) { return c ? drain_timed(c, c->timed_rgb, total_ms, launches) : fail(EINVAL, "null context"); }
 
 // ================================================================================================ C-ABI: reference module interfaces
 

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/vp8_parse.h"
+#include "vp8_parse_internal.h"
 #include "vp8_tables.h"
 
 namespace {
@@ -217,6 +218,232 @@ struct Carver {
 	}
 };
 
+// ------------------------------------------------------------------------------------------------ where coefficients go
+// The token loop hands every 4x4 block to a sink: slot() says where block `bit` of macroblock i is decoded (16 zeroed
+// int16), done() is told whether it ended up non-zero. bit = 0..15 luma (raster), 16..19 U, 20..23 V, 24 Y2.
+struct DenseSink { // the reference's own arrays (vp8_tokens.h:52-99)
+	Vp8DecodedFrame* f;
+	void begin_mb(size_t) {}
+	int16_t* slot(size_t i, int bit) {
+		if (bit < 16) return f->coeff_y + (i * 16 + bit) * 16;
+		if (bit < 20) return f->coeff_u + (i * 4 + bit - 16) * 16;
+		if (bit < 24) return f->coeff_v + (i * 4 + bit - 20) * 16;
+		return f->coeff_y2 + i * 16;
+	}
+	void done(int, int) {}
+	bool end_mb(size_t) { return true; }
+};
+
+// Compact wire format (vp8_parse_internal.h): per macroblock a presence mask and the index of its first packed block;
+// only non-zero blocks are kept, 32 bytes each, in bit order. A block is decoded in place at the running position and
+// the position only moves on when it turned out non-zero; Y2 comes first in the bitstream but last in bit order, so it
+// waits in a side buffer.
+struct CompactSink {
+	uint8_t* arena;                 // packed-block base: mb_first counts 32-byte blocks from here
+	std::atomic<size_t>* cursor;    // shared allocation cursor of the arena (granule mode), or null: [pos, end) is all there is
+	size_t capacity;
+	uint32_t* mask;
+	uint32_t* first;
+	size_t pos = 0, end = 0;        // current granule, arena offsets
+	uint32_t cur = 0, blocks = 0;
+	alignas(32) int16_t y2[16];
+	bool y2_nz = false;
+
+	bool room() {
+		if (end - pos >= vp8c::kMbWorst + 32) return true; // done() zeroes one slot ahead
+		if (!cursor) return false;
+		pos = cursor->fetch_add(vp8c::kGranule);
+		end = pos + vp8c::kGranule;
+		return end <= capacity;
+	}
+	bool begin_ok = true;
+	void begin_mb(size_t i) {
+		begin_ok = room();
+		first[i] = (uint32_t)(pos / 32);
+		cur = 0;
+		y2_nz = false;
+		if (begin_ok) memset(arena + pos, 0, 32);
+	}
+	int16_t* slot(size_t, int bit) {
+		if (bit == 24 || !begin_ok) { // (out of space: decode into the side buffer, the frame is reported as failed)
+			memset(y2, 0, 32);
+			return y2;
+		}
+		return reinterpret_cast<int16_t*>(arena + pos);
+	}
+	void done(int bit, int nz) {
+		if (!nz || !begin_ok) return;
+		cur |= 1u << bit;
+		if (bit == 24) {
+			y2_nz = true;
+			return;
+		}
+		pos += 32;
+		blocks++;
+		memset(arena + pos, 0, 32); // next slot (room() keeps 800 bytes = 25 blocks ahead of begin_mb's position)
+	}
+	bool end_mb(size_t i) {
+		if (y2_nz && begin_ok) {
+			memcpy(arena + pos, y2, 32);
+			pos += 32;
+			blocks++;
+		}
+		mask[i] = cur;
+		return begin_ok;
+	}
+	// hand the unused tail of the last granule back when nobody has taken space after it
+	void finish() {
+		if (cursor && end > pos) {
+			size_t expect = end;
+			cursor->compare_exchange_strong(expect, (pos + 31) / 32 * 32);
+		}
+	}
+};
+
+// ---- first partition: frame header (RFC 6386 section 9.2-9.11, 19.2) and per-macroblock modes (sections 9.3, 11).
+// The mode arrays of `out` (segment_id, skip_coeff, ymode, uv_mode, bmode) must be in place and zeroed.
+int parse_first_partition(const uint8_t* d, const Vp8KeyFrameHeader* kf, Vp8DecodedFrame* out, uint8_t* probs) {
+	const uint32_t cols = out->mb_cols, rows = out->mb_rows;
+	BoolReader br(d + 10, kf->first_partition_len);
+	br.bit(128); // color space
+	br.bit(128); // clamping type
+	uint8_t seg_probs[3] = {255, 255, 255};
+	bool update_map = false;
+	out->segmentation_enabled = (uint8_t)br.bit(128);
+	if (out->segmentation_enabled) {
+		update_map = br.bit(128);
+		if (br.bit(128)) { // update segment feature data
+			out->segmentation_abs = (uint8_t)br.bit(128);
+			for (int i = 0; i < 4; i++)
+				if (br.bit(128)) out->seg_quant_idx[i] = (int8_t)clamp_i8(br.sint(7));
+			for (int i = 0; i < 4; i++)
+				if (br.bit(128)) out->seg_lf_level[i] = (int8_t)clamp_i8(br.sint(6));
+		}
+		if (update_map)
+			for (int i = 0; i < 3; i++)
+				if (br.bit(128)) seg_probs[i] = (uint8_t)br.literal(8);
+	}
+	out->lf_use_simple = (uint8_t)br.bit(128);
+	out->lf_level = (uint8_t)br.literal(6);
+	out->lf_sharpness = (uint8_t)br.literal(3);
+	out->lf_delta_enabled = (uint8_t)br.bit(128);
+	if (out->lf_delta_enabled && br.bit(128)) {
+		for (int i = 0; i < 4; i++)
+			if (br.bit(128)) out->lf_ref_delta[i] = (int8_t)clamp_i8(br.sint(6));
+		for (int i = 0; i < 4; i++)
+			if (br.bit(128)) out->lf_mode_delta[i] = (int8_t)clamp_i8(br.sint(6));
+	}
+	const int partitions = 1 << br.literal(2);
+	out->q_index = (uint8_t)br.literal(7);
+	int8_t* dq[5] = {&out->y1_dc_delta_q, &out->y2_dc_delta_q, &out->y2_ac_delta_q, &out->uv_dc_delta_q, &out->uv_ac_delta_q};
+	for (int i = 0; i < 5; i++) *dq[i] = br.bit(128) ? (int8_t)clamp_i8(br.sint(4)) : 0;
+	br.bit(128); // refresh_entropy_probs
+
+	// coefficient probabilities: defaults + updates, private to this call
+	memcpy(probs, kDefaultCoeffProbs, 4 * 8 * 3 * 11);
+	for (int i = 0; i < 4 * 8 * 3 * 11; i++)
+		if (br.bit(kCoeffUpdateProbs[i])) probs[i] = (uint8_t)br.literal(8);
+
+	const bool has_skip = br.bit(128);
+	const uint8_t skip_prob = has_skip ? (uint8_t)br.literal(8) : 0;
+
+	std::vector<uint8_t> above(cols * 4, B_DC);
+	for (uint32_t my = 0; my < rows; my++) {
+		uint8_t left[4] = {B_DC, B_DC, B_DC, B_DC};
+		for (uint32_t mx = 0; mx < cols; mx++) {
+			const size_t i = (size_t)my * cols + mx;
+			if (update_map) out->segment_id[i] = (uint8_t)read_segment_id(br, seg_probs);
+			if (has_skip) out->skip_coeff[i] = (uint8_t)br.bit(skip_prob);
+			const int ym = read_kf_ymode(br);
+			out->ymode[i] = (uint8_t)ym;
+			uint8_t* bm = out->bmode + i * 16;
+			uint8_t* ab = &above[mx * 4];
+			if (ym == 4) {
+				for (int r = 0; r < 4; r++)
+					for (int c = 0; c < 4; c++) {
+						const int A = r ? bm[4 * (r - 1) + c] : ab[c];
+						const int L = c ? bm[4 * r + c - 1] : left[r];
+						bm[4 * r + c] = (uint8_t)read_bmode(br, kKfBmodeProbs + (A * 10 + L) * 9);
+					}
+				for (int k = 0; k < 4; k++) {
+					ab[k] = bm[12 + k];
+					left[k] = bm[4 * k + 3];
+				}
+			} else {
+				static const uint8_t implied[4] = {B_DC, B_VE, B_HE, B_TM};
+				memset(bm, implied[ym], 16);
+				memset(ab, implied[ym], 4);
+				memset(left, implied[ym], 4);
+			}
+			out->uv_mode[i] = (uint8_t)read_uv_mode(br);
+		}
+	}
+	// a single token partition; the reference rejects more, vp8_tokens.c:357-360
+	return partitions == 1 ? 0 : fail(ENOTSUP);
+}
+
+// ---- token partition. Returns false when the sink ran out of space.
+template <class Sink>
+bool parse_tokens(const uint8_t* d, size_t n, const Vp8KeyFrameHeader* kf, Vp8DecodedFrame* out, const uint8_t* probs, Sink& sink) {
+	const uint32_t cols = out->mb_cols, rows = out->mb_rows;
+	const size_t tok_off = 10 + (size_t)kf->first_partition_len;
+	BoolReader tr(d + tok_off, n - tok_off);
+	// non-zero contexts: per MB column 4 luma + 2 U + 2 V + 1 Y2 above flags; same set to the left
+	std::vector<uint8_t> above(cols * 9, 0);
+	bool ok = true;
+	for (uint32_t my = 0; my < rows; my++) {
+		uint8_t left[9] = {0};
+		for (uint32_t mx = 0; mx < cols; mx++) {
+			const size_t i = (size_t)my * cols + mx;
+			uint8_t* ab = &above[mx * 9];
+			const bool has_y2 = out->ymode[i] != 4;
+			sink.begin_mb(i);
+			if (out->skip_coeff[i]) {
+				// no tokens: contexts clear, except Y2's which a B_PRED macroblock leaves alone
+				const uint8_t a8 = ab[8], l8 = left[8];
+				memset(ab, 0, 9);
+				memset(left, 0, 9);
+				if (!has_y2) {
+					ab[8] = a8;
+					left[8] = l8;
+				}
+				ok &= sink.end_mb(i);
+				continue;
+			}
+			int any = 0;
+			if (has_y2) {
+				const int nz = read_block(tr, probs + 1 * 264, 0, ab[8] + left[8], sink.slot(i, 24));
+				sink.done(24, nz);
+				ab[8] = left[8] = (uint8_t)nz;
+				any |= nz;
+			}
+			const uint8_t* py = probs + (has_y2 ? 0 : 3) * 264;
+			for (int r = 0; r < 4; r++)
+				for (int c = 0; c < 4; c++) {
+					const int nz = read_block(tr, py, has_y2 ? 1 : 0, ab[c] + left[r], sink.slot(i, 4 * r + c));
+					sink.done(4 * r + c, nz);
+					ab[c] = left[r] = (uint8_t)nz;
+					any |= nz;
+				}
+			for (int pl = 0; pl < 2; pl++) {
+				uint8_t* a = ab + 4 + 2 * pl;
+				uint8_t* l = left + 4 + 2 * pl;
+				for (int r = 0; r < 2; r++)
+					for (int c = 0; c < 2; c++) {
+						const int bit = 16 + 4 * pl + 2 * r + c;
+						const int nz = read_block(tr, probs + 2 * 264, 0, a[c] + l[r], sink.slot(i, bit));
+						sink.done(bit, nz);
+						a[c] = l[r] = (uint8_t)nz;
+						any |= nz;
+					}
+			}
+			out->has_coeff[i] = (uint8_t)any;
+			ok &= sink.end_mb(i);
+		}
+	}
+	return ok;
+}
+
 int parse_payload(const uint8_t* d, size_t n, Vp8KeyFrameHeader* kf, Vp8DecodedFrame* out, void* arena, size_t arena_bytes) {
 	if (!kf || !out) return fail(EINVAL);
 	memset(out, 0, sizeof(*out));
@@ -261,139 +488,65 @@ int parse_payload(const uint8_t* d, size_t n, Vp8KeyFrameHeader* kf, Vp8DecodedF
 		memset(out, 0, sizeof(*out));
 		return fail(e);
 	};
-
-	// ---- first partition: frame header (RFC 6386 section 9.2-9.11, 19.2)
-	BoolReader br(d + 10, kf->first_partition_len);
-	br.bit(128); // color space
-	br.bit(128); // clamping type
-	uint8_t seg_probs[3] = {255, 255, 255};
-	bool update_map = false;
-	out->segmentation_enabled = (uint8_t)br.bit(128);
-	if (out->segmentation_enabled) {
-		update_map = br.bit(128);
-		if (br.bit(128)) { // update segment feature data
-			out->segmentation_abs = (uint8_t)br.bit(128);
-			for (int i = 0; i < 4; i++)
-				if (br.bit(128)) out->seg_quant_idx[i] = (int8_t)clamp_i8(br.sint(7));
-			for (int i = 0; i < 4; i++)
-				if (br.bit(128)) out->seg_lf_level[i] = (int8_t)clamp_i8(br.sint(6));
-		}
-		if (update_map)
-			for (int i = 0; i < 3; i++)
-				if (br.bit(128)) seg_probs[i] = (uint8_t)br.literal(8);
-	}
-	out->lf_use_simple = (uint8_t)br.bit(128);
-	out->lf_level = (uint8_t)br.literal(6);
-	out->lf_sharpness = (uint8_t)br.literal(3);
-	out->lf_delta_enabled = (uint8_t)br.bit(128);
-	if (out->lf_delta_enabled && br.bit(128)) {
-		for (int i = 0; i < 4; i++)
-			if (br.bit(128)) out->lf_ref_delta[i] = (int8_t)clamp_i8(br.sint(6));
-		for (int i = 0; i < 4; i++)
-			if (br.bit(128)) out->lf_mode_delta[i] = (int8_t)clamp_i8(br.sint(6));
-	}
-	const int partitions = 1 << br.literal(2);
-	out->q_index = (uint8_t)br.literal(7);
-	int8_t* dq[5] = {&out->y1_dc_delta_q, &out->y2_dc_delta_q, &out->y2_ac_delta_q, &out->uv_dc_delta_q, &out->uv_ac_delta_q};
-	for (int i = 0; i < 5; i++) *dq[i] = br.bit(128) ? (int8_t)clamp_i8(br.sint(4)) : 0;
-	br.bit(128); // refresh_entropy_probs
-
-	// coefficient probabilities: defaults + updates, private to this call
 	uint8_t probs[4 * 8 * 3 * 11];
-	memcpy(probs, kDefaultCoeffProbs, sizeof(probs));
-	for (int i = 0; i < 4 * 8 * 3 * 11; i++)
-		if (br.bit(kCoeffUpdateProbs[i])) probs[i] = (uint8_t)br.literal(8);
+	if (parse_first_partition(d, kf, out, probs)) return bail(errno);
+	DenseSink sink{out};
+	parse_tokens(d, n, kf, out, probs, sink);
+	return 0;
+}
 
-	const bool has_skip = br.bit(128);
-	const uint8_t skip_prob = has_skip ? (uint8_t)br.literal(8) : 0;
-
-	// ---- first partition: per-macroblock modes (RFC 6386 sections 9.3, 11)
-	{
-		std::vector<uint8_t> above(cols * 4, B_DC);
-		for (uint32_t my = 0; my < rows; my++) {
-			uint8_t left[4] = {B_DC, B_DC, B_DC, B_DC};
-			for (uint32_t mx = 0; mx < cols; mx++) {
-				const size_t i = (size_t)my * cols + mx;
-				if (update_map) out->segment_id[i] = (uint8_t)read_segment_id(br, seg_probs);
-				if (has_skip) out->skip_coeff[i] = (uint8_t)br.bit(skip_prob);
-				const int ym = read_kf_ymode(br);
-				out->ymode[i] = (uint8_t)ym;
-				uint8_t* bm = out->bmode + i * 16;
-				uint8_t* ab = &above[mx * 4];
-				if (ym == 4) {
-					for (int r = 0; r < 4; r++)
-						for (int c = 0; c < 4; c++) {
-							const int A = r ? bm[4 * (r - 1) + c] : ab[c];
-							const int L = c ? bm[4 * r + c - 1] : left[r];
-							bm[4 * r + c] = (uint8_t)read_bmode(br, kKfBmodeProbs + (A * 10 + L) * 9);
-						}
-					for (int k = 0; k < 4; k++) {
-						ab[k] = bm[12 + k];
-						left[k] = bm[4 * k + 3];
-					}
-				} else {
-					static const uint8_t implied[4] = {B_DC, B_VE, B_HE, B_TM};
-					memset(bm, implied[ym], 16);
-					memset(ab, implied[ym], 4);
-					memset(left, implied[ym], 4);
-				}
-				out->uv_mode[i] = (uint8_t)read_uv_mode(br);
-			}
-		}
+// Compact flavour. space: where the frame goes; with a shared cursor (granule mode) the head is taken from it in one piece
+// and the packed blocks in 64 KiB granules, otherwise head and blocks sit back to back at space->base + space->at.
+int parse_payload_compact(const uint8_t* d, size_t n, Vp8KeyFrameHeader* kf, Vp8CompactFrame* cf, uint8_t* base, size_t capacity,
+                          std::atomic<size_t>* cursor, size_t at) {
+	if (!kf || !cf || !base) return fail(EINVAL);
+	memset(cf, 0, sizeof(*cf));
+	Vp8DecodedFrame* out = &cf->f;
+	if (read_frame_header(d, n, kf)) return -1;
+	const uint32_t cols = (kf->width + 15u) / 16u, rows = (kf->height + 15u) / 16u;
+	const size_t mb = (size_t)cols * rows;
+	if (mb > (1u << 20)) return fail(EINVAL);
+	out->mb_cols = cols;
+	out->mb_rows = rows;
+	out->mb_total = (uint32_t)mb;
+	const vp8c::Layout L = vp8c::layout(mb);
+	const size_t head = cursor ? cursor->fetch_add(L.o_packed) : at;
+	if (head + (cursor ? L.o_packed : vp8c::standalone_bound(mb)) > capacity) return fail(ENOSPC);
+	uint8_t* h = base + head;
+	memset(h + L.o_ymode, 0, L.o_packed - L.o_ymode); // modes; mask / first are written for every macroblock
+	out->ymode = h + L.o_ymode;
+	out->uv_mode = h + L.o_uv;
+	out->segment_id = h + L.o_seg;
+	out->has_coeff = h + L.o_hc;
+	out->bmode = h + L.o_bmode;
+	std::vector<uint8_t> skip(mb, 0); // not part of the wire format: the pixel path never reads it
+	out->skip_coeff = skip.data();
+	uint8_t probs[4 * 8 * 3 * 11];
+	if (parse_first_partition(d, kf, out, probs)) return -1;
+	CompactSink sink;
+	sink.capacity = capacity;
+	sink.mask = reinterpret_cast<uint32_t*>(h + L.o_mask);
+	sink.first = reinterpret_cast<uint32_t*>(h + L.o_first);
+	if (cursor) {
+		sink.arena = base;
+		sink.cursor = cursor;
+	} else {
+		sink.arena = h + L.o_packed; // standalone frame: mb_first counts from the frame's own packed base
+		sink.cursor = nullptr;
+		sink.pos = 0;
+		sink.end = vp8c::kMbWorst * mb + vp8c::kSlack;
 	}
-
-	// ---- token partition (single; the reference rejects more, vp8_tokens.c:357-360)
-	if (partitions != 1) return bail(ENOTSUP);
-	const size_t tok_off = 10 + (size_t)kf->first_partition_len;
-	BoolReader tr(d + tok_off, n - tok_off);
-	{
-		// non-zero contexts: per MB column 4 luma + 2 U + 2 V + 1 Y2 above flags; same set to the left
-		std::vector<uint8_t> above(cols * 9, 0);
-		for (uint32_t my = 0; my < rows; my++) {
-			uint8_t left[9] = {0};
-			for (uint32_t mx = 0; mx < cols; mx++) {
-				const size_t i = (size_t)my * cols + mx;
-				uint8_t* ab = &above[mx * 9];
-				const bool has_y2 = out->ymode[i] != 4;
-				if (out->skip_coeff[i]) {
-					// no tokens: contexts clear, except Y2's which a B_PRED macroblock leaves alone
-					const uint8_t a8 = ab[8], l8 = left[8];
-					memset(ab, 0, 9);
-					memset(left, 0, 9);
-					if (!has_y2) {
-						ab[8] = a8;
-						left[8] = l8;
-					}
-					continue;
-				}
-				int any = 0;
-				if (has_y2) {
-					const int nz = read_block(tr, probs + 1 * 264, 0, ab[8] + left[8], out->coeff_y2 + i * 16);
-					ab[8] = left[8] = (uint8_t)nz;
-					any |= nz;
-				}
-				const uint8_t* py = probs + (has_y2 ? 0 : 3) * 264;
-				for (int r = 0; r < 4; r++)
-					for (int c = 0; c < 4; c++) {
-						const int nz = read_block(tr, py, has_y2 ? 1 : 0, ab[c] + left[r], out->coeff_y + (i * 16 + 4 * r + c) * 16);
-						ab[c] = left[r] = (uint8_t)nz;
-						any |= nz;
-					}
-				for (int pl = 0; pl < 2; pl++) {
-					int16_t* dst = (pl ? out->coeff_v : out->coeff_u) + i * 64;
-					uint8_t* a = ab + 4 + 2 * pl;
-					uint8_t* l = left + 4 + 2 * pl;
-					for (int r = 0; r < 2; r++)
-						for (int c = 0; c < 2; c++) {
-							const int nz = read_block(tr, probs + 2 * 264, 0, a[c] + l[r], dst + (2 * r + c) * 16);
-							a[c] = l[r] = (uint8_t)nz;
-							any |= nz;
-						}
-				}
-				out->has_coeff[i] = (uint8_t)any;
-			}
-		}
-	}
+	const bool ok = parse_tokens(d, n, kf, out, probs, sink);
+	sink.finish();
+	out->skip_coeff = nullptr;
+	if (!ok) return fail(ENOSPC);
+	cf->base = base;
+	cf->head_off = head;
+	cf->packed_off = cursor ? 0 : head + L.o_packed;
+	cf->bytes = cursor ? 0 : L.o_packed + sink.pos;
+	cf->n_blocks = sink.blocks;
+	cf->width = kf->width;
+	cf->height = kf->height;
 	return 0;
 }
 
@@ -428,6 +581,41 @@ int vp8_parse_webp(const uint8_t* file, size_t size, Vp8KeyFrameHeader* kf, Vp8D
 	return parse_payload(payload, psize, kf, out, arena, arena_bytes);
 }
 
+size_t vp8_parse_compact_bytes(uint32_t width, uint32_t height) {
+	return vp8c::standalone_bound((size_t)((width + 15) / 16) * ((height + 15) / 16));
+}
+
+int vp8_parse_webp_compact(const uint8_t* file, size_t size, Vp8KeyFrameHeader* kf, Vp8CompactFrame* out, void* arena, size_t arena_bytes) {
+	const uint8_t* payload;
+	size_t psize;
+	Vp8KeyFrameHeader peek;
+	if (!kf || !out) return fail(EINVAL);
+	if (find_vp8_chunk(file, size, &payload, &psize) || read_frame_header(payload, psize, &peek)) return -1;
+	bool own = false;
+	if (!arena) {
+		arena_bytes = vp8_parse_compact_bytes(peek.width, peek.height);
+		arena = aligned_alloc(256, (arena_bytes + 255) / 256 * 256);
+		if (!arena) return fail(ENOMEM);
+		own = true;
+	} else if ((uintptr_t)arena & 31) {
+		return fail(EINVAL);
+	}
+	if (parse_payload_compact(payload, psize, kf, out, (uint8_t*)arena, arena_bytes, nullptr, 0)) {
+		const int e = errno;
+		if (own) free(arena);
+		memset(out, 0, sizeof(*out));
+		return fail(e == ENOSPC ? EINVAL : e);
+	}
+	out->owned = own;
+	return 0;
+}
+
+void vp8_parse_compact_free(Vp8CompactFrame* f) {
+	if (!f) return;
+	if (f->owned) free(f->base);
+	memset(f, 0, sizeof(*f));
+}
+
 void vp8_parse_free(Vp8DecodedFrame* f) {
 	if (!f) return;
 	if (f->stats_opaque[24] == 0x6f776e6564ull) free(f->coeff_y);
@@ -458,4 +646,75 @@ int vp8_parse_batch(const uint8_t* const* files, const size_t* sizes, int n, int
 	return failed.load();
 }
 
+int vp8_parse_batch_compact(const uint8_t* const* files, const size_t* sizes, int n, int threads, Vp8KeyFrameHeader* kf,
+                            Vp8CompactFrame* out, void* arena, size_t arena_bytes, size_t* used, int* status) {
+	if (!files || !sizes || !kf || !out || n < 0 || (arena && ((uintptr_t)arena & 255))) {
+		errno = EINVAL;
+		return -1;
+	}
+	if (threads < 1) threads = 1;
+	if (threads > n) threads = n;
+	// with an arena, frame i goes to a slot of its worst-case size and is then moved down so that the frames end up back
+	// to back (256-byte aligned) in index order: one contiguous block for the whole batch, ready for a single transfer
+	std::vector<size_t> slot(n + 1, 0);
+	if (arena) {
+		for (int i = 0; i < n; i++) {
+			uint32_t w = 0, h = 0;
+			if (vp8_parse_webp_size(files[i], sizes[i], &w, &h)) w = h = 16;
+			slot[i + 1] = slot[i] + (vp8_parse_compact_bytes(w, h) + 255) / 256 * 256;
+		}
+		if (slot[n] > arena_bytes) {
+			errno = EINVAL;
+			return -1;
+		}
+	}
+	std::atomic<int> next{0}, failed{0};
+	auto worker = [&]() {
+		for (int i; (i = next.fetch_add(1)) < n;) {
+			const int rc = vp8_parse_webp_compact(files[i], sizes[i], &kf[i], &out[i], arena ? (uint8_t*)arena + slot[i] : nullptr,
+			                                      arena ? slot[i + 1] - slot[i] : 0);
+			if (status) status[i] = rc ? errno : 0;
+			if (rc) failed++;
+		}
+	};
+	std::vector<std::thread> pool;
+	for (int t = 1; t < threads; t++) pool.emplace_back(worker);
+	worker();
+	for (auto& t : pool) t.join();
+	if (arena) {
+		size_t at = 0;
+		for (int i = 0; i < n; i++) {
+			if (status && status[i]) continue;
+			if (!out[i].base) continue;
+			uint8_t* dst = (uint8_t*)arena + at;
+			if (dst != out[i].base) memmove(dst, out[i].base, out[i].bytes);
+			vp8_compact_rebase(&out[i], dst);
+			at += (out[i].bytes + 255) / 256 * 256;
+		}
+		if (used) *used = at;
+	}
+	return failed.load();
+}
+
+void vp8_compact_rebase(Vp8CompactFrame* f, void* new_start) {
+	if (!f || !f->base || !new_start) return;
+	const ptrdiff_t d = (uint8_t*)new_start - (f->base + f->head_off);
+	f->f.ymode += d;
+	f->f.uv_mode += d;
+	f->f.segment_id += d;
+	f->f.has_coeff += d;
+	f->f.bmode += d;
+	f->base = (uint8_t*)new_start;
+	f->packed_off -= f->head_off;
+	f->head_off = 0;
+}
+
 } // extern "C"
+
+int vp8_parse_webp_shared(const uint8_t* file, size_t size, Vp8KeyFrameHeader* kf, Vp8CompactFrame* cf, uint8_t* base, size_t capacity,
+                          std::atomic<size_t>* cursor) {
+	const uint8_t* payload;
+	size_t psize;
+	if (find_vp8_chunk(file, size, &payload, &psize)) return -1;
+	return parse_payload_compact(payload, psize, kf, cf, base, capacity, cursor, 0);
+}
