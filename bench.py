@@ -350,16 +350,14 @@ def gpu_arm(args):
         # (2a) the reference's contract: dense Vp8DecodedFrames, every frame with its own host memory
         dense = P.replicate_dense(pf, order)
         dkfs, dfrs = dense.kf_list(), dense.frame_list()
-        # compact transport needs host threads to read every frame once; with few threads per GPU plain DMA of the dense
-        # arrays wins (measured: profiles/README.md, r2 transport table)
-        compact_auto = threads >= args.compact_min_threads
-        use_compact = compact_auto if args.transport == "auto" else args.transport == "compact"
-        ctx.set_transport(use_compact, threads)
+        # transport "auto": chunk by chunk, dense when the copy engine has run dry, compact (host threads drop the all-zero
+        # blocks) otherwise - neither the link nor the host threads wait for the other
+        ctx.set_transport({"auto": "auto", "compact": True, "dense": False}[args.transport], threads)
         ms, up, down, prof = timed_calls(lambda: ctx.decode_into(dkfs, dfrs, host_out.array, filtered=filtered, ppm=ppm, chunk=args.chunk), n_e2e, warm)
         ok = check(host_out.array, *_layout(ctx, dkfs, ppm), idx=_spot(args.batch))
         e2e = {"value": world * px_step / (ms / 1e3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": up, "d2h_bytes_per_step": down,
                "steps": n_e2e, "ms_per_step": ms, "api": "vp8_gpu_decode_ppm" if ppm else "vp8_gpu_decode_i420",
-               "transport": "compact (host threads drop all-zero blocks)" if use_compact else "dense (DMA of the arrays as they are)",
+               "transport": {"mode": args.transport, **ctx.last_transport(), "host_threads": threads},
                "host_bytes_in_per_step": dense.nbytes, "host_profile_ms": prof, "bit_exact_spot_check": ok,
                "note": "dense Vp8DecodedFrame arrays (the reference's m05 output layout) in pinned host memory, one private copy per "
                        "frame; token decode (m03/m05) not included"}
@@ -380,7 +378,7 @@ def gpu_arm(args):
         # (2c) from .webp bytes: host threads parse chunk k while the GPU works on the chunks before it
         nw = max(nd, min(args.batch, args.webp_batch))
         wf = W.WebpFiles([datas[i % nd] for i in range(nw)])
-        ctx.set_transport(True, threads)
+        ctx.set_transport("auto", threads)
         steps_w = max(1, min(n_e2e, 2))
         ms, up, down, prof = timed_calls(lambda: ctx.decode_webp_into(wf, host_out.array, filtered=filtered, ppm=ppm, chunk=args.chunk), steps_w, 1)
         ok = check(host_out.array, *_layout(ctx, kfs[:nw], ppm), idx=_spot(nw))
@@ -596,7 +594,6 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--chunk", type=int, default=0, help="frames per pipeline chunk of the end-to-end calls (0 = library default)")
     ap.add_argument("--transport", default="auto", choices=["auto", "compact", "dense"], help="how e2e (dense contract) crosses the link")
-    ap.add_argument("--compact-min-threads", type=int, default=8, help="auto transport: compact when a GPU has at least this many host threads")
     ap.add_argument("--webp-batch", type=int, default=256, help="frames per step of the e2e_from_webp leg (parser-bound: seconds per step)")
     ap.add_argument("--mixed-copies", type=int, default=2, help="config 5: copies of the 48-file mixed set per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -57,7 +57,7 @@ typedef struct vp8_gpu_batch vp8_gpu_batch; /* n frames resident on the device *
  * private stream. All work of the context is issued on that stream. */
 /* Environment presets read by vp8_gpu_init (each has a setter below; the legacy single-frame entry points, which
  * create their context themselves, can only be steered this way): VP8_GPU_DEVICE, VP8_GPU_KERNEL (2|3),
- * VP8_GPU_WARPS, VP8_GPU_IMAGES_PER_SM, VP8_GPU_CLUSTER, VP8_GPU_COMPACT (0|1), VP8_GPU_HOST_THREADS,
+ * VP8_GPU_WARPS, VP8_GPU_IMAGES_PER_SM, VP8_GPU_CLUSTER, VP8_GPU_COMPACT (0|1|2), VP8_GPU_HOST_THREADS,
  * VP8_GPU_LOCKSTEP_SMALL (0: 8-warp CTAs spin instead of meeting at a barrier), VP8_GPU_NT_STORES (0: host compaction
  * with ordinary stores), VP8_GPU_TRACE (1: host-time split of a pipelined call on stderr, 2: plus a per-chunk device
  * timeline). */
@@ -89,12 +89,16 @@ int vp8_gpu_last_segments(const vp8_gpu_ctx* ctx);
 int vp8_gpu_set_cluster(vp8_gpu_ctx* ctx, int ctas_per_image);
 int vp8_gpu_last_cluster(const vp8_gpu_ctx* ctx); /* CTAs per image of the last wavefront launch */
 
-/* Transport of vp8_gpu_decode_i420 / _ppm (dense Vp8DecodedFrames in): compact != 0 (default) ships each frame without
- * its all-zero 4x4 blocks (per-macroblock presence mask + packed blocks, built by host_threads workers; 0 = all cores,
- * at most 32), which is what the host->device link is bound by; compact == 0 ships the dense arrays as they are (pure
- * DMA of three times the bytes: the better choice when only a few host threads per GPU are available). host_threads is
- * also the number of parser threads of vp8_gpu_decode_webp. */
+/* Transport of vp8_gpu_decode_i420 / _ppm (dense Vp8DecodedFrames in). compact = 1: every chunk is shipped without its
+ * all-zero 4x4 blocks (per-macroblock presence mask + packed blocks, built by host_threads workers; 0 = all cores, at
+ * most 32) - a third of the bytes on the link for typical content, but the host has to read every array once.
+ * compact = 0: the dense arrays travel as they are, pure DMA. compact = 2 (default, also any other value): balanced
+ * chunk by chunk - the call keeps totals of the time its host threads have spent compacting and of the time the copy
+ * engine needs for what it was given (bytes / VP8_GPU_LINK_GBPS, default 50), and hands the next chunk to whichever is
+ * behind - so that neither waits for the other. host_threads is also the number of parser threads of
+ * vp8_gpu_decode_webp. vp8_gpu_last_transport tells what the last call did. */
 int vp8_gpu_set_transport(vp8_gpu_ctx* ctx, int compact, int host_threads);
+int vp8_gpu_last_transport(const vp8_gpu_ctx* ctx, int* dense_chunks, int* compact_chunks);
 
 /* Pinned host memory: frames whose arrays live here are copied to the device without staging. */
 void* vp8_gpu_host_alloc(size_t bytes);

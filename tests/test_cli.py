@@ -22,6 +22,13 @@ def test_batch_cli_outputs_match_reference_digests(lib, golden, tmp_path):
         for n in names:
             data = (out / (n[:-5] + "." + ext)).read_bytes()
             assert hashlib.sha256(data).hexdigest() == golden[n][key], (flag, n)
+    # --devices: the files are dealt longest-first to the listed GPUs (the same GPU twice stands in for two here), one
+    # pipeline per entry; same bytes
+    out = tmp_path / "two"
+    r = subprocess.run([str(exe), "-yuvf", str(out), "--devices", "0,0", "--threads", "4", *files], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for n in names:
+        assert hashlib.sha256((out / (n[:-5] + ".i420")).read_bytes()).hexdigest() == golden[n]["yuvf"], n
     # a broken input fails that file only, with exit status 1
     bad = tmp_path / "broken.webp"
     bad.write_bytes(b"RIFF\x00\x00\x00\x00WEBPVP8 ")

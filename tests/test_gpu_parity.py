@@ -318,7 +318,7 @@ def test_pipelined_decode_matches_digests(lib, gpu_ctx, golden, parsed_golden):
     kfs = [parsed_golden[n][0] for n in names]
     frs = [parsed_golden[n][1] for n in names]
     try:
-        for compact in (True, False):  # compact transport (zero blocks dropped on the host) and dense transport
+        for compact in (True, False, "auto"):  # zero blocks dropped on the host / arrays as they are / chosen per chunk
             gpu_ctx.set_transport(compact, 3)
             h2d0 = gpu_ctx.h2d_bytes
             for ppm, key, filtered in ((False, "yuvf", True), (False, "yuv", False), (True, "ppm", True)):
@@ -331,12 +331,17 @@ def test_pipelined_decode_matches_digests(lib, gpu_ctx, golden, parsed_golden):
                     assert not bad, (compact, key, len(bad), bad[:4])
                 pinned.close()
             moved = gpu_ctx.h2d_bytes - h2d0
-            if compact:
+            t = gpu_ctx.last_transport()
+            if compact is True:
                 compact_bytes = moved
-            else:
+                assert t["dense_chunks"] == 0 and t["compact_chunks"] > 0
+            elif compact is False:
                 assert compact_bytes < 0.6 * moved, (compact_bytes, moved)  # the corpus is mostly sparse
+                assert t["compact_chunks"] == 0 and t["dense_chunks"] > 0
+            else:
+                assert t["compact_chunks"] + t["dense_chunks"] > 0
     finally:
-        gpu_ctx.set_transport(True, 0)
+        gpu_ctx.set_transport("auto", 0)
     with pytest.raises(OSError):
         gpu_ctx.decode_into(kfs, frs, np.empty(10, np.uint8))
 
@@ -390,7 +395,7 @@ def test_webp_bytes_to_pixels_in_one_call(lib, gpu_ctx, golden, threads, chunk):
         prof = gpu_ctx.last_call_profile()
         assert prof["total_ms"] > 0 and prof["host_work_ms"] > 0
     finally:
-        gpu_ctx.set_transport(True, 0)
+        gpu_ctx.set_transport("auto", 0)
     # a broken file fails the whole call with the parser's errno
     junk = lib.WebpFiles([(GOLDEN / "webp" / names[0]).read_bytes(), b"RIFF\x04\x00\x00\x00WEBP"])
     assert gpu_ctx.decode_webp_bytes(junk) == 0
@@ -429,7 +434,7 @@ def test_pipelined_chunk_schedule_and_arena_granules(gpu_ctx, oracle, chunk):
             bad = [i for i, (o, s) in enumerate(zip(offs, sizes)) if not np.array_equal(out[int(o):int(o) + int(s)], want[i])]
             assert not bad, (chunk, threads, bad)
     finally:
-        gpu_ctx.set_transport(True, 0)
+        gpu_ctx.set_transport("auto", 0)
 
 
 def test_argument_errors(lib, gpu_ctx):

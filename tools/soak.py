@@ -15,12 +15,11 @@ import webp_decoder_b200 as W  # noqa: E402
 from vp8fix import Oracle, fuzz_frame  # noqa: E402
 
 
-def main():
-    seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
-    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
-    orc, ctx = Oracle(), W.Context(0)
-    t0, rounds, frames_done = time.time(), 0, 0
-    while time.time() - t0 < seconds:
+def soak(ctx, orc, rng, seconds=None, rounds=None):
+    """Runs until `seconds` have passed or `rounds` rounds are done; raises AssertionError on the first mismatch.
+    Returns (rounds, frames)."""
+    t0, done, frames_done = time.time(), 0, 0
+    while (seconds is None or time.time() - t0 < seconds) and (rounds is None or done < rounds):
         n = int(rng.choice([1, 2, 5, 13, 40, 150, 300]))
         big = rng.random() < 0.2
         frames = []
@@ -43,7 +42,7 @@ def main():
         if api == "batch":
             outs = ctx.decode_i420(kfs, ds, filtered=filtered)
         elif api == "pipelined":  # chunked, compact or dense transport, several host threads
-            ctx.set_transport(bool(rng.integers(2)), int(rng.choice([1, 3, 8])))
+            ctx.set_transport([True, False, "auto"][int(rng.integers(3))], int(rng.choice([1, 3, 8])))
             buf = np.empty(ctx.decode_bytes(kfs), np.uint8)
             offs, szs = ctx.decode_into(kfs, ds, buf, filtered=filtered, chunk=int(rng.choice([1, 3, 16, 64])))
             outs = [buf[int(o):int(o) + int(z)] for o, z in zip(offs, szs)]
@@ -53,12 +52,22 @@ def main():
             outs = [np.frombuffer(p, np.uint8) for p in ctx.decode_ppm(kfs, ds)]
         cfg = ctx.last_launch_config()
         bad = [i for i, (w, o) in enumerate(zip(want, outs)) if not np.array_equal(o, w)]
-        if bad:
-            print(f"MISMATCH round {rounds} ({api}): kernel {kernel} warps {warps} per_sm {per_sm} cluster {cluster} filtered {filtered} "
-                  f"launch {cfg}: frames {bad[:8]} of {n}, e.g. {frames[bad[0]].width}x{frames[bad[0]].height}")
-            return 1
-        rounds += 1
+        assert not bad, (f"MISMATCH round {done} ({api}): kernel {kernel} warps {warps} per_sm {per_sm} cluster {cluster} filtered {filtered} "
+                         f"launch {cfg}: frames {bad[:8]} of {n}, e.g. {frames[bad[0]].width}x{frames[bad[0]].height}")
+        done += 1
         frames_done += n
+    return done, frames_done
+
+
+def main():
+    seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    t0 = time.time()
+    try:
+        rounds, frames_done = soak(W.Context(0), Oracle(), rng, seconds=seconds)
+    except AssertionError as e:
+        print(e)
+        return 1
     print(f"soak ok: {rounds} rounds, {frames_done} frames, {time.time() - t0:.0f} s")
     return 0
 

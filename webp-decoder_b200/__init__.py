@@ -44,7 +44,7 @@ EXPORTS = [
     "vp8_gpu_decode_i420", "vp8_gpu_decode_ppm", "vp8_gpu_decode_bytes", "vp8_gpu_set_kernel",
     "vp8_gpu_png_bound", "vp8_gpu_png_frame", "vp8_gpu_set_transport",
     "vp8_gpu_set_cluster", "vp8_gpu_last_cluster", "vp8_gpu_last_groups", "vp8_gpu_last_segments",
-    "vp8_gpu_decode_compact", "vp8_gpu_decode_webp", "vp8_gpu_decode_webp_bytes", "vp8_gpu_last_call_profile", "vp8_gpu_bind_host",
+    "vp8_gpu_decode_compact", "vp8_gpu_decode_webp", "vp8_gpu_decode_webp_bytes", "vp8_gpu_last_call_profile", "vp8_gpu_bind_host", "vp8_gpu_last_transport",
 ]
 
 _lib = None
@@ -116,6 +116,7 @@ def load_library() -> C.CDLL:
     L.vp8_gpu_decode_webp_bytes.restype = sz
     L.vp8_gpu_last_call_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.vp8_gpu_bind_host.argtypes = [vp, C.c_int, C.c_int]
+    L.vp8_gpu_last_transport.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.yuv420_alloc.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.yuv420_free.argtypes = [vp]
     L.yuv420_free.restype = None
@@ -239,9 +240,15 @@ class Context:
         """CTAs per image in cluster mode: 0 automatic, 1 never, 2/4/8 upper bound."""
         _check(self._L.vp8_gpu_set_cluster(self._h, ctas_per_image), "vp8_gpu_set_cluster")
 
-    def set_transport(self, compact: bool = True, host_threads: int = 0):
-        """Pipelined calls: ship frames without their all-zero 4x4 blocks (compacted by host threads) or dense."""
-        _check(self._L.vp8_gpu_set_transport(self._h, int(compact), host_threads), "vp8_gpu_set_transport")
+    def set_transport(self, compact=True, host_threads: int = 0):
+        """compact: True / False, or "auto" (chosen chunk by chunk, the library's default)."""
+        mode = 2 if compact == "auto" else int(bool(compact))
+        _check(self._L.vp8_gpu_set_transport(self._h, mode, host_threads), "vp8_gpu_set_transport")
+
+    def last_transport(self):
+        d, c = C.c_int(), C.c_int()
+        _check(self._L.vp8_gpu_last_transport(self._h, C.byref(d), C.byref(c)), "vp8_gpu_last_transport")
+        return {"dense_chunks": d.value, "compact_chunks": c.value}
 
     def sync(self):
         _check(self._L.vp8_gpu_sync(self._h), "vp8_gpu_sync")

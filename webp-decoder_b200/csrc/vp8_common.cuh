@@ -50,6 +50,40 @@ __device__ __forceinline__ int sclamp(int v) { return min(max(v, -128), 127); }
 __device__ __forceinline__ int absdiff(int a, int b) { return (int)__sad(a, b, 0u); }               // VABSDIFF
 __device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
 __device__ __forceinline__ void st32(uint8_t* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
+// Final pixels leave through here. VP8P_STORE_HINT picks the cache operator (measured with ncu dram__bytes_*, profiles/README.md r2):
+// 0 plain st.global, 1 .cg, 2 L2::evict_last policy, 3 .wt, 4 .cs
+#ifndef VP8P_STORE_HINT
+#define VP8P_STORE_HINT 0
+#endif
+__device__ __forceinline__ void st_pix32(uint8_t* p, uint32_t v) {
+#if VP8P_STORE_HINT == 1
+	__stcg(reinterpret_cast<uint32_t*>(p), v);
+#elif VP8P_STORE_HINT == 2
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+#elif VP8P_STORE_HINT == 3
+	__stwt(reinterpret_cast<uint32_t*>(p), v);
+#elif VP8P_STORE_HINT == 4
+	__stcs(reinterpret_cast<uint32_t*>(p), v);
+#else
+	*reinterpret_cast<uint32_t*>(p) = v;
+#endif
+}
+
+// selp: selects the compiler will not turn into branches; the condition is tested inside (sign bit / a bit mask of x)
+__device__ __forceinline__ int sel_neg(uint32_t x, int a, int b) { // (int)x < 0 ? a : b
+	int r;
+	asm("{\n\t.reg .pred q;\n\tsetp.lt.s32 q, %3, 0;\n\tselp.s32 %0, %1, %2, q;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"(x));
+	return r;
+}
+__device__ __forceinline__ int sel_bits(uint32_t x, uint32_t mask, int a, int b) { // (x & mask) ? a : b
+	int r;
+	asm("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %3, %4;\n\tsetp.ne.u32 q, t, 0;\n\tselp.s32 %0, %1, %2, q;\n\t}"
+	    : "=r"(r)
+	    : "r"(a), "r"(b), "r"(x), "r"(mask));
+	return r;
+}
 __device__ __forceinline__ uint32_t sum4(uint32_t w) { return __dp4a(w, 0x01010101u, 0u); }
 
 // 16-byte global -> shared copy that bypasses L1 (coefficients are read exactly once).
@@ -68,7 +102,7 @@ __device__ __noinline__ void put_bytes(uint8_t* d, uint32_t v, uint32_t n) {
 __device__ __forceinline__ void put_word(const OutPlane& o, int ox, int oy, uint32_t v) {
 	if ((uint32_t)oy >= o.h || (uint32_t)ox >= o.w) return;
 	uint8_t* d = o.p + (size_t)oy * o.stride + ox;
-	if (o.word_ok && (uint32_t)ox + 4 <= o.w) st32(d, v);
+	if (o.word_ok && (uint32_t)ox + 4 <= o.w) st_pix32(d, v);
 	else put_bytes(d, v, min(4u, o.w - (uint32_t)ox));
 }
 
@@ -175,15 +209,28 @@ __device__ __forceinline__ bool lf_position(int p3, int& p2, int& p1, int& p0, i
 }
 
 // Filter across a vertical edge: q points at the word holding q0..q3 of this lane's pixel row (4-byte aligned).
+#ifndef VP8P_LF_PRMT
+#define VP8P_LF_PRMT 1 // taps leave and enter their words through PRMT (one instruction per byte) instead of shift + mask
+#endif
 template <int KIND>
 __device__ __forceinline__ void lf_across_columns(uint8_t* q, int lim, int interior, int hev_thr) {
 	uint32_t wp = ld32(q - 4), wq = ld32(q);
+#if VP8P_LF_PRMT
+	int p3 = __byte_perm(wp, 0, 0x4440), p2 = __byte_perm(wp, 0, 0x4441), p1 = __byte_perm(wp, 0, 0x4442), p0 = __byte_perm(wp, 0, 0x4443);
+	int q0 = __byte_perm(wq, 0, 0x4440), q1 = __byte_perm(wq, 0, 0x4441), q2 = __byte_perm(wq, 0, 0x4442), q3 = __byte_perm(wq, 0, 0x4443);
+	if (lf_position<KIND>(p3, p2, p1, p0, q0, q1, q2, q3, lim, interior, hev_thr)) {
+		// every tap is 0..255 again: byte 0 of its register
+		st32(q - 4, __byte_perm(__byte_perm(p3, p2, 0x4040), __byte_perm(p1, p0, 0x4040), 0x5410));
+		st32(q, __byte_perm(__byte_perm(q0, q1, 0x4040), __byte_perm(q2, q3, 0x4040), 0x5410));
+	}
+#else
 	int p3 = wp & 255, p2 = (wp >> 8) & 255, p1 = (wp >> 16) & 255, p0 = wp >> 24;
 	int q0 = wq & 255, q1 = (wq >> 8) & 255, q2 = (wq >> 16) & 255, q3 = wq >> 24;
 	if (lf_position<KIND>(p3, p2, p1, p0, q0, q1, q2, q3, lim, interior, hev_thr)) {
 		st32(q - 4, (uint32_t)p3 | (p2 << 8) | (p1 << 16) | ((uint32_t)p0 << 24));
 		st32(q, (uint32_t)q0 | (q1 << 8) | (q2 << 16) | ((uint32_t)q3 << 24));
 	}
+#endif
 }
 
 // Filter across a horizontal edge: q points at q0 of this lane's pixel column, s = row stride.

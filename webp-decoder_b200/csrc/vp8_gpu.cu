@@ -173,7 +173,10 @@ struct vp8_gpu_ctx {
 	int trace_mallocs = 0, trace_frees = 0;             // device block cache misses / evictions (VP8_GPU_TRACE)
 	double trace_malloc_ms = 0;
 	WorkerPool* pool = nullptr;                         // created by the first pipelined call
-	bool compact_transport = true;                      // pipelined decode ships coefficients without their all-zero blocks
+	int transport_mode = 2;                             // dense frames through the pipelined call: 0 = as they are (DMA), 1 = compacted by
+	                                                    // host threads (all-zero blocks dropped), 2 = chosen chunk by chunk (decode_dense)
+	int last_dense_chunks = 0, last_compact_chunks = 0; // what the last such call chose
+	double link_bytes_per_ms = 50e6;                    // host->device with the other direction busy (tools/pcie_probe.py); VP8_GPU_LINK_GBPS
 	double trace_compact_ms = 0, trace_total_ms = 0, trace_retire_ms = 0; // VP8_GPU_TRACE=1: where a pipelined call spends host time
 };
 
@@ -184,6 +187,7 @@ struct FrameMeta {
 	size_t in_off[9];   // coeff_y, coeff_u, coeff_v, coeff_y2, bmode, ymode, uv_mode, segment_id, has_coeff
 	const uint8_t* span_src = nullptr; // non-null: the arrays sit in one host block, copied with a single transfer
 	size_t span_off = 0, span_bytes = 0;
+	bool span_joined = false;          // ... and that block follows the previous frame's: part of the same transfer
 	bool compact = false;              // compact layout: in_off[0..2] = packed blocks, mb_mask, mb_first (see Vp8ImgDesc)
 	bool has_seg, has_hc;
 	size_t tight_off;   // tight I420 (Y|U|V) within d_tight
@@ -519,11 +523,22 @@ int batch_create(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8De
 		                       hi <= (const uint8_t*)(uintptr_t)f->stats_opaque[22] + f->stats_opaque[23];
 		if (need_coeffs && aligned && one_block && payload) {
 			m.span_src = lo;
-			m.span_off = in;
 			m.span_bytes = (size_t)(hi - lo);
-			for (int k = 0; k < 9; k++) m.in_off[k] = sz[k] ? in + (size_t)(src[k] - lo) : in;
-			in += align_up(m.span_bytes);
+			// A frame whose block starts right behind the previous frame's (a batch parsed into one arena) keeps that
+			// distance on the device, so that the whole run crosses the link as ONE transfer: many per-frame copies ran
+			// at two thirds of the link speed while the other direction was busy (profiles/README.md, r2 transport).
+			const FrameMeta* prev = i ? &b->meta[i - 1] : nullptr;
+			if (prev && prev->span_src && lo >= prev->span_src + prev->span_bytes && lo < prev->span_src + prev->span_bytes + 256 &&
+			    ((size_t)(lo - prev->span_src) & 15) == 0 && is_pinned(lo) && is_pinned(prev->span_src)) {
+				m.span_off = prev->span_off + (size_t)(lo - prev->span_src);
+				m.span_joined = true;
+			} else {
+				m.span_off = align_up(in);
+			}
+			for (int k = 0; k < 9; k++) m.in_off[k] = sz[k] ? m.span_off + (size_t)(src[k] - lo) : m.span_off;
+			in = m.span_off + m.span_bytes;
 		} else {
+			in = align_up(in);
 			for (int k = 0; k < 9; k++) {
 				m.in_off[k] = in;
 				in += align_up(sz[k]);
@@ -548,12 +563,12 @@ int batch_create(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8De
 			for (int k = 0; k < 2; k++) m.any_filter |= m.lf[s][k][0] != 0;
 		b->max_mb_cols = std::max<int>(b->max_mb_cols, m.mb_cols);
 	}
-	b->in_bytes = in;
+	b->in_bytes = align_up(in);
 	b->tight_bytes = tight;
 	b->pad_bytes = pad;
 	b->rgb_bytes = rgb;
 
-	if (dev_alloc(c, in, (void**)&b->d_in) || dev_alloc(c, sizeof(Vp8ImgDesc) * n, (void**)&b->d_desc)) {
+	if (dev_alloc(c, b->in_bytes, (void**)&b->d_in) || dev_alloc(c, sizeof(Vp8ImgDesc) * n, (void**)&b->d_desc)) {
 		batch_destroy(c, b);
 		return -1;
 	}
@@ -563,10 +578,17 @@ int batch_create(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8De
 		const Vp8DecodedFrame* f = fr[i];
 		const size_t mb = (size_t)m.mb_cols * m.mb_rows;
 		if (m.span_src) {
-			if (up.put(b->d_in + m.span_off, m.span_src, m.span_bytes)) {
+			size_t bytes = m.span_bytes;
+			int j = i;
+			while (j + 1 < n && b->meta[j + 1].span_joined) { // the run that starts here
+				j++;
+				bytes = b->meta[j].span_off + b->meta[j].span_bytes - m.span_off;
+			}
+			if (up.put(b->d_in + m.span_off, m.span_src, bytes)) {
 				batch_destroy(c, b);
 				return -1;
 			}
+			i = j;
 			continue;
 		}
 		const void* src[9] = {f->coeff_y, f->coeff_u, f->coeff_v, f->coeff_y2, f->bmode, f->ymode, f->uv_mode, f->segment_id, f->has_coeff};
@@ -1032,8 +1054,9 @@ int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out) {
 	if (const char* w = getenv("VP8_GPU_CLUSTER")) c->tune_cluster = atoi(w);
 	if (const char* w = getenv("VP8_GPU_HOST_THREADS")) c->host_threads = atoi(w);
 	if (const char* w = getenv("VP8_GPU_LOCKSTEP_SMALL")) c->lockstep_small = atoi(w) != 0;
-	if (const char* w = getenv("VP8_GPU_COMPACT")) c->compact_transport = atoi(w) != 0;
+	if (const char* w = getenv("VP8_GPU_COMPACT")) c->transport_mode = std::min(2, std::max(0, atoi(w)));
 	if (const char* w = getenv("VP8_GPU_IMAGES_PER_SM")) c->tune_imgs_per_sm = atoi(w);
+	if (const char* w = getenv("VP8_GPU_LINK_GBPS")) c->link_bytes_per_ms = std::max(1.0, atof(w)) * 1e6;
 	*out = c;
 	return 0;
 }
@@ -1092,7 +1115,7 @@ int vp8_gpu_set_tuning(vp8_gpu_ctx* c, int warps_per_image, int images_per_sm) {
 
 int vp8_gpu_set_transport(vp8_gpu_ctx* c, int compact, int host_threads) {
 	if (!c || host_threads < 0) return fail(EINVAL, "bad transport options");
-	c->compact_transport = compact != 0;
+	c->transport_mode = compact < 0 || compact > 1 ? 2 : compact;
 	c->host_threads = host_threads;
 	return 0;
 }
@@ -1678,8 +1701,9 @@ int batch_create_webp(vp8_gpu_ctx* c, const uint8_t* const* files, const size_t*
 // Chunked pipeline: chunk k's host->device copies, kernels and device->host copy run on internal streams, so the
 // copy engines (one per direction) and the SMs work on different chunks at the same time. Blocking: returns when
 // dst holds every frame. Output layout = the layout of one big batch (frame i at offsets[i], 256-byte aligned).
-// make_chunk(first, count, staging slot, upload stream, &batch) builds and uploads one chunk.
-using ChunkMaker = std::function<int(int, int, int, cudaStream_t, vp8_gpu_batch**)>;
+// make_chunk(first, count, staging slot, upload stream, link_idle, &batch) builds and uploads one chunk; link_idle says
+// whether everything queued on the upload stream so far has already left the host.
+using ChunkMaker = std::function<int(int, int, int, cudaStream_t, bool, vp8_gpu_batch**)>;
 
 static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const ChunkMaker& make_chunk, int filtered, bool want_ppm,
                             uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk) {
@@ -1755,7 +1779,8 @@ static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const 
 		c->trace_retire_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_r0).count();
 		vp8_gpu_batch* b = nullptr;
 		if (timeline) tl_host.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_p0).count());
-		rc = make_chunk(first, cnt, slot, s_up, &b);
+		const bool link_idle = k == 0 || cudaEventQuery(ring[(k - 1) % kDepth].up) == cudaSuccess;
+		rc = make_chunk(first, cnt, slot, s_up, link_idle, &b);
 		if (rc) break;
 		ch.b = b;
 		mark(s_up);
@@ -1832,8 +1857,13 @@ static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const 
 }
 
 // The reference's contract: dense Vp8DecodedFrames in host memory. Which transport carries them is a host question: the
-// compact one needs every frame's 6.7 MB (1080p) read by host threads, the dense one is pure DMA of three times the
-// bytes. With few host threads per GPU (eight ranks sharing one host) the copy engine wins.
+// compact one needs every frame's 6.7 MB (1080p) read by host threads and then moves a third of the bytes, the dense one
+// is pure DMA of all of them and costs the host nothing. Neither resource should wait for the other, so in automatic mode
+// the call keeps two running totals - the time its host threads have spent compacting, and the time the copy engine needs
+// for everything queued so far (bytes / link speed) - and gives the next chunk to whichever side is behind: dense when
+// the host has been the busier one, compact otherwise. Many host threads per GPU: three chunks in four travel compact;
+// few (eight ranks sharing one host): mostly dense. No prediction involved, so nothing to mis-estimate but the link
+// speed, and that only shifts the balance a little.
 static int decode_dense(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n, int filtered,
                         bool want_ppm, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk) {
 	if (!c || !kf || !frames || !dst || n <= 0) return fail(EINVAL, "bad arguments");
@@ -1842,12 +1872,21 @@ static int decode_dense(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, cons
 		if (validate_frame(kf[i], frames[i], true)) return -1;
 		g[i] = {kf[i]->width, kf[i]->height};
 	}
-	const bool compact = c->compact_transport;
+	const int mode = c->transport_mode;
+	c->last_dense_chunks = c->last_compact_chunks = 0;
+	double host_ms = 0, link_ms = 0;
 	return decode_pipelined(
 	    c, g.data(), n,
-	    [&](int first, int cnt, int slot, cudaStream_t s_up, vp8_gpu_batch** out) {
-		    return compact ? batch_create_compact(c, kf + first, frames + first, cnt, slot, s_up, out)
-		                   : batch_create(c, kf + first, frames + first, cnt, true, out, s_up, true);
+	    [&](int first, int cnt, int slot, cudaStream_t s_up, bool, vp8_gpu_batch** out) {
+		    const bool compact = mode == 1 || (mode == 2 && host_ms <= link_ms);
+		    (compact ? c->last_compact_chunks : c->last_dense_chunks)++;
+		    const uint64_t sent0 = c->h2d;
+		    const auto t0 = std::chrono::steady_clock::now();
+		    const int rc = compact ? batch_create_compact(c, kf + first, frames + first, cnt, slot, s_up, out)
+		                           : batch_create(c, kf + first, frames + first, cnt, true, out, s_up, true);
+		    if (compact) host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		    link_ms += (double)(c->h2d - sent0) / c->link_bytes_per_ms;
+		    return rc;
 	    },
 	    filtered, want_ppm, dst, cap, offsets, sizes, chunk);
 }
@@ -1872,7 +1911,7 @@ int vp8_gpu_decode_compact(vp8_gpu_ctx* c, const Vp8CompactFrame* const* frames,
 	}
 	return decode_pipelined(
 	    c, g.data(), n,
-	    [&](int first, int cnt, int slot, cudaStream_t s_up, vp8_gpu_batch** out) { return batch_create_precompact(c, frames + first, cnt, slot, s_up, out); },
+	    [&](int first, int cnt, int slot, cudaStream_t s_up, bool, vp8_gpu_batch** out) { return batch_create_precompact(c, frames + first, cnt, slot, s_up, out); },
 	    ppm ? 1 : filtered, ppm != 0, dst, cap, offsets, sizes, chunk);
 }
 
@@ -1887,7 +1926,7 @@ int vp8_gpu_decode_webp(vp8_gpu_ctx* c, const uint8_t* const* files, const size_
 	}
 	return decode_pipelined(
 	    c, g.data(), n,
-	    [&](int first, int cnt, int slot, cudaStream_t s_up, vp8_gpu_batch** out) {
+	    [&](int first, int cnt, int slot, cudaStream_t s_up, bool, vp8_gpu_batch** out) {
 		    return batch_create_webp(c, files + first, file_sizes + first, g.data() + first, cnt, slot, s_up, out);
 	    },
 	    ppm ? 1 : filtered, ppm != 0, dst, cap, offsets, sizes, chunk);
@@ -1901,6 +1940,13 @@ size_t vp8_gpu_decode_webp_bytes(const uint8_t* const* files, const size_t* file
 		total += ppm ? align_up(kPpmSlot + (size_t)w * h * 3) : align_up((size_t)w * h + 2 * (size_t)((w + 1) / 2) * ((h + 1) / 2));
 	}
 	return total;
+}
+
+int vp8_gpu_last_transport(const vp8_gpu_ctx* c, int* dense_chunks, int* compact_chunks) {
+	if (!c) return fail(EINVAL, "null context");
+	if (dense_chunks) *dense_chunks = c->last_dense_chunks;
+	if (compact_chunks) *compact_chunks = c->last_compact_chunks;
+	return 0;
 }
 
 int vp8_gpu_last_call_profile(const vp8_gpu_ctx* c, double* total_ms, double* host_work_ms, double* wait_ms) {

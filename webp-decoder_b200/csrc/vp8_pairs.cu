@@ -30,6 +30,14 @@
 //     images stay resident per SM although every warp now carries two macroblock workspaces.
 #include "vp8_common.cuh"
 
+#ifndef VP8P_BPRED_V2
+#define VP8P_BPRED_V2 1 // B_PRED step: width-16 mode shuffle, signed residual load, B_DC rounding folded into the reduction, kind as sign bits
+#endif
+#if VP8P_BPRED_V2
+#define VP8P_KIND_CODE(k) ((k) == 1 ? 0x40u : (k) == 2 ? 0x80u : (k) == 3 ? 0xc0u : 0u)
+#else
+#define VP8P_KIND_CODE(k) (k)
+#endif
 #ifndef VP8P_HALF_SKEW
 #define VP8P_HALF_SKEW 64
 #endif
@@ -179,7 +187,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 				const int tap = c_bpred_taps[m * 16 + p], t0 = tap & 15;
 				a = t0; b = t0 + 1; c = (tap & 16) ? t0 : t0 + 2;
 			}
-			btab[i] = (base + a) | ((base + b) << 8) | ((base + c) << 16) | (kind << 24);
+			btab[i] = (base + a) | ((base + b) << 8) | ((base + c) << 16) | (VP8P_KIND_CODE(kind) << 24);
 		}
 	}
 
@@ -298,7 +306,10 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 // a warp whose dependency (stamp of the row above) or next image is not ready yet simply sits the step out, and the
 // loop ends when no warp has work left (__syncthreads_or). Image hand-over inside a group: warps count themselves out
 // (ctl[0]); when all NW have, the group's first warp loads the next descriptor and publishes it (ctl[1]).
-constexpr int kLockMaxGroups = 7;
+#ifndef VP8P_LOCK_GROUPS
+#define VP8P_LOCK_GROUPS 7
+#endif
+constexpr int kLockMaxGroups = VP8P_LOCK_GROUPS;
 constexpr int kLockBarrierEvery = 2; // the lockstep kernel's warps meet every N-th step (measured: 1 -> 14.37 ms, 2 -> 14.11, 4 -> 14.32)
 
 // Per-image values every warp of a group needs but only now and then: kept in shared memory, not in registers.
@@ -377,7 +388,7 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 				const int tap = c_bpred_taps[m * 16 + p], t0 = tap & 15;
 				a = t0; b = t0 + 1; c = (tap & 16) ? t0 : t0 + 2;
 			}
-			btab[i] = (base + a) | ((base + b) << 8) | ((base + c) << 16) | (kind << 24);
+			btab[i] = (base + a) | ((base + b) << 8) | ((base + c) << 16) | (VP8P_KIND_CODE(kind) << 24);
 		}
 	}
 	if (warp == 0 && lane < 2) ctl[lane] = 0;
