@@ -92,11 +92,10 @@ int vp8_gpu_last_cluster(const vp8_gpu_ctx* ctx); /* CTAs per image of the last 
 /* Transport of vp8_gpu_decode_i420 / _ppm (dense Vp8DecodedFrames in). compact = 1: every chunk is shipped without its
  * all-zero 4x4 blocks (per-macroblock presence mask + packed blocks, built by host_threads workers; 0 = all cores, at
  * most 32) - a third of the bytes on the link for typical content, but the host has to read every array once.
- * compact = 0: the dense arrays travel as they are, pure DMA. compact = 2 (default, also any other value): balanced
- * chunk by chunk - the call keeps totals of the time its host threads have spent compacting and of the time the copy
- * engine needs for what it was given (bytes / VP8_GPU_LINK_GBPS, default 50), and hands the next chunk to whichever is
- * behind - so that neither waits for the other. host_threads is also the number of parser threads of
- * vp8_gpu_decode_webp. vp8_gpu_last_transport tells what the last call did. */
+ * compact = 0: the dense arrays travel as they are, pure DMA - the better worker when a GPU has only a few host threads
+ * (eight ranks sharing one host). compact = 2 (default, also any other value): compact when the context may use at
+ * least 8 host threads, dense otherwise. host_threads is also the number of parser threads of vp8_gpu_decode_webp.
+ * vp8_gpu_last_transport tells what the last call did. */
 int vp8_gpu_set_transport(vp8_gpu_ctx* ctx, int compact, int host_threads);
 int vp8_gpu_last_transport(const vp8_gpu_ctx* ctx, int* dense_chunks, int* compact_chunks);
 

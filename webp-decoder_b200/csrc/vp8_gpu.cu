@@ -52,6 +52,7 @@ int fail(int err, const char* what, cudaError_t ce = cudaSuccess) {
 
 constexpr size_t kAlign = 256;
 constexpr size_t kBounceBytes = 32u << 20;
+constexpr int kCompactMinThreads = 8; // automatic transport of dense frames: compact when the context has at least this many host threads
 constexpr int kPpmSlot = 32; // header slot in front of each RGB image; RGB starts 32 bytes into the slot
 constexpr uint64_t kArenaMagic = 0x564138415245414eull; // stats_opaque[21] of frames whose arrays vp8_parse carved from ONE block
                                                         // ([22] = base address, [23] = bytes); same constant in vp8_parse.cpp
@@ -169,6 +170,7 @@ struct vp8_gpu_ctx {
 	int desc_next = 0;
 	uint8_t* cstage[3] = {nullptr, nullptr, nullptr};   // pinned staging of compacted chunks, one per pipeline slot
 	size_t cstage_bytes[3] = {0, 0, 0};
+	size_t cstage_want = 0;                             // biggest staging request so far
 	int host_threads = 0;                               // workers compacting frames (0 = all cores, at most 32)
 	int trace_mallocs = 0, trace_frees = 0;             // device block cache misses / evictions (VP8_GPU_TRACE)
 	double trace_malloc_ms = 0;
@@ -176,7 +178,6 @@ struct vp8_gpu_ctx {
 	int transport_mode = 2;                             // dense frames through the pipelined call: 0 = as they are (DMA), 1 = compacted by
 	                                                    // host threads (all-zero blocks dropped), 2 = chosen chunk by chunk (decode_dense)
 	int last_dense_chunks = 0, last_compact_chunks = 0; // what the last such call chose
-	double link_bytes_per_ms = 50e6;                    // host->device with the other direction busy (tools/pcie_probe.py); VP8_GPU_LINK_GBPS
 	double trace_compact_ms = 0, trace_total_ms = 0, trace_retire_ms = 0; // VP8_GPU_TRACE=1: where a pipelined call spends host time
 };
 
@@ -740,7 +741,9 @@ int plan_launch(const vp8_gpu_ctx* c, int n, int max_mb_cols, int max_rows, int 
 	// 16-warp CTAs are already in use, the GPU would otherwise be mostly idle and the frame has rows to hand out.
 	if (p.warps == 16 && c->tune_cluster != 1) {
 		int want = c->tune_cluster > 1 ? c->tune_cluster : 8;
-		while (want > 1 && (n * want > c->sm_count || 32 * (want - 1) >= max_rows)) want /= 2; // every CTA must get rows
+		// a CTA's 16 warps take 32 macroblock rows; a cluster size stays as long as the GPU has room for it and more than
+		// half of its CTAs get rows (a 1080p frame, 68 rows: 3 of 4 CTAs busy beats 2 CTAs that need a second round)
+		while (want > 1 && (n * want > c->sm_count || 32 * (want / 2) >= max_rows)) want /= 2;
 		p.cluster = want;
 		if (p.cluster > 1) p.grid = std::min(n, c->sm_count / p.cluster) * p.cluster;
 	}
@@ -1056,7 +1059,6 @@ int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out) {
 	if (const char* w = getenv("VP8_GPU_LOCKSTEP_SMALL")) c->lockstep_small = atoi(w) != 0;
 	if (const char* w = getenv("VP8_GPU_COMPACT")) c->transport_mode = std::min(2, std::max(0, atoi(w)));
 	if (const char* w = getenv("VP8_GPU_IMAGES_PER_SM")) c->tune_imgs_per_sm = atoi(w);
-	if (const char* w = getenv("VP8_GPU_LINK_GBPS")) c->link_bytes_per_ms = std::max(1.0, atof(w)) * 1e6;
 	*out = c;
 	return 0;
 }
@@ -1520,6 +1522,10 @@ void compact_meta(FrameMeta& m, const Vp8DecodedFrame* f, size_t head, size_t pa
 }
 
 int stage_reserve(vp8_gpu_ctx* c, int slot, size_t bytes) {
+	// every slot grows to the biggest request any slot has seen: which chunk lands in which slot changes from call to call,
+	// and growing a slot is a cudaHostAlloc of hundreds of megabytes (100 ms and more)
+	c->cstage_want = std::max(c->cstage_want, bytes);
+	bytes = c->cstage_want;
 	if (c->cstage_bytes[slot] >= bytes) return 0;
 	if (c->cstage[slot]) cudaFreeHost(c->cstage[slot]);
 	c->cstage[slot] = nullptr;
@@ -1858,12 +1864,12 @@ static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const 
 
 // The reference's contract: dense Vp8DecodedFrames in host memory. Which transport carries them is a host question: the
 // compact one needs every frame's 6.7 MB (1080p) read by host threads and then moves a third of the bytes, the dense one
-// is pure DMA of all of them and costs the host nothing. Neither resource should wait for the other, so in automatic mode
-// the call keeps two running totals - the time its host threads have spent compacting, and the time the copy engine needs
-// for everything queued so far (bytes / link speed) - and gives the next chunk to whichever side is behind: dense when
-// the host has been the busier one, compact otherwise. Many host threads per GPU: three chunks in four travel compact;
-// few (eight ranks sharing one host): mostly dense. No prediction involved, so nothing to mis-estimate but the link
-// speed, and that only shifts the balance a little.
+// is pure DMA of all of them. Measured (profiles/README.md, r2 transport): with 16+ host threads per GPU compact wins
+// clearly (91 vs 174 ms per 1024 frames: the link is the limit), with 12 it is 166 vs 181 ms (two ranks sharing one
+// host's memory bandwidth), below that the copy engine is the better worker. Automatic mode therefore asks how many
+// host threads this context may use. (A per-chunk balance between the two - give the next chunk to whichever of host
+// and link is behind - was measured too: 109-197 ms; dense chunks slow the compaction threads down, both pull on the same
+// host memory.)
 static int decode_dense(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n, int filtered,
                         bool want_ppm, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk) {
 	if (!c || !kf || !frames || !dst || n <= 0) return fail(EINVAL, "bad arguments");
@@ -1872,21 +1878,15 @@ static int decode_dense(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, cons
 		if (validate_frame(kf[i], frames[i], true)) return -1;
 		g[i] = {kf[i]->width, kf[i]->height};
 	}
-	const int mode = c->transport_mode;
+	const int threads = c->host_threads > 0 ? c->host_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+	const bool compact = c->transport_mode == 1 || (c->transport_mode == 2 && threads >= kCompactMinThreads);
 	c->last_dense_chunks = c->last_compact_chunks = 0;
-	double host_ms = 0, link_ms = 0;
 	return decode_pipelined(
 	    c, g.data(), n,
 	    [&](int first, int cnt, int slot, cudaStream_t s_up, bool, vp8_gpu_batch** out) {
-		    const bool compact = mode == 1 || (mode == 2 && host_ms <= link_ms);
 		    (compact ? c->last_compact_chunks : c->last_dense_chunks)++;
-		    const uint64_t sent0 = c->h2d;
-		    const auto t0 = std::chrono::steady_clock::now();
-		    const int rc = compact ? batch_create_compact(c, kf + first, frames + first, cnt, slot, s_up, out)
-		                           : batch_create(c, kf + first, frames + first, cnt, true, out, s_up, true);
-		    if (compact) host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-		    link_ms += (double)(c->h2d - sent0) / c->link_bytes_per_ms;
-		    return rc;
+		    return compact ? batch_create_compact(c, kf + first, frames + first, cnt, slot, s_up, out)
+		                   : batch_create(c, kf + first, frames + first, cnt, true, out, s_up, true);
 	    },
 	    filtered, want_ppm, dst, cap, offsets, sizes, chunk);
 }

@@ -42,20 +42,15 @@ struct BoolReader {
 		if (avail < 16) refill();
 		const uint32_t split = 1 + (((range - 1) * prob) >> 8);
 		const uint64_t big = (uint64_t)split << 56;
-		int b;
-		if (window >= big) {
-			range -= split;
-			window -= big;
-			b = 1;
-		} else {
-			range = split;
-			b = 0;
-		}
+		// branch-free: the decoded bit is data, not control flow (the token tree branches on it right after anyway)
+		const uint64_t m = (uint64_t)0 - (uint64_t)(window >= big); // all ones when the bit is 1
+		window -= big & m;
+		range = (uint32_t)((split & ~m) | ((range - split) & m));
 		const int shift = __builtin_clz(range) - 24; // renormalise to [128, 255]
 		range <<= shift;
 		window <<= shift;
 		avail -= shift;
-		return b;
+		return (int)(m & 1);
 	}
 	inline uint32_t literal(int bits) {
 		uint32_t v = 0;
