@@ -71,6 +71,8 @@ __device__ __forceinline__ void st_pix32(uint8_t* p, uint32_t v) {
 #endif
 }
 
+__device__ __forceinline__ void st_pix128(uint8_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+
 // selp: selects the compiler will not turn into branches; the condition is tested inside (sign bit / a bit mask of x)
 __device__ __forceinline__ int sel_neg(uint32_t x, int a, int b) { // (int)x < 0 ? a : b
 	int r;

@@ -41,6 +41,14 @@
 #ifndef VP8P_HALF_SKEW
 #define VP8P_HALF_SKEW 64
 #endif
+// vp8_pairs_step_a.inc asks for the filtered rows of the row above here; who owns the two words depends on the loop structure
+#define VP8P_TA_DECL uint32_t ta_y = 0, ta_c = 0;
+#ifndef VP8P_ANTIPHASE
+#define VP8P_ANTIPHASE 0 // lockstep kernel: odd groups run half a step behind the even ones (see vp8_mb_lockstep)
+#endif
+#ifndef VP8P_LOCK_EVERY
+#define VP8P_LOCK_EVERY 2
+#endif
 
 namespace {
 
@@ -58,10 +66,14 @@ struct __align__(16) HalfWs {
 	uint8_t ft_u[12 * 12];
 	uint8_t ft_v[12 * 12];
 	uint4 coef[52];
+	uint8_t so_y[16 * 32];    // output strip, luma: rows -4..11 of a PAIR of macroblocks, i.e. whole 32-byte sectors (vp8_pairs_step_c.inc)
+	uint8_t so_c[2 * 8 * 16]; // output strip, U then V: rows -4..3 of the pair
 	uint8_t skew_[VP8P_HALF_SKEW]; // the two halves of a warp touch the same offsets of their workspaces in the same instruction:
 	                               // with sizeof(HalfWs) = 64 mod 128 they do so on complementary shared-memory banks
 };
-static_assert(sizeof(HalfWs) % 16 == 0 && offsetof(HalfWs, res) % 16 == 0 && offsetof(HalfWs, coef) % 16 == 0, "HalfWs alignment");
+static_assert(sizeof(HalfWs) % 16 == 0 && offsetof(HalfWs, res) % 16 == 0 && offsetof(HalfWs, coef) % 16 == 0 && offsetof(HalfWs, so_y) % 16 == 0 &&
+                  offsetof(HalfWs, so_c) % 16 == 0 && sizeof(HalfWs) % 128 == VP8P_HALF_SKEW,
+              "HalfWs alignment");
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
 	uint32_t r;
@@ -121,6 +133,17 @@ __device__ __forceinline__ void fetch_dense(HalfWs& ws, const Vp8ImgDesc* sd, si
 		cp_async16(&ws.coef[2 * 13 + hl], src + 16);
 		cp_async16(&ws.coef[3 * 13 + hl], src + 24);
 	}
+}
+
+// May this image's pixels leave as whole 32-byte sectors (vp8_pairs_step_c.inc)? Planes and strides 16-byte aligned, width a
+// multiple of 32 (the chroma planes then end on a 16-byte boundary and the number of macroblock columns is even).
+__device__ __forceinline__ bool planes_wide_ok(const Vp8ImgDesc* sd) {
+	const uintptr_t a = reinterpret_cast<uintptr_t>(sd->out_y) | reinterpret_cast<uintptr_t>(sd->out_u) | reinterpret_cast<uintptr_t>(sd->out_v) |
+	                    sd->out_stride_y | sd->out_stride_uv;
+#ifdef VP8P_NO_WIDE_STORES
+	return false;
+#endif
+	return (a & 15) == 0 && (sd->out_w & 31) == 0 && sd->out_w == 16 * sd->mb_cols;
 }
 
 constexpr int kClusterProg = 1024; // progress stamps per image in cluster mode (VP8 frames have at most 1024 macroblock rows)
@@ -232,7 +255,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 
 		int cols, rows;
 		OutPlane oy, ou, ov;
-		bool words_ok, lf_simple;
+		bool words_ok, wide_ok, lf_simple;
 		const uint8_t *g_ymode, *g_seg, *g_hc;
 #include "vp8_pairs_image.inc"
 
@@ -248,6 +271,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 #define VP8P_STEP_ACTIVE true
 #include "vp8_pairs_step_a.inc"
 #include "vp8_pairs_step_b.inc"
+#include "vp8_pairs_step_c.inc"
 #undef VP8P_STEP_ACTIVE
 				}
 			}
@@ -282,6 +306,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 #define VP8P_STEP_ACTIVE true
 #include "vp8_pairs_step_a.inc"
 #include "vp8_pairs_step_b.inc"
+#include "vp8_pairs_step_c.inc"
 #undef VP8P_STEP_ACTIVE
 #undef VP8P_STEP_NO_SPIN
 					if (++t == cols + 2) {
@@ -310,12 +335,12 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 #define VP8P_LOCK_GROUPS 7
 #endif
 constexpr int kLockMaxGroups = VP8P_LOCK_GROUPS;
-constexpr int kLockBarrierEvery = 2; // the lockstep kernel's warps meet every N-th step (measured: 1 -> 14.37 ms, 2 -> 14.11, 4 -> 14.32)
+constexpr int kLockBarrierEvery = VP8P_LOCK_EVERY * (VP8P_ANTIPHASE ? 2 : 1); // the lockstep kernel's warps meet every N-th step (measured: 1 -> 14.37 ms, 2 -> 14.11, 4 -> 14.32); a round is half a step when the groups alternate
 
 // Per-image values every warp of a group needs but only now and then: kept in shared memory, not in registers.
 struct LockImage {
 	OutPlane oy, ou, ov;
-	int all_words, simple;
+	int all_words, wide, simple;
 };
 constexpr int kLockGroupFixed = 256 + 256 + 16 + 96; // progress ring + image descriptor + hand-over counters + LockImage
 static_assert(sizeof(LockImage) <= 96, "LockImage slot");
@@ -325,6 +350,7 @@ __device__ __forceinline__ void lock_image_init(LockImage* gi, const Vp8ImgDesc*
 	gi->ou = OutPlane{sd->out_u, sd->out_stride_uv, ocw, och, ((reinterpret_cast<uintptr_t>(sd->out_u) | sd->out_stride_uv) & 3) == 0};
 	gi->ov = OutPlane{sd->out_v, sd->out_stride_uv, ocw, och, ((reinterpret_cast<uintptr_t>(sd->out_v) | sd->out_stride_uv) & 3) == 0};
 	gi->all_words = gi->oy.word_ok && gi->ou.word_ok && gi->ov.word_ok;
+	gi->wide = planes_wide_ok(sd);
 	gi->simple = sd->lf_simple != 0;
 }
 
@@ -413,6 +439,7 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 	int cols = 0, rows = 0;
 	const OutPlane &oy = gi->oy, &ou = gi->ou, &ov = gi->ov;
 #define words_ok (gi->all_words != 0)
+#define wide_ok (gi->wide != 0)
 #define lf_simple (gi->simple != 0)
 #define g_ymode (sd->ymode)
 #define g_seg (sd->segment_id)
@@ -422,10 +449,22 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 	size_t mb_row0 = 0;
 	uint32_t staged_nz = 0;
 
+#if VP8P_ANTIPHASE
+	// Even groups do [parts A+B | part C] between two barriers, odd groups [part C of the previous step | parts A+B]: while
+	// one half of an SM's warps reconstructs (shared-memory and shuffle latency chains) the other half filters (ALU pipe),
+	// instead of all 28 walking the same phase. What a step hands from B to C crosses the loop edge in carry / ta_y / ta_c.
+	int phase = group & 1;
+	uint32_t carry = 0, ta_y = 0, ta_c = 0;
+#undef VP8P_TA_DECL
+#define VP8P_TA_DECL ta_y = 0, ta_c = 0;
+#else
+	constexpr int phase = 0;
+#endif
+	bool active = false;
 	for (;;) {
 		// ---- what does this warp do in this round? (nothing here blocks, see above)
-		bool active = false;
-		do {
+		if (phase == 0) do {
+			active = false;
 			if (state == ST_DONE) break;
 			if (state == ST_IMAGE) {
 				const long long img = slot + (long long)taken * (gridDim.x * groups);
@@ -484,19 +523,42 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 		//      the barrier instead was measured: slower, 15.5 vs 15.0 ms)
 #define VP8P_STEP_NO_SPIN
 #define VP8P_STEP_ACTIVE active
-		if ((++round_no % kLockBarrierEvery) == 0 && !__syncthreads_or(state != ST_DONE)) break;
+		if ((++round_no % kLockBarrierEvery) == 0 && !__syncthreads_or(state != ST_DONE || active)) break;
+#if VP8P_ANTIPHASE
+		if (active) {
+			if (phase == 0) {
+#include "vp8_pairs_step_a.inc"
+#include "vp8_pairs_step_b.inc"
+				carry = (uint32_t)seg | (bpred ? 4u : 0u) | (inner ? 8u : 0u);
+			} else {
+				const int x = t - 2 * half;
+				const bool v = row_ok && x >= 0 && x < cols, last_col = (x == cols - 1);
+				const int seg = carry & 3;
+				const bool bpred = (carry & 4) != 0, inner = (carry & 8) != 0;
+#include "vp8_pairs_step_c.inc"
+				if (++t == cols + 2) {
+					p += NW;
+					state = ST_ROW;
+				}
+			}
+		}
+		phase ^= 1;
+#else
 		if (active) {
 #include "vp8_pairs_step_a.inc"
 #include "vp8_pairs_step_b.inc"
+#include "vp8_pairs_step_c.inc"
 			if (++t == cols + 2) {
 				p += NW;
 				state = ST_ROW;
 			}
 		}
+#endif
 #undef VP8P_STEP_ACTIVE
 #undef VP8P_STEP_NO_SPIN
 	}
 #undef words_ok
+#undef wide_ok
 #undef lf_simple
 #undef g_ymode
 #undef g_seg
