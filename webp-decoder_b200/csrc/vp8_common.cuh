@@ -144,6 +144,28 @@ __device__ __forceinline__ void idct4x4(const int (&v)[16], int (&r)[16]) {
 	}
 }
 
+// Same transform, result as the residual travels: two int16 per word (row k: r[2k] = columns 0,1; r[2k+1] = columns 2,3).
+// Packing keeps the low 16 bits of each value, which is the reference's int16 store.
+__device__ __forceinline__ void idct4x4_packed(const int (&v)[16], uint32_t (&r)[8]) {
+	int t[16];
+#pragma unroll
+	for (int c = 0; c < 4; c++) {
+		int o0, o1, o2, o3;
+		idct_1d(v[c], v[4 + c], v[8 + c], v[12 + c], o0, o1, o2, o3);
+		t[c] = s16(o0);
+		t[4 + c] = s16(o1);
+		t[8 + c] = s16(o2);
+		t[12 + c] = s16(o3);
+	}
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		int o0, o1, o2, o3;
+		idct_1d(t[4 * k], t[4 * k + 1], t[4 * k + 2], t[4 * k + 3], o0, o1, o2, o3);
+		r[2 * k] = __byte_perm((uint32_t)((o0 + 4) >> 3), (uint32_t)((o1 + 4) >> 3), 0x5410);
+		r[2 * k + 1] = __byte_perm((uint32_t)((o2 + 4) >> 3), (uint32_t)((o3 + 4) >> 3), 0x5410);
+	}
+}
+
 // Reference inv_wht4x4 (vp8_recon.c:80-105).
 __device__ __forceinline__ void iwht4x4(const int (&v)[16], int (&r)[16]) {
 	int t[16];

@@ -221,6 +221,7 @@ struct vp8_gpu_batch {
 	PlaneState state = PLANES_NONE;
 	bool filtered = false, have_rgb = false, have_coeffs = true;
 	int desc_key = -1; // kernel_mode*2 + layout of the descriptors currently on the device
+	int rgbdesc_key = -1; // plane state the RGB descriptors on the device were built for
 	cudaStream_t stream = nullptr; // all work on this batch is issued here (the context's stream unless pipelined)
 	uint8_t* d_scratch = nullptr;  // filtered-row line buffers of the pair kernel (one line set per CTA)
 	size_t scratch_bytes = 0;
@@ -1203,21 +1204,19 @@ int vp8_gpu_filter(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
 	return 0;
 }
 
-int vp8_gpu_rgb(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
-	if (!c || !b) return fail(EINVAL, "bad arguments");
-	if (b->state == PLANES_NONE) return fail(EINVAL, "no planes to convert; run reconstruction first");
-	CU(cudaSetDevice(c->device));
+// RGB arena and work items of the m08 kernel for planes in state `state`, sent on the batch's stream.
+static int push_rgb_descs(vp8_gpu_ctx* c, vp8_gpu_batch* b, int state) {
 	if (!b->d_rgb && dev_alloc(c, b->rgb_bytes, (void**)&b->d_rgb)) return -1;
 	if (!b->d_rgbdesc && dev_alloc(c, sizeof(Vp8RgbDesc) * b->n, (void**)&b->d_rgbdesc)) return -1;
+	if (b->rgbdesc_key == state) return 0;
 	std::vector<Vp8RgbDesc> h(b->n);
-	std::vector<uint32_t> tiles(b->n);
 	for (int i = 0; i < b->n; i++) {
 		const FrameMeta& m = b->meta[i];
 		Vp8RgbDesc& d = h[i];
 		memset(&d, 0, sizeof(d));
 		d.width = m.width;
 		d.height = m.height;
-		if (b->state == PLANES_TIGHT) {
+		if (state == PLANES_TIGHT) {
 			const size_t cw = (m.width + 1) / 2, ch = (m.height + 1) / 2;
 			d.y = b->d_tight + m.tight_off;
 			d.u = d.y + (size_t)m.width * m.height;
@@ -1232,9 +1231,31 @@ int vp8_gpu_rgb(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
 			d.stride_uv = m.mb_cols * 8;
 		}
 		d.rgb = b->d_rgb + m.rgb_off + kPpmSlot;
-		tiles[i] = vp8_rgb_tiles(m.width, m.height);
 	}
 	if (push_table(c, b->d_rgbdesc, h.data(), sizeof(Vp8RgbDesc) * b->n, b->stream)) return -1;
+	b->rgbdesc_key = state;
+	return 0;
+}
+
+// Pipelined calls: everything a chunk's kernels read travels on the UPLOAD stream, in front of the event the kernels wait
+// for. A descriptor table copied on the kernels' own stream is handed to the copy engine only once that event has fired,
+// i.e. behind the arenas of the next chunks the host has queued meanwhile: the first kernels then start 10 ms late
+// (VP8_GPU_TRACE=2 timeline, profiles/README.md r2).
+static int push_tables_ahead(vp8_gpu_ctx* c, vp8_gpu_batch* b, int filtered, bool want_ppm) {
+	if (ensure_planes(c, b, VP8_GPU_TIGHT)) return -1;
+	bool any = false;
+	for (auto& m : b->meta) any |= m.any_filter;
+	if (push_descs(c, b, (filtered && any) ? VP8_K_RECON_FILTER : VP8_K_RECON, VP8_GPU_TIGHT)) return -1;
+	return want_ppm ? push_rgb_descs(c, b, PLANES_TIGHT) : 0;
+}
+
+int vp8_gpu_rgb(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
+	if (!c || !b) return fail(EINVAL, "bad arguments");
+	if (b->state == PLANES_NONE) return fail(EINVAL, "no planes to convert; run reconstruction first");
+	CU(cudaSetDevice(c->device));
+	if (push_rgb_descs(c, b, b->state)) return -1;
+	std::vector<uint32_t> tiles(b->n);
+	for (int i = 0; i < b->n; i++) tiles[i] = vp8_rgb_tiles(b->meta[i].width, b->meta[i].height);
 	std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
 	if (!c->spare.empty()) {
 		ev = c->spare.back();
@@ -1789,6 +1810,9 @@ static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const 
 		rc = make_chunk(first, cnt, slot, s_up, link_idle, &b);
 		if (rc) break;
 		ch.b = b;
+		b->stream = s_up;
+		rc = push_tables_ahead(c, b, filtered, want_ppm);
+		if (rc) break;
 		mark(s_up);
 		if (cudaEventRecord(ch.up, s_up) != cudaSuccess || cudaStreamWaitEvent(s_run, ch.up, 0) != cudaSuccess) {
 			rc = fail(EIO, "pipeline events", cudaGetLastError());

@@ -43,12 +43,6 @@
 #endif
 // vp8_pairs_step_a.inc asks for the filtered rows of the row above here; who owns the two words depends on the loop structure
 #define VP8P_TA_DECL uint32_t ta_y = 0, ta_c = 0;
-#ifndef VP8P_ANTIPHASE
-#define VP8P_ANTIPHASE 0 // lockstep kernel: odd groups run half a step behind the even ones (see vp8_mb_lockstep)
-#endif
-#ifndef VP8P_LOCK_EVERY
-#define VP8P_LOCK_EVERY 2
-#endif
 
 namespace {
 
@@ -140,9 +134,6 @@ __device__ __forceinline__ void fetch_dense(HalfWs& ws, const Vp8ImgDesc* sd, si
 __device__ __forceinline__ bool planes_wide_ok(const Vp8ImgDesc* sd) {
 	const uintptr_t a = reinterpret_cast<uintptr_t>(sd->out_y) | reinterpret_cast<uintptr_t>(sd->out_u) | reinterpret_cast<uintptr_t>(sd->out_v) |
 	                    sd->out_stride_y | sd->out_stride_uv;
-#ifdef VP8P_NO_WIDE_STORES
-	return false;
-#endif
 	return (a & 15) == 0 && (sd->out_w & 31) == 0 && sd->out_w == 16 * sd->mb_cols;
 }
 
@@ -335,7 +326,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 #define VP8P_LOCK_GROUPS 7
 #endif
 constexpr int kLockMaxGroups = VP8P_LOCK_GROUPS;
-constexpr int kLockBarrierEvery = VP8P_LOCK_EVERY * (VP8P_ANTIPHASE ? 2 : 1); // the lockstep kernel's warps meet every N-th step (measured: 1 -> 14.37 ms, 2 -> 14.11, 4 -> 14.32); a round is half a step when the groups alternate
+constexpr int kLockBarrierEvery = 2; // the lockstep kernel's warps meet every N-th step (measured: 1 -> 14.37 ms, 2 -> 14.11, 4 -> 14.32)
 
 // Per-image values every warp of a group needs but only now and then: kept in shared memory, not in registers.
 struct LockImage {
@@ -449,22 +440,10 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 	size_t mb_row0 = 0;
 	uint32_t staged_nz = 0;
 
-#if VP8P_ANTIPHASE
-	// Even groups do [parts A+B | part C] between two barriers, odd groups [part C of the previous step | parts A+B]: while
-	// one half of an SM's warps reconstructs (shared-memory and shuffle latency chains) the other half filters (ALU pipe),
-	// instead of all 28 walking the same phase. What a step hands from B to C crosses the loop edge in carry / ta_y / ta_c.
-	int phase = group & 1;
-	uint32_t carry = 0, ta_y = 0, ta_c = 0;
-#undef VP8P_TA_DECL
-#define VP8P_TA_DECL ta_y = 0, ta_c = 0;
-#else
-	constexpr int phase = 0;
-#endif
-	bool active = false;
 	for (;;) {
 		// ---- what does this warp do in this round? (nothing here blocks, see above)
-		if (phase == 0) do {
-			active = false;
+		bool active = false;
+		do {
 			if (state == ST_DONE) break;
 			if (state == ST_IMAGE) {
 				const long long img = slot + (long long)taken * (gridDim.x * groups);
@@ -523,27 +502,7 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 		//      the barrier instead was measured: slower, 15.5 vs 15.0 ms)
 #define VP8P_STEP_NO_SPIN
 #define VP8P_STEP_ACTIVE active
-		if ((++round_no % kLockBarrierEvery) == 0 && !__syncthreads_or(state != ST_DONE || active)) break;
-#if VP8P_ANTIPHASE
-		if (active) {
-			if (phase == 0) {
-#include "vp8_pairs_step_a.inc"
-#include "vp8_pairs_step_b.inc"
-				carry = (uint32_t)seg | (bpred ? 4u : 0u) | (inner ? 8u : 0u);
-			} else {
-				const int x = t - 2 * half;
-				const bool v = row_ok && x >= 0 && x < cols, last_col = (x == cols - 1);
-				const int seg = carry & 3;
-				const bool bpred = (carry & 4) != 0, inner = (carry & 8) != 0;
-#include "vp8_pairs_step_c.inc"
-				if (++t == cols + 2) {
-					p += NW;
-					state = ST_ROW;
-				}
-			}
-		}
-		phase ^= 1;
-#else
+		if ((++round_no % kLockBarrierEvery) == 0 && !__syncthreads_or(state != ST_DONE)) break;
 		if (active) {
 #include "vp8_pairs_step_a.inc"
 #include "vp8_pairs_step_b.inc"
@@ -553,7 +512,6 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 				state = ST_ROW;
 			}
 		}
-#endif
 #undef VP8P_STEP_ACTIVE
 #undef VP8P_STEP_NO_SPIN
 	}
