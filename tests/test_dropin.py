@@ -26,3 +26,30 @@ def test_reference_cli_linked_against_libvp8gpu(golden, tmp_path):
             assert hashlib.sha256(out.read_bytes()).hexdigest() == golden[n][key], (n, flag)
             checked += 1
     assert checked == 4 * len(picks) >= 12
+
+
+def test_reference_encoder_cli_linked_against_libvp8gpu(oracle, tmp_path):
+    """The encoder-side drop-in (oracle/Makefile target _ref/encoder_gpu): the reference's unmodified encoder_main.c and
+    modules with the whole-macroblock in-loop front ends taken from libvp8gpu.so. Its .webp files for --mode dc and
+    --mode i16 must equal the reference encoder's byte for byte; --mode bpred (still the reference's own code in that
+    binary) shows the rest of the program is untouched."""
+    import numpy as np
+    gpu, ref = REF_DIR / "encoder_gpu", REF_DIR / "encoder"
+    if not gpu.exists() or not ref.exists():
+        pytest.skip("oracle/_ref/encoder_gpu not built (needs /root/reference at build time)")
+    rng = np.random.default_rng(11)
+    checked = 0
+    for (w, h), q in (((77, 45), 60), ((16, 16), 5), ((130, 97), 90), ((1, 1), 50)):
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if q != 90 else np.tile(np.arange(w, dtype=np.uint8)[None, :, None] * 2, (h, 1, 3))
+        src = tmp_path / f"in_{w}x{h}.png"
+        src.write_bytes(bytes(oracle.png(np.ascontiguousarray(rgb).reshape(-1), w, h)))
+        for mode in ("dc", "i16", "bpred"):
+            outs = []
+            for exe in (ref, gpu):
+                out = tmp_path / f"{exe.name}_{mode}.webp"
+                r = subprocess.run([str(exe), "--q", str(q), "--mode", mode, "--loopfilter", str(src), str(out)], capture_output=True, text=True)
+                assert r.returncode == 0, (exe.name, mode, r.stderr)
+                outs.append(out.read_bytes())
+            assert outs[0] == outs[1], (w, h, q, mode)
+            checked += 1
+    assert checked == 12

@@ -45,6 +45,9 @@ EXPORTS = [
     "vp8_gpu_png_bound", "vp8_gpu_png_frame", "vp8_gpu_set_transport",
     "vp8_gpu_set_cluster", "vp8_gpu_last_cluster", "vp8_gpu_last_groups", "vp8_gpu_last_segments",
     "vp8_gpu_decode_compact", "vp8_gpu_decode_webp", "vp8_gpu_decode_webp_bytes", "vp8_gpu_last_call_profile", "vp8_gpu_bind_host", "vp8_gpu_last_transport",
+    # encoder in-loop reconstruction (include/vp8_enc.h)
+    "enc_vp8_encode_dc_pred_inloop", "enc_vp8_encode_i16x16_uv_sad_inloop", "enc_vp8_encode_i16x16_sad_inloop",
+    "vp8_gpu_enc_i16_inloop", "vp8_gpu_enc_mb_total", "vp8_gpu_enc_last_kernel_ms",
 ]
 
 _lib = None

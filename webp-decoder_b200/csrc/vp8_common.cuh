@@ -270,9 +270,11 @@ __device__ __forceinline__ void lf_across_rows(uint8_t* q, int s, int lim, int i
 		q[-s] = (uint8_t)p0;
 		q[0] = (uint8_t)q0;
 		if (KIND != EDGE_SIMPLE) {
-			q[-3 * s] = (uint8_t)p2;
 			q[-2 * s] = (uint8_t)p1;
 			q[s] = (uint8_t)q1;
+		}
+		if (KIND == EDGE_MB) { // only the macroblock-edge filter reaches the third pixel (vp8_loopfilter.c:84-104)
+			q[-3 * s] = (uint8_t)p2;
 			q[2 * s] = (uint8_t)q2;
 		}
 	}

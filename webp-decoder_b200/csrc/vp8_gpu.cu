@@ -1029,6 +1029,8 @@ int png_frame(const uint8_t* rgb, uint32_t w, uint32_t h, std::vector<uint8_t>& 
 extern "C" {
 
 const char* vp8_gpu_last_error(void) { return g_err.c_str(); }
+// for the library's other translation units (vp8_enc.cu): errno, the text above, -1
+int vp8_set_error(int err, const char* what, int cuda_error) { return fail(err, what, (cudaError_t)cuda_error); }
 
 int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out) {
 	if (!out) return fail(EINVAL, "null out");
