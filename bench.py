@@ -577,6 +577,41 @@ def other_configs(ctx, W, P, S, torch, dist, world, rank, local, stream, job_max
         host_out.close()
         cf.free()
         ctx.trim()
+
+    # ---- the encoder's in-loop reconstruction (whole-macroblock mode search), 1080p pictures per launch
+    enc_gold = ROOT / "tests" / "golden" / "enc.json"
+    if enc_gold.exists():
+        sys.path.insert(0, str(ROOT / "tests"))
+        from encfix import digest as enc_digest, picture as enc_picture
+        from webp_decoder_b200 import enc as E
+        gd = json.loads(enc_gold.read_text())
+        base = [enc_picture(900, 1920, 1080, 0), enc_picture(901, 1920, 1080, 1)]
+        keys = ["900_1920x1080_k0_q75_s1", "901_1920x1080_k1_q75_s1"]
+        n_pic = args.enc_batch
+        pics = [base[i % 2] for i in range(n_pic)]
+        E.encode_batch(pics, 75, 1, device=local)
+        sync_all()
+        t0 = time.perf_counter()
+        outs, qi = E.encode_batch(pics, 75, 1, device=local)
+        sync_all()
+        wall = job_max((time.perf_counter() - t0) * 1e3)
+        k_ms = job_max(E.last_kernel_ms())
+        ok = all(enc_digest(o["coeffs"], o["y_modes"], o["uv_modes"]) == gd[keys[i % 2]]["digest"] and qi == gd[keys[i % 2]]["qindex"]
+                 for i, o in enumerate(outs))
+        px = n_pic * 1920 * 1080
+        out["encoder_inloop_i16"] = {"value": world * px / (k_ms / 1e3) / 1e6, "unit": "Mpixel/s", "kernel_ms": k_ms, "pictures_per_gpu": n_pic,
+                                     "e2e": {"value": world * px / (wall / 1e3) / 1e6, "unit": "Mpixel/s", "ms_per_step": wall,
+                                             "h2d_bytes_per_step": n_pic * 3110400, "d2h_bytes_per_step": n_pic * 8160 * 802,
+                                             "note": "pageable numpy planes in, coefficients and modes out (vp8_gpu_enc_i16_inloop)"},
+                                     "bit_exact_all_pictures_vs_reference_digests": ok,
+                                     "note": "enc_vp8_encode_i16x16_uv_sad_inloop (reference enc_recon.c:1189-1483) for 1920x1080 noise / gradient "
+                                             "pictures, quality 75: mode search + forward transforms + quantisation + reconstruction, one kernel"}
+        if rank == 0 and not args.no_cpu_baseline:
+            r = subprocess.run([sys.executable, str(ROOT / "oracle" / "cpu_baseline.py"), "--encoder", "--seconds", "4"], capture_output=True, text=True)
+            try:
+                out["encoder_inloop_i16"]["cpu_baseline"] = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception:
+                out["encoder_inloop_i16"]["cpu_baseline"] = {"unavailable": (r.stderr or r.stdout)[-200:]}
     return out
 
 
@@ -596,6 +631,7 @@ def main():
     ap.add_argument("--transport", default="auto", choices=["auto", "compact", "dense"], help="how e2e (dense contract) crosses the link")
     ap.add_argument("--webp-batch", type=int, default=256, help="frames per step of the e2e_from_webp leg (parser-bound: seconds per step)")
     ap.add_argument("--mixed-copies", type=int, default=2, help="config 5: copies of the 48-file mixed set per step")
+    ap.add_argument("--enc-batch", type=int, default=64, help="encoder row: 1080p pictures per GPU per launch")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -80,9 +80,11 @@ class EncReference:
     def available(cls):
         return cls.SO.exists()
 
+    class Img(C.Structure):  # reference src/enc-m04_yuv/enc_rgb_to_yuv.h:9-17
+        _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("y_stride", C.c_uint32), ("uv_stride", C.c_uint32),
+                    ("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p)]
+
     def __init__(self):
-        from webp_decoder_b200.enc import EncYuv420Image
-        self.Img = EncYuv420Image
         self.lib = C.CDLL(str(self.SO))
         self.libc = C.CDLL(None)
         self.libc.free.argtypes = [C.c_void_p]

@@ -30,14 +30,8 @@
 //     images stay resident per SM although every warp now carries two macroblock workspaces.
 #include "vp8_common.cuh"
 
-#ifndef VP8P_BPRED_V2
-#define VP8P_BPRED_V2 1 // B_PRED step: width-16 mode shuffle, signed residual load, B_DC rounding folded into the reduction, kind as sign bits
-#endif
-#if VP8P_BPRED_V2
+// B_PRED lane table, byte 3: what a sub-block mode needs besides its three taps, as bits the step can test directly
 #define VP8P_KIND_CODE(k) ((k) == 1 ? 0x40u : (k) == 2 ? 0x80u : (k) == 3 ? 0xc0u : 0u)
-#else
-#define VP8P_KIND_CODE(k) (k)
-#endif
 #ifndef VP8P_HALF_SKEW
 #define VP8P_HALF_SKEW 64
 #endif
