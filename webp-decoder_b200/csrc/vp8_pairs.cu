@@ -183,7 +183,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 	static_assert(sizeof(Vp8ImgDesc) <= 256, "descriptor must fit its shared-memory slot");
 	static_assert(4 * NW <= kProgRing, "progress ring too small");
 
-	// B_PRED lane table, see vp8_kernels.cu: btab[half][mode 0..10][pixel] = lane(a) | lane(b)<<8 | lane(c)<<16 | kind<<24
+	// B_PRED lane table: btab[half][mode 0..10][pixel] = lane(a) | lane(b)<<8 | lane(c)<<16 | kind<<24
 	if (RECON) {
 		for (int i = tid; i < kBtabWords; i += NW * 32) {
 			const int h = i / 176, m = (i % 176) / 16, p = i % 16, base = h * 16;
