@@ -58,7 +58,8 @@ typedef struct vp8_gpu_batch vp8_gpu_batch; /* n frames resident on the device *
 /* Environment presets read by vp8_gpu_init (each has a setter below; the legacy single-frame entry points, which
  * create their context themselves, can only be steered this way): VP8_GPU_DEVICE, VP8_GPU_KERNEL (2|3),
  * VP8_GPU_WARPS, VP8_GPU_IMAGES_PER_SM, VP8_GPU_CLUSTER, VP8_GPU_COMPACT (0|1|2), VP8_GPU_HOST_THREADS,
- * VP8_GPU_LOCKSTEP_SMALL (0: 8-warp CTAs spin instead of meeting at a barrier), VP8_GPU_NT_STORES (0: host compaction
+ * VP8_GPU_LOCKSTEP_SMALL (0: 8-warp CTAs spin instead of meeting at a barrier), VP8_GPU_DENSE_PASSTHROUGH (0: compact
+ * every frame of a compact chunk), VP8_GPU_NT_STORES (0: host compaction
  * with ordinary stores), VP8_GPU_TRACE (1: host-time split of a pipelined call on stderr, 2: plus a per-chunk device
  * timeline). */
 int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out);
@@ -98,6 +99,11 @@ int vp8_gpu_last_cluster(const vp8_gpu_ctx* ctx); /* CTAs per image of the last 
  * vp8_gpu_last_transport tells what the last call did. */
 int vp8_gpu_set_transport(vp8_gpu_ctx* ctx, int compact, int host_threads);
 int vp8_gpu_last_transport(const vp8_gpu_ctx* ctx, int* dense_chunks, int* compact_chunks);
+/* Inside a compact chunk, a dense frame whose arrays sit in ONE pinned block (vp8_parse arenas) and whose blocks are at
+ * least 75 % non-zero (sampled) is not compacted - the host would read all of it to write nearly as much - but handed to
+ * the copy engine as it is; the kernel reads both layouts in one launch. VP8_GPU_DENSE_PASSTHROUGH=0 turns that off.
+ * Returns how many frames of the last pipelined call crossed that way. */
+int vp8_gpu_last_dense_frames(const vp8_gpu_ctx* ctx);
 
 /* Pinned host memory: frames whose arrays live here are copied to the device without staging. */
 void* vp8_gpu_host_alloc(size_t bytes);

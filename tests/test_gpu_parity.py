@@ -437,6 +437,28 @@ def test_pipelined_chunk_schedule_and_arena_granules(gpu_ctx, oracle, chunk):
         gpu_ctx.set_transport("auto", 0)
 
 
+def test_dense_frames_pass_through_compact_chunks(lib, gpu_ctx, golden):
+    """Compact transport of dense Vp8DecodedFrames: frames from pinned parser arenas whose blocks are mostly non-zero are not
+    compacted but shipped as they are, next to compacted ones in the same chunk and the same launch."""
+    from vp8fix import GOLDEN
+    from webp_decoder_b200 import parse as P
+    names = sorted(n for n in golden if "noise" in n and golden[n]["width"] >= 32)[:6] + sorted(n for n in golden if "noise" not in n)[:14]
+    pf = P.parse_batch([(GOLDEN / "webp" / n).read_bytes() for n in names], pinned=True)
+    kfs, frs = [pf.kfs[i] for i in range(pf.n)], [pf.frames[i] for i in range(pf.n)]
+    try:
+        gpu_ctx.set_transport(True, 3)
+        for filtered, key in ((True, "yuvf"), (False, "yuv")):
+            out = np.full(gpu_ctx.decode_bytes(kfs), 0x33, np.uint8)
+            offs, sizes = gpu_ctx.decode_into(kfs, frs, out, filtered=filtered, chunk=8)
+            bad = [n for n, o, s in zip(names, offs, sizes) if sha(out[int(o):int(o) + int(s)]) != golden[n][key]]
+            assert not bad, (key, bad)
+            passed = gpu_ctx.last_dense_frames()
+            assert 0 < passed < len(names), passed  # some crossed dense, some compact
+    finally:
+        gpu_ctx.set_transport("auto", 0)
+        pf.free()
+
+
 def test_argument_errors(lib, gpu_ctx):
     f = fuzz_frame(5, 64, 64)
     kf, d = f.header(), f.cstruct()

@@ -44,7 +44,7 @@ EXPORTS = [
     "vp8_gpu_decode_i420", "vp8_gpu_decode_ppm", "vp8_gpu_decode_bytes", "vp8_gpu_set_kernel",
     "vp8_gpu_png_bound", "vp8_gpu_png_frame", "vp8_gpu_set_transport",
     "vp8_gpu_set_cluster", "vp8_gpu_last_cluster", "vp8_gpu_last_groups", "vp8_gpu_last_segments",
-    "vp8_gpu_decode_compact", "vp8_gpu_decode_webp", "vp8_gpu_decode_webp_bytes", "vp8_gpu_last_call_profile", "vp8_gpu_bind_host", "vp8_gpu_last_transport",
+    "vp8_gpu_decode_compact", "vp8_gpu_decode_webp", "vp8_gpu_decode_webp_bytes", "vp8_gpu_last_call_profile", "vp8_gpu_bind_host", "vp8_gpu_last_transport", "vp8_gpu_last_dense_frames",
     # encoder in-loop reconstruction (include/vp8_enc.h)
     "enc_vp8_encode_dc_pred_inloop", "enc_vp8_encode_i16x16_uv_sad_inloop", "enc_vp8_encode_i16x16_sad_inloop",
     "vp8_gpu_enc_i16_inloop", "vp8_gpu_enc_mb_total", "vp8_gpu_enc_last_kernel_ms",
@@ -120,6 +120,7 @@ def load_library() -> C.CDLL:
     L.vp8_gpu_last_call_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.vp8_gpu_bind_host.argtypes = [vp, C.c_int, C.c_int]
     L.vp8_gpu_last_transport.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.vp8_gpu_last_dense_frames.argtypes = [vp]
     L.yuv420_alloc.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.yuv420_free.argtypes = [vp]
     L.yuv420_free.restype = None
@@ -247,6 +248,10 @@ class Context:
         """compact: True / False, or "auto" (chosen chunk by chunk, the library's default)."""
         mode = 2 if compact == "auto" else int(bool(compact))
         _check(self._L.vp8_gpu_set_transport(self._h, mode, host_threads), "vp8_gpu_set_transport")
+
+    def last_dense_frames(self):
+        """Frames of the last pipelined call that crossed dense inside compact chunks (vp8_gpu_last_dense_frames)."""
+        return int(self._L.vp8_gpu_last_dense_frames(self._h))
 
     def last_transport(self):
         d, c = C.c_int(), C.c_int()

@@ -179,6 +179,8 @@ struct vp8_gpu_ctx {
 	                                                    // host threads (all-zero blocks dropped), 2 = chosen chunk by chunk (decode_dense)
 	int last_dense_chunks = 0, last_compact_chunks = 0; // what the last such call chose
 	double trace_compact_ms = 0, trace_total_ms = 0, trace_retire_ms = 0; // VP8_GPU_TRACE=1: where a pipelined call spends host time
+	int trace_dense_frames = 0; // frames of the last pipelined call that crossed dense inside compact chunks
+	bool dense_passthrough = true; // VP8_GPU_DENSE_PASSTHROUGH=0 compacts every frame
 };
 
 namespace {
@@ -1059,6 +1061,7 @@ int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out) {
 	if (const char* w = getenv("VP8_GPU_WARPS")) c->tune_warps = atoi(w);
 	if (const char* w = getenv("VP8_GPU_CLUSTER")) c->tune_cluster = atoi(w);
 	if (const char* w = getenv("VP8_GPU_HOST_THREADS")) c->host_threads = atoi(w);
+	if (const char* w = getenv("VP8_GPU_DENSE_PASSTHROUGH")) c->dense_passthrough = atoi(w) != 0;
 	if (const char* w = getenv("VP8_GPU_LOCKSTEP_SMALL")) c->lockstep_small = atoi(w) != 0;
 	if (const char* w = getenv("VP8_GPU_COMPACT")) c->transport_mode = std::min(2, std::max(0, atoi(w)));
 	if (const char* w = getenv("VP8_GPU_IMAGES_PER_SM")) c->tune_imgs_per_sm = atoi(w);
@@ -1574,44 +1577,131 @@ void pool_run(vp8_gpu_ctx* c, int threads, const std::function<void()>& work) {
 	else work();
 }
 
-// (a) dense frames in: compacted by host threads into the pinned staging slot, then one transfer of the bytes in use.
+// A dense frame whose arrays sit in ONE pinned block (vp8_parse arenas mark theirs) and whose blocks are mostly non-zero gains
+// nothing from compaction - the host would read 6.7 MB (1080p) to write nearly as much - so it is handed to the copy engine
+// as it is and the kernel reads it through the dense layout (Vp8ImgDesc::compact = 0 for that image; a chunk may mix).
+// Returns the block [lo, lo + bytes) when the frame qualifies.
+bool dense_passthrough(const Vp8DecodedFrame* f, const uint8_t** lo_out, size_t* bytes_out) {
+	if (f->stats_opaque[21] != kArenaMagic) return false;
+	const size_t mb = (size_t)f->mb_cols * f->mb_rows;
+	const uint8_t* src[9] = {(const uint8_t*)f->coeff_y, (const uint8_t*)f->coeff_u, (const uint8_t*)f->coeff_v, (const uint8_t*)f->coeff_y2,
+	                         f->bmode, f->ymode, f->uv_mode, f->segmentation_enabled ? f->segment_id : nullptr, f->has_coeff};
+	const size_t sz[9] = {mb * 512, mb * 128, mb * 128, mb * 32, mb * 16, mb, mb, mb, mb};
+	const uint8_t *lo = nullptr, *hi = nullptr;
+	for (int k = 0; k < 9; k++) {
+		if (!src[k]) continue;
+		if (!lo || src[k] < lo) lo = src[k];
+		if (!hi || src[k] + sz[k] > hi) hi = src[k] + sz[k];
+	}
+	const uint8_t* base = (const uint8_t*)(uintptr_t)f->stats_opaque[22];
+	if (!lo || lo < base || hi > base + f->stats_opaque[23]) return false;
+	for (int k = 0; k < 4; k++)
+		if ((src[k] - lo) & 15) return false; // cp.async wants 16-byte aligned coefficient blocks
+	// density of the luma blocks of 64 macroblocks spread over the frame (every sample is a cache miss: keep it short)
+	size_t seen = 0, nz = 0;
+	const size_t stride = std::max<size_t>(1, mb / 64);
+	for (size_t i = stride / 2; i < mb; i += stride) {
+		const uint64_t* w = reinterpret_cast<const uint64_t*>(f->coeff_y + i * 256);
+		for (int b = 0; b < 16; b++, w += 4) nz += (w[0] | w[1] | w[2] | w[3]) != 0;
+		seen += 16;
+	}
+	if (!seen || nz * 4 < seen * 3) return false; // under 75 %: compaction pays
+	*lo_out = lo;
+	*bytes_out = (size_t)(hi - lo);
+	return true;
+}
+
+// (a) dense frames in: compacted by host threads into the pinned staging slot, then one transfer of the bytes in use;
+// frames that dense_passthrough() picks cross as they are, behind the compact region of the device arena.
 int batch_create_compact(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* fr, int n, int slot,
                          cudaStream_t st, vp8_gpu_batch** out) {
 	std::vector<FrameGeom> g(n);
+	struct Span {
+		const uint8_t* lo = nullptr;
+		size_t bytes = 0, off = 0;
+	};
+	std::vector<Span> span(n);
+	std::vector<int> todo;
+	todo.reserve(n);
 	size_t in = 0;
+	if (c->dense_passthrough) { // the probes miss the cache: all of the chunk's at once, on the worker threads
+		std::atomic<int> nextp{0};
+		pool_run(c, pool_threads(c, n), [&]() {
+			for (int i; (i = nextp.fetch_add(1)) < n;)
+				if (!dense_passthrough(fr[i], &span[i].lo, &span[i].bytes)) span[i].lo = nullptr;
+		});
+	}
 	for (int i = 0; i < n; i++) {
 		g[i] = {kf[i]->width, kf[i]->height};
+		if (span[i].lo && is_pinned(span[i].lo) && is_pinned(span[i].lo + span[i].bytes - 1)) continue;
+		span[i].lo = nullptr;
+		todo.push_back(i);
 		in += vp8c::shared_bound((size_t)fr[i]->mb_cols * fr[i]->mb_rows);
 	}
 	if (in / 32 > 0xffffffffull) return fail(EINVAL, "compact chunk exceeds the 32-bit block index; use a smaller chunk");
+	const size_t stage_bytes = in;
+	for (int i = 0; i < n; i++)
+		if (span[i].lo) {
+			span[i].off = align_up(in);
+			in = span[i].off + span[i].bytes;
+		}
 	vp8_gpu_batch* b = compact_batch_shell(g.data(), n, st);
 	if (!b) return fail(ENOMEM, "batch");
-	b->in_bytes = in;
-	if (stage_reserve(c, slot, in) || dev_alloc(c, in, (void**)&b->d_in) || dev_alloc(c, sizeof(Vp8ImgDesc) * n, (void**)&b->d_desc)) {
+	b->in_bytes = align_up(in);
+	if ((stage_bytes && stage_reserve(c, slot, stage_bytes)) || dev_alloc(c, b->in_bytes, (void**)&b->d_in) ||
+	    dev_alloc(c, sizeof(Vp8ImgDesc) * n, (void**)&b->d_desc)) {
 		batch_destroy(c, b);
 		return -1;
 	}
-	const auto t_c0 = std::chrono::steady_clock::now();
-	uint8_t* stage = c->cstage[slot];
-	std::atomic<size_t> cursor{0};
-	std::atomic<int> next{0};
-	const int threads = pool_threads(c, n);
-	pool_run(c, threads, [&]() {
-		for (int i; (i = next.fetch_add(1)) < n;) {
-			const size_t head = compact_frame(fr[i], stage, cursor);
-			compact_meta(b->meta[i], fr[i], head, 0);
-			b->meta[i].has_seg = fr[i]->segmentation_enabled && fr[i]->segment_id;
-			b->meta[i].has_hc = fr[i]->has_coeff != nullptr;
+	// the pass-through frames first: the copy engine works on them while the host threads compact the others
+	for (int i = 0; i < n; i++) {
+		if (!span[i].lo) continue;
+		const Vp8DecodedFrame* f = fr[i];
+		FrameMeta& m = b->meta[i];
+		m.compact = false;
+		m.has_seg = f->segmentation_enabled && f->segment_id;
+		m.has_hc = f->has_coeff != nullptr;
+		const uint8_t* src[9] = {(const uint8_t*)f->coeff_y, (const uint8_t*)f->coeff_u, (const uint8_t*)f->coeff_v, (const uint8_t*)f->coeff_y2,
+		                         f->bmode, f->ymode, f->uv_mode, m.has_seg ? f->segment_id : nullptr, f->has_coeff};
+		for (int k = 0; k < 9; k++) m.in_off[k] = span[i].off + (src[k] ? (size_t)(src[k] - span[i].lo) : 0);
+		frame_params(f, m.dq, m.lf);
+		m.lf_simple = f->lf_use_simple;
+		m.any_filter = false;
+		for (int s2 = 0; s2 < (m.has_seg ? 4 : 1); s2++)
+			for (int k = 0; k < 2; k++) m.any_filter |= m.lf[s2][k][0] != 0;
+		cudaError_t e = cudaMemcpyAsync(b->d_in + span[i].off, span[i].lo, span[i].bytes, cudaMemcpyHostToDevice, st);
+		if (e != cudaSuccess) {
+			batch_destroy(c, b);
+			return fail(EIO, "dense frame upload", e);
 		}
-	});
-	c->trace_compact_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_c0).count();
-	const size_t used = cursor.load();
-	cudaError_t e = cudaMemcpyAsync(b->d_in, stage, used, cudaMemcpyHostToDevice, st);
-	if (e != cudaSuccess) {
-		batch_destroy(c, b);
-		return fail(EIO, "compact chunk upload", e);
+		c->h2d += span[i].bytes;
+		c->trace_dense_frames++;
 	}
-	c->h2d += used;
+	if (!todo.empty()) {
+		const auto t_c0 = std::chrono::steady_clock::now();
+		uint8_t* stage = c->cstage[slot];
+		std::atomic<size_t> cursor{0};
+		std::atomic<int> next{0};
+		const int nt = (int)todo.size();
+		const int threads = pool_threads(c, nt);
+		pool_run(c, threads, [&]() {
+			for (int k; (k = next.fetch_add(1)) < nt;) {
+				const int i = todo[k];
+				const size_t head = compact_frame(fr[i], stage, cursor);
+				compact_meta(b->meta[i], fr[i], head, 0);
+				b->meta[i].has_seg = fr[i]->segmentation_enabled && fr[i]->segment_id;
+				b->meta[i].has_hc = fr[i]->has_coeff != nullptr;
+			}
+		});
+		c->trace_compact_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_c0).count();
+		const size_t used = cursor.load();
+		cudaError_t e = cudaMemcpyAsync(b->d_in, stage, used, cudaMemcpyHostToDevice, st);
+		if (e != cudaSuccess) {
+			batch_destroy(c, b);
+			return fail(EIO, "compact chunk upload", e);
+		}
+		c->h2d += used;
+	}
 	*out = b;
 	return 0;
 }
@@ -1777,6 +1867,7 @@ static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const 
 	for (int i = 0; i < kDepth && !rc; i++) rc = make_event(&ring[i].up) || make_event(&ring[i].done);
 	const auto t_p0 = std::chrono::steady_clock::now();
 	c->trace_compact_ms = c->trace_retire_ms = c->trace_malloc_ms = 0;
+	c->trace_dense_frames = 0;
 	c->trace_mallocs = c->trace_frees = 0;
 	cudaStream_t s_up = c->pipe[0], s_down = c->pipe[3];
 	// VP8_GPU_TRACE=2: device-side timeline, four timed events per chunk (upload start/end, kernels end, download end)
@@ -1864,9 +1955,9 @@ static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const 
 	if (getenv("VP8_GPU_TRACE")) {
 		const auto now = std::chrono::steady_clock::now();
 		fprintf(stderr, "[vp8gpu] pipelined call: total %.1f ms, host work on chunks (compaction / gather / parse) %.1f ms, waiting on slots/retiring chunks %.1f ms, final drain %.1f ms, "
-		        "%d cudaMalloc + %d cudaFree %.1f ms\n",
+		        "%d cudaMalloc + %d cudaFree %.1f ms, %d frames passed through dense\n",
 		        std::chrono::duration<double, std::milli>(now - t_p0).count(), c->trace_compact_ms, c->trace_retire_ms,
-		        std::chrono::duration<double, std::milli>(now - t_e0).count(), c->trace_mallocs, c->trace_frees, c->trace_malloc_ms);
+		        std::chrono::duration<double, std::milli>(now - t_e0).count(), c->trace_mallocs, c->trace_frees, c->trace_malloc_ms, c->trace_dense_frames);
 	}
 	if (rc) {
 		errno = saved;
@@ -1974,6 +2065,8 @@ int vp8_gpu_last_transport(const vp8_gpu_ctx* c, int* dense_chunks, int* compact
 	if (compact_chunks) *compact_chunks = c->last_compact_chunks;
 	return 0;
 }
+
+int vp8_gpu_last_dense_frames(const vp8_gpu_ctx* c) { return c ? c->trace_dense_frames : 0; }
 
 int vp8_gpu_last_call_profile(const vp8_gpu_ctx* c, double* total_ms, double* host_work_ms, double* wait_ms) {
 	if (!c) return fail(EINVAL, "null context");
