@@ -466,6 +466,7 @@ def _spot(n):
 def other_configs(ctx, W, P, S, torch, dist, world, rank, local, stream, job_max, sync_all, ppm_done, args):
     """BASELINE.json configs 3, 4, 5, each bounded to a few seconds; every result is byte-checked against the reference
     decoder's digests (bench_data/digests.json, bench_data/mixed/digests.json)."""
+    import numpy as np
     out = {}
     dg = json.loads((ROOT / "bench_data" / "digests.json").read_text())
     peak, _ = measured_peak()
@@ -508,6 +509,49 @@ def other_configs(ctx, W, P, S, torch, dist, world, rank, local, stream, job_max
         del buf
         b.free()
         pf.free()
+        ctx.trim()
+
+    # ---- the -png path (m09, north_star: "-png is a drop-in"): the pipelined -ppm call, then the reference's PNG framing
+    #      (stored deflate, CRC-32, Adler-32) of every picture on the host threads; bytes checked against `decoder -png`
+    if not args.no_e2e:
+        from concurrent.futures import ThreadPoolExecutor
+        names = FRAMES_1080P
+        n_png = args.png_batch
+        cf = P.parse_batch_compact([(ROOT / "bench_data" / names[i % len(names)]).read_bytes() for i in range(len(names))], pinned=True)
+        cfrs = [cf.frame_list()[i % cf.n] for i in range(n_png)]
+        kfs = [cf.kfs[i % cf.n] for i in range(n_png)]
+        host_ppm = W.PinnedBuffer(ctx.decode_bytes(kfs, ppm=True))
+        L = W.load_library()
+        L.vp8_gpu_png_bound.argtypes, L.vp8_gpu_png_bound.restype = [C.c_uint32, C.c_uint32], C.c_size_t
+        L.vp8_gpu_png_frame.argtypes, L.vp8_gpu_png_frame.restype = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p], C.c_size_t
+        bound = L.vp8_gpu_png_bound(1920, 1080)
+        png_out = np.empty((n_png, bound), np.uint8)
+        threads = max(1, len(os.sched_getaffinity(0)))
+        offs = sizes = None
+
+        def frame_png(i):
+            o = int(offs[i]) + int(sizes[i]) - 1920 * 1080 * 3  # RGB behind the PPM header
+            return L.vp8_gpu_png_frame(host_ppm.array[o:].ctypes.data, 1920, 1080, png_out[i].ctypes.data)
+
+        def run_png():
+            nonlocal offs, sizes
+            offs, sizes = ctx.decode_compact_into(cfrs, host_ppm.array, filtered=True, ppm=True, chunk=args.chunk)
+            with ThreadPoolExecutor(threads) as ex:
+                return list(ex.map(frame_png, range(n_png)))
+        run_png()
+        sync_all()
+        t0 = time.perf_counter()
+        lens = run_png()
+        sync_all()
+        ms = job_max((time.perf_counter() - t0) * 1e3)
+        ok = all(hashlib.sha256(png_out[i, :lens[i]]).hexdigest() == dg[names[i % len(names)]]["png"] for i in range(n_png))
+        out["png_1080p_batch"] = {"value": world * n_png * 1920 * 1080 / (ms / 1e3) / 1e6, "unit": "Mpixel/s", "ms_per_step": ms,
+                                  "frames_per_gpu": n_png, "host_threads": threads, "bit_exact_all_frames_vs_reference_digests": ok,
+                                  "note": "compact frames in host memory -> PNG files in host memory: vp8_gpu_decode_compact(ppm) then "
+                                          "vp8_gpu_png_frame per picture on the host threads (6.2 MB of CRC-32 + Adler-32 each); host-bound"}
+        host_ppm.close()
+        cf.free()
+        del png_out
         ctx.trim()
 
     # ---- config 3: one 3840x2160 frame, latency of recon + loop filter (one image per GPU: replicas, no split)
@@ -588,11 +632,22 @@ def other_configs(ctx, W, P, S, torch, dist, world, rank, local, stream, job_max
         base = [enc_picture(900, 1920, 1080, 0), enc_picture(901, 1920, 1080, 1)]
         keys = ["900_1920x1080_k0_q75_s1", "901_1920x1080_k1_q75_s1"]
         n_pic = args.enc_batch
-        pics = [base[i % 2] for i in range(n_pic)]
-        E.encode_batch(pics, 75, 1, device=local)
+        # every picture its own copy in pinned memory, results into pinned memory: the copies are asynchronous DMA
+        pin_in = W.PinnedBuffer(n_pic * 3110400)
+        pics = []
+        for i in range(n_pic):
+            yb, ub, vb = base[i % 2]
+            o = i * 3110400
+            y = pin_in.array[o:o + 2073600].reshape(1080, 1920)
+            u = pin_in.array[o + 2073600:o + 2592000].reshape(540, 960)
+            v = pin_in.array[o + 2592000:o + 3110400].reshape(540, 960)
+            y[:], u[:], v[:] = yb, ub, vb
+            pics.append((y, u, v))
+        pin_out = W.PinnedBuffer(E.batch_out_bytes(pics))
+        E.encode_batch(pics, 75, 1, device=local, out_buffer=pin_out.array)
         sync_all()
         t0 = time.perf_counter()
-        outs, qi = E.encode_batch(pics, 75, 1, device=local)
+        outs, qi = E.encode_batch(pics, 75, 1, device=local, out_buffer=pin_out.array)
         sync_all()
         wall = job_max((time.perf_counter() - t0) * 1e3)
         k_ms = job_max(E.last_kernel_ms())
@@ -602,10 +657,13 @@ def other_configs(ctx, W, P, S, torch, dist, world, rank, local, stream, job_max
         out["encoder_inloop_i16"] = {"value": world * px / (k_ms / 1e3) / 1e6, "unit": "Mpixel/s", "kernel_ms": k_ms, "pictures_per_gpu": n_pic,
                                      "e2e": {"value": world * px / (wall / 1e3) / 1e6, "unit": "Mpixel/s", "ms_per_step": wall,
                                              "h2d_bytes_per_step": n_pic * 3110400, "d2h_bytes_per_step": n_pic * 8160 * 802,
-                                             "note": "pageable numpy planes in, coefficients and modes out (vp8_gpu_enc_i16_inloop)"},
+                                             "note": "pinned planes in, coefficients and modes out into pinned memory (vp8_gpu_enc_i16_inloop)"},
                                      "bit_exact_all_pictures_vs_reference_digests": ok,
                                      "note": "enc_vp8_encode_i16x16_uv_sad_inloop (reference enc_recon.c:1189-1483) for 1920x1080 noise / gradient "
                                              "pictures, quality 75: mode search + forward transforms + quantisation + reconstruction, one kernel"}
+        del outs
+        pin_in.close()
+        pin_out.close()
         if rank == 0 and not args.no_cpu_baseline:
             r = subprocess.run([sys.executable, str(ROOT / "oracle" / "cpu_baseline.py"), "--encoder", "--seconds", "4"], capture_output=True, text=True)
             try:
@@ -631,6 +689,7 @@ def main():
     ap.add_argument("--transport", default="auto", choices=["auto", "compact", "dense"], help="how e2e (dense contract) crosses the link")
     ap.add_argument("--webp-batch", type=int, default=256, help="frames per step of the e2e_from_webp leg (parser-bound: seconds per step)")
     ap.add_argument("--mixed-copies", type=int, default=2, help="config 5: copies of the 48-file mixed set per step")
+    ap.add_argument("--png-batch", type=int, default=256, help="-png leg: 1080p frames per GPU per step")
     ap.add_argument("--enc-batch", type=int, default=64, help="encoder row: 1080p pictures per GPU per launch")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

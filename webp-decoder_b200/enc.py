@@ -80,19 +80,30 @@ def encode_i16x16_uv_sad_inloop(y, u, v, quality):
     return _take(ym.value, nym.value, np.uint8), _take(cm.value, ncm.value, np.uint8), _take(co.value, n.value, np.int16), qi.value
 
 
-def encode_batch(pictures, quality, search, device=-1, want_recon=False):
-    """pictures: [(y, u, v)]. -> list of dicts {coeffs, y_modes, uv_modes[, rec_y, rec_u, rec_v]} and the qindex."""
+def encode_batch(pictures, quality, search, device=-1, want_recon=False, out_buffer=None):
+    """pictures: [(y, u, v)]. -> list of dicts {coeffs, y_modes, uv_modes[, rec_y, rec_u, rec_v]} and the qindex.
+    out_buffer: optional uint8 array (e.g. a PinnedBuffer's, batch_out_bytes() long) the results are laid out in; copies into
+    pinned memory are asynchronous."""
     L = _lib()
     n = len(pictures)
     imgs = [_image(*p) for p in pictures]
     arr = (C.c_void_p * n)(*[C.addressof(i) for i in imgs])
     outs, cols = [], {k: (C.c_void_p * n)() for k in ("coeffs", "y_modes", "uv_modes", "rec_y", "rec_u", "rec_v")}
+    at = 0
+
+    def take(nbytes, dtype):
+        nonlocal at
+        if out_buffer is None:
+            return np.empty(nbytes // np.dtype(dtype).itemsize, dtype)
+        a = out_buffer[at:at + nbytes].view(dtype)
+        at += (nbytes + 255) // 256 * 256
+        return a
     for i, (y, _, _) in enumerate(pictures):
         h, w = y.shape
         mb = L.vp8_gpu_enc_mb_total(w, h)
-        o = {"coeffs": np.empty(mb * 400, np.int16), "y_modes": np.empty(mb, np.uint8), "uv_modes": np.empty(mb, np.uint8)}
+        o = {"coeffs": take(mb * 800, np.int16), "y_modes": take(mb, np.uint8), "uv_modes": take(mb, np.uint8)}
         if want_recon:
-            o.update(rec_y=np.empty(mb * 256, np.uint8), rec_u=np.empty(mb * 64, np.uint8), rec_v=np.empty(mb * 64, np.uint8))
+            o.update(rec_y=take(mb * 256, np.uint8), rec_u=take(mb * 64, np.uint8), rec_v=take(mb * 64, np.uint8))
         for k, a in o.items():
             cols[k][i] = a.ctypes.data
         outs.append(o)
@@ -101,6 +112,17 @@ def encode_batch(pictures, quality, search, device=-1, want_recon=False):
     _check(L.vp8_gpu_enc_i16_inloop(device, arr, n, quality, 1 if search else 0, cols["coeffs"], cols["y_modes"], cols["uv_modes"], *rec,
                                     C.byref(qi)), "vp8_gpu_enc_i16_inloop")
     return outs, qi.value
+
+
+def batch_out_bytes(pictures, want_recon=False):
+    """Bytes encode_batch needs in out_buffer."""
+    L = _lib()
+    total = 0
+    for y, _, _ in pictures:
+        mb = L.vp8_gpu_enc_mb_total(y.shape[1], y.shape[0])
+        for nbytes in (mb * 800, mb, mb) + ((mb * 256, mb * 64, mb * 64) if want_recon else ()):
+            total += (nbytes + 255) // 256 * 256
+    return total
 
 
 def last_kernel_ms():
