@@ -1790,8 +1790,14 @@ int batch_create_webp(vp8_gpu_ctx* c, const uint8_t* const* files, const size_t*
 	std::atomic<size_t> cursor{0};
 	std::atomic<int> next{0}, bad{0}, bad_errno{0};
 	const int threads = pool_threads(c, n);
+	// parse time goes with the file size and differs by two orders of magnitude between files: longest first, so that the
+	// chunk does not end with one thread on a big file and the others idle
+	std::vector<int> order(n);
+	for (int i = 0; i < n; i++) order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return sizes[a] > sizes[b2]; });
 	pool_run(c, threads, [&]() {
-		for (int i; (i = next.fetch_add(1)) < n;) {
+		for (int k; (k = next.fetch_add(1)) < n;) {
+			const int i = order[k];
 			Vp8KeyFrameHeader kf;
 			Vp8CompactFrame cf;
 			if (vp8_parse_webp_shared(files[i], sizes[i], &kf, &cf, stage, in, &cursor) || kf.width != g[i].width || kf.height != g[i].height) {
@@ -1825,7 +1831,7 @@ int batch_create_webp(vp8_gpu_ctx* c, const uint8_t* const* files, const size_t*
 using ChunkMaker = std::function<int(int, int, int, cudaStream_t, bool, vp8_gpu_batch**)>;
 
 static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const ChunkMaker& make_chunk, int filtered, bool want_ppm,
-                            uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk) {
+                            uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk, bool ramp = true) {
 	CU(cudaSetDevice(c->device));
 	if (chunk <= 0) chunk = 64;
 	// global layout
@@ -1888,8 +1894,10 @@ static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const 
 	int k = 0, cnt = 0;
 	for (int first = 0; first < n && !rc; first += cnt, k++) {
 		const int left = n - first, slot = k % 3;
-		cnt = k < 2 ? quarter : k == 2 ? std::max(1, chunk / 2) : chunk;
-		if (left > quarter && left <= cnt + quarter) cnt = left - quarter;
+		// (not when the host is the slow stage - parsing .webp files: a small chunk then only leaves most parser threads idle
+		// behind its longest frame)
+		cnt = !ramp ? chunk : k < 2 ? quarter : k == 2 ? std::max(1, chunk / 2) : chunk;
+		if (ramp && left > quarter && left <= cnt + quarter) cnt = left - quarter;
 		cnt = std::min(cnt, left);
 		cudaStream_t s_run = c->pipe[1 + (k & 1)];
 		Chunk& ch = ring[k % kDepth];
@@ -2046,7 +2054,7 @@ int vp8_gpu_decode_webp(vp8_gpu_ctx* c, const uint8_t* const* files, const size_
 	    [&](int first, int cnt, int slot, cudaStream_t s_up, bool, vp8_gpu_batch** out) {
 		    return batch_create_webp(c, files + first, file_sizes + first, g.data() + first, cnt, slot, s_up, out);
 	    },
-	    ppm ? 1 : filtered, ppm != 0, dst, cap, offsets, sizes, chunk);
+	    ppm ? 1 : filtered, ppm != 0, dst, cap, offsets, sizes, chunk, /*ramp*/ false);
 }
 
 size_t vp8_gpu_decode_webp_bytes(const uint8_t* const* files, const size_t* file_sizes, int n, int ppm) {
