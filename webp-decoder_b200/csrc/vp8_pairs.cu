@@ -76,6 +76,16 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
 	asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Progress stamps that other CTAs of a cluster read: release / acquire at gpu scope instead of a full fence around a plain
+// access (the fence also invalidates L1, which nothing here needs: every cross-CTA read is ld.global.cg).
+__device__ __forceinline__ void st_release_gpu(volatile int* p, int v) {
+	asm volatile("st.release.gpu.s32 [%0], %1;" ::"l"((const int*)p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const volatile int* p) {
+	int v;
+	asm volatile("ld.acquire.gpu.s32 %0, [%1];" : "=r"(v) : "l"((const int*)p) : "memory");
+	return v;
+}
 __device__ __forceinline__ uint32_t ldcg32(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint32_t*>(p)); }
 __device__ __forceinline__ void stcg32(uint8_t* p, uint32_t v) { __stcg(reinterpret_cast<uint32_t*>(p), v); }
 // unfiltered line buffer: shared memory normally, L2 (never L1) when the image is spread over a cluster
