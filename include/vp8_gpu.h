@@ -168,8 +168,10 @@ int vp8_gpu_decode_compact(vp8_gpu_ctx* ctx, const Vp8CompactFrame* const* frame
 /* .webp bytes in, pixels out: the host threads of the context (vp8_gpu_set_transport) run the serial part - container,
  * header, bool decoder and token parsing, one image per thread (the reference's m01 + m02 + m05, main.c:630-664) - straight
  * into the pinned arena of the chunk while the GPU works on the chunks before it. Same acceptance rules as
- * vp8_parse_webp; a file that fails to parse fails the call with its errno. vp8_gpu_decode_webp_bytes gives the
- * capacity needed (0 if a file is not a simple lossy WebP key frame). */
+ * vp8_parse_webp; a file that fails to parse fails the call with its errno. Here every chunk has `chunk` frames (no small
+ * first chunks: the parser threads are the slow stage, and a small chunk leaves most of them idle behind its longest file),
+ * and the files of a chunk are parsed longest first. vp8_gpu_decode_webp_bytes gives the capacity needed (0 if a file is not
+ * a simple lossy WebP key frame). */
 int vp8_gpu_decode_webp(vp8_gpu_ctx* ctx, const uint8_t* const* files, const size_t* file_sizes, int n, int filtered, int ppm,
                         uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk);
 size_t vp8_gpu_decode_webp_bytes(const uint8_t* const* files, const size_t* file_sizes, int n, int ppm);
