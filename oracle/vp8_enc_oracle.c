@@ -296,3 +296,147 @@ int orc_enc_i16_inloop(const uint8_t* y, const uint8_t* u, const uint8_t* v, uin
 	for (int i = 0; i < 3; i++) free(own[i]);
 	return qindex;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * enc_vp8_encode_bpred_uv_sad_inloop (/root/reference/src/enc-m08_recon/enc_recon.c:1507-1831): every macroblock B_PRED.
+ * Chroma: best whole-block mode by SAD (U + V). Luma: the sixteen sub-blocks in raster order, each the best of the ten
+ * 4x4 modes by SAD against predictors built from the reconstruction so far (:197-336), then forward DCT, quantisation with
+ * the y1 steps (no Y2 block: its sixteen coefficients stay zero), dequantisation, inverse DCT, add. */
+static const uint8_t kTap[8][16] = { /* modes 2..9: first tap over E[16], | 0x10 for the two-tap average */
+    {6, 7, 8, 9, 6, 7, 8, 9, 6, 7, 8, 9, 6, 7, 8, 9},
+    {4, 4, 4, 4, 3, 3, 3, 3, 2, 2, 2, 2, 1, 1, 1, 1},
+    {7, 8, 9, 10, 8, 9, 10, 11, 9, 10, 11, 12, 10, 11, 12, 13},
+    {5, 6, 7, 8, 4, 5, 6, 7, 3, 4, 5, 6, 2, 3, 4, 5},
+    {0x16, 0x17, 0x18, 0x19, 5, 6, 7, 8, 4, 0x16, 0x17, 0x18, 3, 5, 6, 7},
+    {0x17, 0x18, 0x19, 0x1a, 7, 8, 9, 10, 0x18, 0x19, 0x1a, 11, 8, 9, 10, 12},
+    {0x15, 5, 6, 7, 0x14, 4, 0x15, 5, 0x13, 3, 0x14, 4, 0x12, 2, 0x13, 3},
+    {0x14, 3, 0x13, 2, 0x13, 2, 0x12, 1, 0x12, 1, 0, 0, 0, 0, 0, 0},
+};
+
+/* E[0..2] = L3, E[3] = L2, E[4] = L1, E[5] = L0, E[6] = P, E[7..14] = A0..A7, E[15] = A7 */
+static void sub_predict(const uint8_t E[16], int mode, uint8_t pred[16]) {
+	for (int p = 0; p < 16; p++) {
+		int v;
+		if (mode == 0) v = (E[7] + E[8] + E[9] + E[10] + E[2] + E[3] + E[4] + E[5] + 4) >> 3;
+		else if (mode == 1) v = clip255(E[5 - (p >> 2)] + E[7 + (p & 3)] - E[6]);
+		else {
+			const int t = kTap[mode - 2][p], i = t & 15;
+			v = (t & 16) ? (E[i] + E[i + 1] + 1) >> 1 : (E[i] + 2 * E[i + 1] + E[i + 2] + 2) >> 2;
+		}
+		pred[p] = (uint8_t)v;
+	}
+}
+
+static uint32_t abs_error(const EncPlane* p, uint32_t x0, uint32_t y0, int n, const uint8_t* pred) {
+	uint32_t e = 0;
+	for (int r = 0; r < n; r++)
+		for (int c = 0; c < n; c++) e += (uint32_t)abs(src_px(p, x0 + c, y0 + r) - pred[r * n + c]);
+	return e;
+}
+
+/* b_modes: mb_total * 16 bytes; y_modes (always 4) and uv_modes: mb_total bytes. Returns the qindex, or -1. */
+int orc_enc_bpred_inloop(const uint8_t* y, const uint8_t* u, const uint8_t* v, uint32_t width, uint32_t height, uint32_t y_stride,
+                         uint32_t uv_stride, int quality, uint8_t* y_modes, uint8_t* b_modes, uint8_t* uv_modes, int16_t* coeffs,
+                         uint8_t* rec_y, uint8_t* rec_u, uint8_t* rec_v) {
+	if (!y || !u || !v || !coeffs || !b_modes || width == 0 || height == 0) return -1;
+	const uint32_t cols = (width + 15) >> 4, rows = (height + 15) >> 4;
+	int q[6];
+	const int qindex = orc_enc_quant(quality, q);
+	uint8_t* own[3] = {NULL, NULL, NULL};
+	if (!rec_y) rec_y = own[0] = (uint8_t*)malloc((size_t)cols * 16 * rows * 16);
+	if (!rec_u) rec_u = own[1] = (uint8_t*)malloc((size_t)cols * 8 * rows * 8);
+	if (!rec_v) rec_v = own[2] = (uint8_t*)malloc((size_t)cols * 8 * rows * 8);
+	if (!rec_y || !rec_u || !rec_v) {
+		for (int i = 0; i < 3; i++) free(own[i]);
+		return -1;
+	}
+	EncPlane pl[3] = {{y, y_stride, width, height, rec_y, cols * 16, 16},
+	                  {u, uv_stride, (width + 1) >> 1, (height + 1) >> 1, rec_u, cols * 8, 8},
+	                  {v, uv_stride, (width + 1) >> 1, (height + 1) >> 1, rec_v, cols * 8, 8}};
+	const uint32_t ys = cols * 16;
+	for (uint32_t my = 0; my < rows; my++)
+		for (uint32_t mx = 0; mx < cols; mx++) {
+			const size_t mb = (size_t)my * cols + mx;
+			int16_t* out = coeffs + mb * 400;
+			memset(out, 0, 400 * sizeof(int16_t));
+			if (y_modes) y_modes[mb] = 4;
+			/* chroma mode: sum of absolute differences over U and V, first minimum */
+			uint8_t pc[2][64], trial[2][64];
+			int cm = 0;
+			uint32_t best = 0xffffffffu;
+			for (int m = 0; m < 4; m++) {
+				predict(&pl[1], mx * 8, my * 8, m, trial[0]);
+				predict(&pl[2], mx * 8, my * 8, m, trial[1]);
+				const uint32_t e = abs_error(&pl[1], mx * 8, my * 8, 8, trial[0]) + abs_error(&pl[2], mx * 8, my * 8, 8, trial[1]);
+				if (e < best) best = e, cm = m;
+			}
+			if (uv_modes) uv_modes[mb] = (uint8_t)cm;
+			predict(&pl[1], mx * 8, my * 8, cm, pc[0]);
+			predict(&pl[2], mx * 8, my * 8, cm, pc[1]);
+			/* luma sub-blocks */
+			for (int sb = 0; sb < 16; sb++) {
+				const uint32_t sx = mx * 16 + (sb & 3) * 4, sy = my * 16 + (sb >> 2) * 4;
+				uint8_t E[16];
+				for (int i = 0; i < 4; i++) E[5 - i] = sx ? rec_y[(size_t)(sy + i) * ys + sx - 1] : 129;
+				E[0] = E[1] = E[2];
+				E[6] = sy == 0 ? 127 : (sx == 0 ? 129 : rec_y[(size_t)(sy - 1) * ys + sx - 1]);
+				for (uint32_t i = 0; i < 8; i++) {
+					int a = 127;
+					if (sy > 0) {
+						uint32_t row = sy - 1, col = sx + i;
+						if ((sb & 3) == 3 && i >= 4) { /* above-right of the last column: always from the macroblock row above */
+							row = my * 16 - 1;
+							col = mx * 16 + 16 + (i - 4);
+						}
+						if (col >= ys) col = ys - 1;
+						a = ((sb & 3) == 3 && i >= 4 && my == 0) ? 127 : rec_y[(size_t)row * ys + col];
+					}
+					E[7 + i] = (uint8_t)a;
+				}
+				E[15] = E[14];
+				uint8_t src[16], pred[16], cand[16];
+				for (int p = 0; p < 16; p++) src[p] = (uint8_t)src_px(&pl[0], sx + (p & 3), sy + (p >> 2));
+				int bm = 0;
+				best = 0xffffffffu;
+				for (int m = 0; m < 10; m++) {
+					sub_predict(E, m, cand);
+					uint32_t e = 0;
+					for (int p = 0; p < 16; p++) e += (uint32_t)abs(src[p] - cand[p]);
+					if (e < best) best = e, bm = m;
+				}
+				b_modes[mb * 16 + sb] = (uint8_t)bm;
+				sub_predict(E, bm, pred);
+				int d[16];
+				int16_t* c16 = out + 16 + 16 * sb, deq[16], res[16];
+				for (int p = 0; p < 16; p++) d[p] = src[p] - pred[p];
+				fdct(d, c16);
+				for (int i = 0; i < 16; i++) {
+					c16[i] = quantise(c16[i], i ? q[1] : q[0]);
+					deq[i] = (int16_t)(c16[i] * (i ? q[1] : q[0]));
+				}
+				idct(deq, res);
+				for (int p = 0; p < 16; p++) rec_y[(size_t)(sy + (p >> 2)) * ys + sx + (p & 3)] = (uint8_t)clip255(pred[p] + res[p]);
+			}
+			/* chroma blocks */
+			for (int k = 1; k < 3; k++)
+				for (int b = 0; b < 4; b++) {
+					const int bx = (b & 1) * 4, by = (b >> 1) * 4;
+					int d[16];
+					int16_t* c16 = out + 16 + 256 + 64 * (k - 1) + 16 * b, deq[16], res[16];
+					for (int r = 0; r < 4; r++)
+						for (int c = 0; c < 4; c++) d[4 * r + c] = src_px(&pl[k], mx * 8 + bx + c, my * 8 + by + r) - pc[k - 1][(by + r) * 8 + bx + c];
+					fdct(d, c16);
+					for (int i = 0; i < 16; i++) {
+						c16[i] = quantise(c16[i], i ? q[3] : q[2]);
+						deq[i] = (int16_t)(c16[i] * (i ? q[3] : q[2]));
+					}
+					idct(deq, res);
+					for (int r = 0; r < 4; r++)
+						for (int c = 0; c < 4; c++)
+							pl[k].rec[(size_t)(my * 8 + by + r) * pl[k].rec_stride + mx * 8 + bx + c] =
+							    (uint8_t)clip255(pc[k - 1][(by + r) * 8 + bx + c] + res[4 * r + c]);
+				}
+		}
+	for (int i = 0; i < 3; i++) free(own[i]);
+	return qindex;
+}

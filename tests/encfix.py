@@ -57,12 +57,24 @@ class EncOracle:
             subprocess.run(["make", "-s", "-C", str(ORACLE_DIR), "oracle"], check=True)
         self.lib = C.CDLL(str(so))
         self.lib.orc_enc_i16_inloop.argtypes = [C.c_void_p] * 3 + [C.c_uint32] * 4 + [C.c_int, C.c_int] + [C.c_void_p] * 6
+        self.lib.orc_enc_bpred_inloop.argtypes = [C.c_void_p] * 3 + [C.c_uint32] * 4 + [C.c_int] + [C.c_void_p] * 7
 
     def run(self, y, u, v, quality, search, want_recon=False):
+        """search: 0 DC, 1 whole-macroblock modes, "bpred" 4x4 sub-block modes."""
         h, w = y.shape
         mb = ((w + 15) // 16) * ((h + 15) // 16)
         co, ym, cm = np.zeros(mb * 400, np.int16), np.zeros(mb, np.uint8), np.zeros(mb, np.uint8)
         rec = [np.zeros(mb * k, np.uint8) for k in (256, 64, 64)] if want_recon else [None] * 3
+        if search == "bpred":
+            bm = np.zeros(mb * 16, np.uint8)
+            qi = self.lib.orc_enc_bpred_inloop(y.ctypes.data, u.ctypes.data, v.ctypes.data, w, h, y.strides[0], u.strides[0], quality,
+                                               ym.ctypes.data, bm.ctypes.data, cm.ctypes.data, co.ctypes.data,
+                                               *[r.ctypes.data if r is not None else None for r in rec])
+            assert qi >= 0
+            out = {"coeffs": co, "y_modes": ym, "uv_modes": cm, "b_modes": bm, "qindex": qi}
+            if want_recon:
+                out.update(rec_y=rec[0], rec_u=rec[1], rec_v=rec[2])
+            return out
         qi = self.lib.orc_enc_i16_inloop(y.ctypes.data, u.ctypes.data, v.ctypes.data, w, h, y.strides[0], u.strides[0], quality, int(search),
                                          ym.ctypes.data, cm.ctypes.data, co.ctypes.data, *[r.ctypes.data if r is not None else None for r in rec])
         assert qi >= 0
@@ -93,6 +105,18 @@ class EncReference:
         h, w = y.shape
         img = self.Img(w, h, y.strides[0], u.strides[0], y.ctypes.data, u.ctypes.data, v.ctypes.data)
         co, n, qi = C.POINTER(C.c_int16)(), C.c_size_t(), C.c_uint8()
+        if search == "bpred":
+            P8 = C.POINTER(C.c_uint8)
+            pym, nym, pbm, nbm, pcm, ncm = P8(), C.c_size_t(), P8(), C.c_size_t(), P8(), C.c_size_t()
+            rc = self.lib.enc_vp8_encode_bpred_uv_sad_inloop(C.byref(img), quality, C.byref(pym), C.byref(nym), C.byref(pbm), C.byref(nbm),
+                                                             C.byref(pcm), C.byref(ncm), C.byref(co), C.byref(n), C.byref(qi))
+            assert rc == 0
+            out = {"coeffs": np.ctypeslib.as_array(co, (n.value,)).copy(), "y_modes": np.ctypeslib.as_array(pym, (nym.value,)).copy(),
+                   "uv_modes": np.ctypeslib.as_array(pcm, (ncm.value,)).copy(), "b_modes": np.ctypeslib.as_array(pbm, (nbm.value,)).copy(),
+                   "qindex": qi.value}
+            for ptr in (pym, pbm, pcm, co):
+                self.libc.free(ptr)
+            return out
         if not search:
             rc = self.lib.enc_vp8_encode_dc_pred_inloop(C.byref(img), quality, C.byref(co), C.byref(n), C.byref(qi))
             assert rc == 0
@@ -111,5 +135,7 @@ class EncReference:
 
 
 def same(a, b, search):
+    if search == "bpred" and not np.array_equal(a["b_modes"], b["b_modes"]):
+        return False
     return (a["qindex"] == b["qindex"] and np.array_equal(a["coeffs"], b["coeffs"])
             and (not search or (np.array_equal(a["y_modes"], b["y_modes"]) and np.array_equal(a["uv_modes"], b["uv_modes"]))))

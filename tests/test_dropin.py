@@ -30,9 +30,9 @@ def test_reference_cli_linked_against_libvp8gpu(golden, tmp_path):
 
 def test_reference_encoder_cli_linked_against_libvp8gpu(oracle, tmp_path):
     """The encoder-side drop-in (oracle/Makefile target _ref/encoder_gpu): the reference's unmodified encoder_main.c and
-    modules with the whole-macroblock in-loop front ends taken from libvp8gpu.so. Its .webp files for --mode dc and
-    --mode i16 must equal the reference encoder's byte for byte; --mode bpred (still the reference's own code in that
-    binary) shows the rest of the program is untouched."""
+    modules with the DC, whole-macroblock and sub-block SAD in-loop front ends taken from libvp8gpu.so. Its .webp files for
+    --mode dc, --mode i16 and --mode bpred must equal the reference encoder's byte for byte; --mode bpred-rdo (still the
+    reference's own code in that binary) shows the rest of the program is untouched."""
     import numpy as np
     gpu, ref = REF_DIR / "encoder_gpu", REF_DIR / "encoder"
     if not gpu.exists() or not ref.exists():
@@ -43,7 +43,7 @@ def test_reference_encoder_cli_linked_against_libvp8gpu(oracle, tmp_path):
         rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if q != 90 else np.tile(np.arange(w, dtype=np.uint8)[None, :, None] * 2, (h, 1, 3))
         src = tmp_path / f"in_{w}x{h}.png"
         src.write_bytes(bytes(oracle.png(np.ascontiguousarray(rgb).reshape(-1), w, h)))
-        for mode in ("dc", "i16", "bpred"):
+        for mode in ("dc", "i16", "bpred", "bpred-rdo"):
             outs = []
             for exe in (ref, gpu):
                 out = tmp_path / f"{exe.name}_{mode}.webp"
@@ -52,4 +52,4 @@ def test_reference_encoder_cli_linked_against_libvp8gpu(oracle, tmp_path):
                 outs.append(out.read_bytes())
             assert outs[0] == outs[1], (w, h, q, mode)
             checked += 1
-    assert checked == 12
+    assert checked == 16

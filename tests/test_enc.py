@@ -27,19 +27,27 @@ def enc_golden():
 
 
 def parse_key(k):
+    """-> seed, w, h, kind, quality, search (0 DC, 1 whole-macroblock modes, "bpred")"""
     seed, size, kind, q, s = k.split("_")
     w, h = size.split("x")
-    return int(seed), int(w), int(h), int(kind[1:]), int(q[1:]), int(s[1:])
+    return int(seed), int(w), int(h), int(kind[1:]), int(q[1:]), {0: 0, 1: 1, 2: "bpred"}[int(s[1:])]
+
+
+def key_digest(r, s):
+    if s == "bpred":
+        return digest(r["coeffs"], r["y_modes"], r["uv_modes"], r["b_modes"])
+    z = np.zeros_like(r["y_modes"])
+    return digest(r["coeffs"], r["y_modes"] if s else z, r["uv_modes"] if s else z)
 
 
 def test_oracle_matches_reference_encoder_digests(enc_oracle, enc_golden):
-    assert len(enc_golden) >= 100
+    assert len(enc_golden) >= 150
     for k, g in enc_golden.items():
         seed, w, h, kind, q, s = parse_key(k)
         if w * h > 1280 * 720:
             continue  # the 1080p entries are for the GPU tests; the scalar oracle takes seconds on each
         r = enc_oracle.run(*picture(seed, w, h, kind), q, s)
-        assert r["qindex"] == g["qindex"] and digest(r["coeffs"], r["y_modes"], r["uv_modes"]) == g["digest"], k
+        assert r["qindex"] == g["qindex"] and key_digest(r, s) == g["digest"], k
 
 
 def test_oracle_matches_reference_encoder_library(enc_oracle):
@@ -48,7 +56,7 @@ def test_oracle_matches_reference_encoder_library(enc_oracle):
     ref = EncReference()
     for seed, w, h, kind, q in cases(40, seed0=5000):
         y, u, v = picture(seed, w, h, kind)
-        for s in (0, 1):
+        for s in (0, 1, "bpred"):
             assert same(ref.run(y, u, v, q, s), enc_oracle.run(y, u, v, q, s), s), (seed, w, h, kind, q, s)
 
 
@@ -63,7 +71,7 @@ def test_library_exports_the_encoder_symbols(lib):
     L = lib.load_library()
     text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "vp8_enc.h").read_text(), flags=re.S)
     syms = sorted(set(re.findall(r"\b((?:enc_vp8|vp8_gpu_enc)\w*)\s*\(", text)))
-    assert len(syms) == 6, syms
+    assert len(syms) == 8, syms
     assert not [s for s in syms if not hasattr(L, s)]
     from webp_decoder_b200.enc import EncYuv420Image
     import ctypes as C
@@ -82,6 +90,10 @@ def test_gpu_reference_entry_points_match_oracle(lib, enc_oracle):
         ym, cm, co, qi = enc.encode_i16x16_uv_sad_inloop(y, u, v, q)
         o = enc_oracle.run(y, u, v, q, 1)
         assert same({"coeffs": co, "y_modes": ym, "uv_modes": cm, "qindex": qi}, o, 1), ("i16", seed, w, h, kind, q)
+        ym, bm, cm, co, qi = enc.encode_bpred_uv_sad_inloop(y, u, v, q)
+        o = enc_oracle.run(y, u, v, q, "bpred")
+        assert same({"coeffs": co, "y_modes": ym, "uv_modes": cm, "b_modes": bm, "qindex": qi}, o, "bpred"), ("bpred", seed, w, h, kind, q)
+        assert (ym == 4).all()
 
 
 @pytest.mark.gpu
@@ -89,7 +101,7 @@ def test_gpu_batch_matches_oracle_with_reconstruction_planes(lib, enc_oracle):
     from webp_decoder_b200 import enc
     cs = cases(40, seed0=300, max_w=260, max_h=200)
     pics = [picture(seed, w, h, kind) for seed, w, h, kind, _ in cs]
-    for s in (0, 1):
+    for s in (0, 1, "bpred"):
         outs, qi = enc.encode_batch(pics, 63, s, want_recon=True)
         for (seed, w, h, kind, _), p, g in zip(cs, pics, outs):
             o = enc_oracle.run(*p, 63, s, want_recon=True)
@@ -105,9 +117,7 @@ def test_gpu_matches_reference_encoder_digests(lib, enc_golden):
     for k, g in enc_golden.items():
         seed, w, h, kind, q, s = parse_key(k)
         outs, qi = enc.encode_batch([picture(seed, w, h, kind)], q, s)
-        r = outs[0]
-        assert qi == g["qindex"] and digest(r["coeffs"], r["y_modes"] if s else np.zeros_like(r["y_modes"]),
-                                            r["uv_modes"] if s else np.zeros_like(r["uv_modes"])) == g["digest"], k
+        assert qi == g["qindex"] and key_digest(outs[0], s) == g["digest"], k
 
 
 @pytest.mark.gpu

@@ -47,7 +47,8 @@ EXPORTS = [
     "vp8_gpu_decode_compact", "vp8_gpu_decode_webp", "vp8_gpu_decode_webp_bytes", "vp8_gpu_last_call_profile", "vp8_gpu_bind_host", "vp8_gpu_last_transport", "vp8_gpu_last_dense_frames",
     # encoder in-loop reconstruction (include/vp8_enc.h)
     "enc_vp8_encode_dc_pred_inloop", "enc_vp8_encode_i16x16_uv_sad_inloop", "enc_vp8_encode_i16x16_sad_inloop",
-    "vp8_gpu_enc_i16_inloop", "vp8_gpu_enc_mb_total", "vp8_gpu_enc_last_kernel_ms",
+    "enc_vp8_encode_bpred_uv_sad_inloop", "vp8_gpu_enc_i16_inloop", "vp8_gpu_enc_bpred_inloop", "vp8_gpu_enc_mb_total",
+    "vp8_gpu_enc_last_kernel_ms",
 ]
 
 _lib = None

@@ -32,6 +32,7 @@ struct EncImgDesc {
 	uint8_t *rec_y, *rec_u, *rec_v;       // reconstruction, macroblock-aligned
 	int16_t* coeffs;                      // mb_total * 400
 	uint8_t *y_modes, *uv_modes;          // mb_total each
+	uint8_t* b_modes;                     // mb_total * 16 (sub-block front end only)
 	uint32_t width, height, mb_cols, mb_rows;
 	int32_t q[6]; // y1dc y1ac uvdc uvac y2dc y2ac
 };
@@ -278,6 +279,232 @@ __global__ void __launch_bounds__(kEncWarps * 32) vp8_enc_i16(const EncImgDesc* 
 	}
 }
 
+
+// ------------------------------------------------------------------------------------------------ 4x4 sub-block front end
+// enc_vp8_encode_bpred_uv_sad_inloop (enc_recon.c:1507-1831): every macroblock B_PRED. Same wavefront, but the luma of a
+// macroblock is sixteen sub-blocks in raster order, each predicted from the reconstruction so far - including the row above
+// up to four pixels to the right of the macroblock (RFC 6386 11.4), so a row trails the row above by TWO macroblocks, as in
+// the decoder. Per sub-block the warp scores all ten modes at once: lanes 0..15 = the pixels under modes 0..4, lanes 16..31
+// under modes 5..9, five REDUX sums carry two modes each.
+struct EncBpWs {
+	uint8_t tile[17 * 24]; // luma of the macroblock being built: row r, column c at (r + 1) * 24 + 4 + c, r = -1..15, c = -1..19
+	uint8_t lcol[32];      // right column of the previous macroblock: Y 0..15, U 16..23, V 24..31
+	uint8_t edge[16];      // the sub-block's edge vector E (vp8_common.cuh: L3 L3 L3 L2 L1 L0 P A0..A7 A7)
+	int16_t buf[16];       // residual -> coefficients -> dequantised -> inverse, between the pixel lanes and lane 0
+	uint8_t bmode[16];
+};
+
+__device__ __forceinline__ int predict_sub_px(int mode, int p, const uint8_t* E) {
+	if (mode == 0) return (E[7] + E[8] + E[9] + E[10] + E[2] + E[3] + E[4] + E[5] + 4) >> 3;
+	if (mode == 1) return clip255(E[5 - (p >> 2)] + E[7 + (p & 3)] - E[6]);
+	const int t = c_bpred_taps[mode * 16 + p], i = t & 15;
+	return (t & 16) ? (E[i] + E[i + 1] + 1) >> 1 : (E[i] + 2 * E[i + 1] + E[i + 2] + 2) >> 2;
+}
+
+__global__ void __launch_bounds__(kEncWarps * 32) vp8_enc_bpred(const EncImgDesc* __restrict__ descs, int n_images) {
+	__shared__ int prog_s[kEncMaxRows];
+	__shared__ EncBpWs ws_s[kEncWarps];
+	volatile int* prog = prog_s;
+	constexpr uint32_t FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	EncBpWs& ws = ws_s[warp];
+
+	// chroma lanes as in vp8_enc_i16: 16..19 U, 20..23 V
+	const int plane = lane < 16 ? 0 : (lane < 20 ? 1 : (lane < 24 ? 2 : 3));
+	const int cb = lane & 3, cbx = (cb & 1) * 4, cby = (cb >> 1) * 4;
+	// luma pixel lanes
+	const int p = lane & 15, pr = p >> 2, pc = p & 3, grp = lane >> 4;
+	const int e_dy = p <= 2 ? 3 : (p <= 5 ? 5 - p : -1), e_dx = p <= 6 ? -1 : (p == 15 ? 7 : p - 7);
+
+	for (int img = blockIdx.x; img < n_images; img += gridDim.x) {
+		__syncthreads();
+		const EncImgDesc& d = descs[img];
+		const int cols = d.mb_cols, rows = d.mb_rows;
+		for (int i = threadIdx.x; i < rows; i += blockDim.x) prog_s[i] = 0;
+		__syncthreads();
+		const int w = (int)d.width, h = (int)d.height, cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+		const int ys = cols * 16, cs = cols * 8;
+		const uint8_t* csrc = plane == 1 ? d.src_u : d.src_v;
+		uint8_t* crec = plane == 1 ? d.rec_u : d.rec_v;
+		uint8_t* const clcol = ws.lcol + (plane == 1 ? 16 : 24);
+
+		for (int row = warp; row < rows; row += kEncWarps) {
+			for (int x = 0; x < cols; x++) {
+				if (row > 0) {
+					if (lane == 0)
+						while (prog[row - 1] < min(x + 2, cols)) __nanosleep(32);
+					__syncwarp();
+					__threadfence();
+				}
+				const bool have_a = row > 0, have_l = x > 0;
+				const int x0 = 16 * x, y0 = 16 * row;
+				const size_t mb = (size_t)row * cols + x;
+				int16_t* const out = d.coeffs + mb * 400;
+
+				// ---- borders of the luma tile: row -1 (columns -1..19) and column -1
+				if (lane < 21) {
+					const int c = lane - 1;
+					int v = 127;
+					if (have_a) v = (c < 0 && !have_l) ? 129 : __ldcg(d.rec_y + (size_t)(y0 - 1) * ys + min(x0 + c, ys - 1));
+					ws.tile[4 + c] = (uint8_t)v;
+					if (c >= 16) ws.tile[4 * 24 + 4 + c] = ws.tile[8 * 24 + 4 + c] = ws.tile[12 * 24 + 4 + c] = (uint8_t)v; // above-right of rows 4, 8, 12
+				}
+				if (lane < 16) ws.tile[(lane + 1) * 24 + 3] = have_l ? ws.lcol[lane] : 129;
+
+				// ---- chroma: mode by sum of absolute differences over U and V (first minimum), then as in vp8_enc_i16
+				uint32_t aw = 0x7f7f7f7fu, lw = 0x81818181u;
+				int cp = have_a ? 129 : 127, part = 0;
+				const bool chroma = plane == 1 || plane == 2;
+				if (chroma) {
+					if (have_a) aw = __ldcg(reinterpret_cast<const uint32_t*>(crec + (size_t)(8 * row - 1) * cs + 8 * x + cbx));
+					if (have_l) lw = *reinterpret_cast<const uint32_t*>(clcol + cby);
+					if (have_a && have_l) cp = __ldcg(crec + (size_t)(8 * row - 1) * cs + 8 * x - 1);
+					if (have_a && cby == 0) part += (int)sum4(aw);
+					if (have_l && cbx == 0) part += (int)sum4(lw);
+				}
+				const uint32_t s_uv = __reduce_add_sync(FULL, plane == 1 ? (uint32_t)part : (plane == 2 ? (uint32_t)part << 16 : 0u));
+				int dc = 128;
+				{
+					int s = plane == 1 ? (int)(s_uv & 0xffffu) : (int)(s_uv >> 16);
+					if (have_a != have_l) s += s;
+					if (have_a || have_l) dc = (s + 8) >> 4;
+				}
+				int sp[16];
+#pragma unroll
+				for (int i = 0; i < 16; i++) sp[i] = 0;
+				if (chroma) {
+#pragma unroll
+					for (int r = 0; r < 4; r++) {
+						const uint8_t* srow = csrc + (size_t)min(8 * row + cby + r, ch - 1) * cw;
+#pragma unroll
+						for (int c = 0; c < 4; c++) sp[4 * r + c] = __ldg(srow + min(8 * x + cbx + c, cw - 1));
+					}
+				}
+				int cmode = 0;
+				{
+					uint32_t best = 0xffffffffu;
+#pragma unroll 1
+					for (int m = 0; m < 4; m++) {
+						int pr4[16];
+						predict4x4(m, dc, aw, lw, cp, pr4);
+						uint32_t e = 0;
+#pragma unroll
+						for (int i = 0; i < 16; i++) e += (uint32_t)abs(sp[i] - pr4[i]);
+						const uint32_t ec = __reduce_add_sync(FULL, chroma ? e : 0u);
+						if (ec < best) best = ec, cmode = m;
+					}
+				}
+				if (chroma) {
+					int pr4[16], cf[16], dd[16];
+					predict4x4(cmode, dc, aw, lw, cp, pr4);
+#pragma unroll
+					for (int i = 0; i < 16; i++) dd[i] = sp[i] - pr4[i];
+					fdct4x4(dd, cf);
+					uint32_t pk[8];
+#pragma unroll
+					for (int i = 0; i < 16; i++) cf[i] = quantise(cf[i], i ? d.q[3] : d.q[2]);
+#pragma unroll
+					for (int i = 0; i < 8; i++) pk[i] = (uint32_t)(cf[2 * i] & 0xffff) | ((uint32_t)cf[2 * i + 1] << 16);
+					uint4* o = reinterpret_cast<uint4*>(out + 16 + (plane == 1 ? 256 : 320) + 16 * cb);
+					o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+					o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+					int deq[16], res[16];
+#pragma unroll
+					for (int i = 0; i < 16; i++) deq[i] = s16(cf[i] * (i ? d.q[3] : d.q[2]));
+					idct4x4(deq, res);
+					uint32_t right = 0;
+#pragma unroll
+					for (int r = 0; r < 4; r++) {
+						uint32_t wv = 0;
+#pragma unroll
+						for (int c = 0; c < 4; c++) wv |= (uint32_t)add_clip255(pr4[4 * r + c], res[4 * r + c]) << (8 * c);
+						__stcg(reinterpret_cast<uint32_t*>(crec + (size_t)(8 * row + cby + r) * cs + 8 * x + cbx), wv);
+						right |= (wv >> 24) << (8 * r);
+					}
+					if (cbx == 4) *reinterpret_cast<uint32_t*>(clcol + cby) = right;
+				}
+				if (lane == 24) { // no Y2 block in a B_PRED macroblock: its sixteen coefficients stay zero
+					reinterpret_cast<uint4*>(out)[0] = make_uint4(0, 0, 0, 0);
+					reinterpret_cast<uint4*>(out)[1] = make_uint4(0, 0, 0, 0);
+					if (d.y_modes) d.y_modes[mb] = 4;
+					if (d.uv_modes) d.uv_modes[mb] = (uint8_t)cmode;
+				}
+				__syncwarp();
+
+				// ---- luma: sixteen sub-blocks in raster order
+#pragma unroll 1
+				for (int sb = 0; sb < 16; sb++) {
+					const int r4 = (sb >> 2) * 4, c4 = (sb & 3) * 4;
+					if (lane < 16) ws.edge[p] = ws.tile[(r4 + e_dy + 1) * 24 + 4 + c4 + e_dx];
+					const int s = __ldg(d.src_y + (size_t)min(y0 + r4 + pr, h - 1) * w + min(x0 + c4 + pc, w - 1));
+					__syncwarp();
+					uint32_t tot[5];
+#pragma unroll
+					for (int k = 0; k < 5; k++) {
+						const uint32_t ad = (uint32_t)abs(s - predict_sub_px(5 * grp + k, p, ws.edge));
+						tot[k] = __reduce_add_sync(FULL, ad << (16 * grp));
+					}
+					int bm = 0;
+					uint32_t best = 0xffffffffu;
+#pragma unroll
+					for (int m = 0; m < 10; m++) {
+						const uint32_t e = m < 5 ? (tot[m] & 0xffffu) : (tot[m - 5] >> 16);
+						if (e < best) best = e, bm = m;
+					}
+					const int pred = predict_sub_px(bm, p, ws.edge);
+					if (lane < 16) ws.buf[p] = (int16_t)(s - pred);
+					__syncwarp();
+					if (lane == 0) {
+						int dd[16], cf[16];
+#pragma unroll
+						for (int i = 0; i < 16; i++) dd[i] = ws.buf[i];
+						fdct4x4(dd, cf);
+#pragma unroll
+						for (int i = 0; i < 16; i++) ws.buf[i] = (int16_t)cf[i];
+						ws.bmode[sb] = (uint8_t)bm;
+					}
+					__syncwarp();
+					if (lane < 16) { // one coefficient per lane: quantise, store, dequantise
+						const int step = lane ? d.q[1] : d.q[0];
+						const int qc = quantise(ws.buf[lane], step);
+						out[16 + 16 * sb + lane] = (int16_t)qc;
+						ws.buf[lane] = (int16_t)(qc * step);
+					}
+					__syncwarp();
+					if (lane == 0) {
+						int deq[16], res[16];
+#pragma unroll
+						for (int i = 0; i < 16; i++) deq[i] = ws.buf[i];
+						idct4x4(deq, res);
+#pragma unroll
+						for (int i = 0; i < 16; i++) ws.buf[i] = (int16_t)res[i];
+					}
+					__syncwarp();
+					if (lane < 16) ws.tile[(r4 + pr + 1) * 24 + 4 + c4 + pc] = (uint8_t)add_clip255(pred, ws.buf[p]);
+					__syncwarp();
+				}
+
+				// ---- the macroblock's luma leaves for the reconstruction plane; right column and modes are kept / stored
+#pragma unroll
+				for (int j = 0; j < 2; j++) {
+					const int i = lane + 32 * j, r = i >> 2, wc = i & 3;
+					__stcg(reinterpret_cast<uint32_t*>(d.rec_y + (size_t)(y0 + r) * ys + x0 + 4 * wc),
+					       *reinterpret_cast<const uint32_t*>(ws.tile + (r + 1) * 24 + 4 + 4 * wc));
+				}
+				if (lane < 16) {
+					ws.lcol[lane] = ws.tile[(lane + 1) * 24 + 4 + 15];
+					d.b_modes[mb * 16 + lane] = ws.bmode[lane];
+				}
+				__syncwarp();
+				if (lane == 0) {
+					__threadfence();
+					prog[row] = x + 1;
+				}
+			}
+		}
+	}
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 // RFC 6386 14.1 (the data of enc_quant.c:15-36) and libwebp's quality -> qindex map (enc_quality_table.c:5-13)
 const uint16_t kDc[128] = {
@@ -360,13 +587,15 @@ int enc_prepare(int device) {
 size_t vp8_gpu_enc_mb_total(uint32_t width, uint32_t height) { return (size_t)((width + 15) >> 4) * ((height + 15) >> 4); }
 double vp8_gpu_enc_last_kernel_ms(void) { return g_enc.last_ms; }
 
-int vp8_gpu_enc_i16_inloop(int device, const EncYuv420Image* const* yuv, int n, int quality, int search, int16_t* const* coeffs,
-                           uint8_t* const* y_modes, uint8_t* const* uv_modes, uint8_t* const* rec_y, uint8_t* const* rec_u,
-                           uint8_t* const* rec_v, uint8_t* qindex_out) {
-	if (!yuv || !coeffs || !qindex_out || n <= 0) return vp8_set_error(EINVAL, "bad arguments", 0);
+// kind: 0 DC prediction, 1 whole-macroblock mode search, 2 sub-block (B_PRED) mode search
+static int enc_run(int device, const EncYuv420Image* const* yuv, int n, int quality, int kind, int16_t* const* coeffs, uint8_t* const* y_modes,
+                   uint8_t* const* b_modes, uint8_t* const* uv_modes, uint8_t* const* rec_y, uint8_t* const* rec_u, uint8_t* const* rec_v,
+                   uint8_t* qindex_out) {
+	if (!yuv || !coeffs || !qindex_out || n <= 0 || (kind == 2 && !b_modes)) return vp8_set_error(EINVAL, "bad arguments", 0);
 	for (int i = 0; i < n; i++) {
 		const EncYuv420Image* im = yuv[i];
-		if (!im || !im->y || !im->u || !im->v || im->width == 0 || im->height == 0 || !coeffs[i]) return vp8_set_error(EINVAL, "bad picture", 0);
+		if (!im || !im->y || !im->u || !im->v || im->width == 0 || im->height == 0 || !coeffs[i] || (kind == 2 && !b_modes[i]))
+			return vp8_set_error(EINVAL, "bad picture", 0);
 		if (im->width > 16383 || im->height > 16383) return vp8_set_error(EINVAL, "picture too large", 0);
 		if (im->y_stride < im->width || im->uv_stride < (im->width + 1) / 2) return vp8_set_error(EINVAL, "bad stride", 0);
 	}
@@ -378,7 +607,7 @@ int vp8_gpu_enc_i16_inloop(int device, const EncYuv420Image* const* yuv, int n, 
 
 	// ---- device layout: per picture [src y|u|v][rec y|u|v][coeffs][y_modes][uv_modes], then the descriptors
 	struct Off {
-		size_t src[3], rec[3], coeffs, ym, cm;
+		size_t src[3], rec[3], coeffs, ym, cm, bm;
 	};
 	std::vector<Off> off(n);
 	size_t total = 0;
@@ -395,6 +624,7 @@ int vp8_gpu_enc_i16_inloop(int device, const EncYuv420Image* const* yuv, int n, 
 		o.coeffs = total, total += up256(mb * 800);
 		o.ym = total, total += up256(mb);
 		o.cm = total, total += up256(mb);
+		o.bm = total, total += kind == 2 ? up256(mb * 16) : 0;
 	}
 	const size_t desc_off = total;
 	total += up256(sizeof(EncImgDesc) * (size_t)n);
@@ -432,6 +662,7 @@ int vp8_gpu_enc_i16_inloop(int device, const EncYuv420Image* const* yuv, int n, 
 		d.coeffs = reinterpret_cast<int16_t*>(s.dev + off[i].coeffs);
 		d.y_modes = s.dev + off[i].ym;
 		d.uv_modes = s.dev + off[i].cm;
+		d.b_modes = s.dev + off[i].bm;
 		d.width = w;
 		d.height = hgt;
 		d.mb_cols = (w + 15) >> 4;
@@ -443,8 +674,10 @@ int vp8_gpu_enc_i16_inloop(int device, const EncYuv420Image* const* yuv, int n, 
 	// ---- one launch: a CTA per picture, as many resident CTAs as the device holds
 	const int grid = std::min(n, s.sm_count * 4);
 	ECU(cudaEventRecord(s.ev0, s.stream));
-	if (search) vp8_enc_i16<true><<<grid, kEncWarps * 32, 0, s.stream>>>(reinterpret_cast<const EncImgDesc*>(s.dev + desc_off), n);
-	else vp8_enc_i16<false><<<grid, kEncWarps * 32, 0, s.stream>>>(reinterpret_cast<const EncImgDesc*>(s.dev + desc_off), n);
+	const EncImgDesc* dd = reinterpret_cast<const EncImgDesc*>(s.dev + desc_off);
+	if (kind == 2) vp8_enc_bpred<<<grid, kEncWarps * 32, 0, s.stream>>>(dd, n);
+	else if (kind == 1) vp8_enc_i16<true><<<grid, kEncWarps * 32, 0, s.stream>>>(dd, n);
+	else vp8_enc_i16<false><<<grid, kEncWarps * 32, 0, s.stream>>>(dd, n);
 	ECU(cudaGetLastError());
 	ECU(cudaEventRecord(s.ev1, s.stream));
 
@@ -454,6 +687,7 @@ int vp8_gpu_enc_i16_inloop(int device, const EncYuv420Image* const* yuv, int n, 
 		ECU(cudaMemcpyAsync(coeffs[i], s.dev + off[i].coeffs, mb * 800, cudaMemcpyDeviceToHost, s.stream));
 		if (y_modes && y_modes[i]) ECU(cudaMemcpyAsync(y_modes[i], s.dev + off[i].ym, mb, cudaMemcpyDeviceToHost, s.stream));
 		if (uv_modes && uv_modes[i]) ECU(cudaMemcpyAsync(uv_modes[i], s.dev + off[i].cm, mb, cudaMemcpyDeviceToHost, s.stream));
+		if (kind == 2) ECU(cudaMemcpyAsync(b_modes[i], s.dev + off[i].bm, mb * 16, cudaMemcpyDeviceToHost, s.stream));
 		uint8_t* const* rp[3] = {rec_y, rec_u, rec_v};
 		for (int k = 0; k < 3; k++)
 			if (rp[k] && rp[k][i]) ECU(cudaMemcpyAsync(rp[k][i], s.dev + off[i].rec[k], mb * (k ? 64 : 256), cudaMemcpyDeviceToHost, s.stream));
@@ -464,39 +698,65 @@ int vp8_gpu_enc_i16_inloop(int device, const EncYuv420Image* const* yuv, int n, 
 	return 0;
 }
 
+int vp8_gpu_enc_i16_inloop(int device, const EncYuv420Image* const* yuv, int n, int quality, int search, int16_t* const* coeffs,
+                           uint8_t* const* y_modes, uint8_t* const* uv_modes, uint8_t* const* rec_y, uint8_t* const* rec_u,
+                           uint8_t* const* rec_v, uint8_t* qindex_out) {
+	return enc_run(device, yuv, n, quality, search ? 1 : 0, coeffs, y_modes, nullptr, uv_modes, rec_y, rec_u, rec_v, qindex_out);
+}
+
+int vp8_gpu_enc_bpred_inloop(int device, const EncYuv420Image* const* yuv, int n, int quality, int16_t* const* coeffs, uint8_t* const* y_modes,
+                             uint8_t* const* b_modes, uint8_t* const* uv_modes, uint8_t* const* rec_y, uint8_t* const* rec_u,
+                             uint8_t* const* rec_v, uint8_t* qindex_out) {
+	return enc_run(device, yuv, n, quality, 2, coeffs, y_modes, b_modes, uv_modes, rec_y, rec_u, rec_v, qindex_out);
+}
+
 // ------------------------------------------------------------------------------------------------ reference entry points
-static int enc_one(const EncYuv420Image* yuv, int quality, int search, uint8_t** y_modes_out, size_t* y_modes_count_out, uint8_t** uv_modes_out,
-                   size_t* uv_modes_count_out, int16_t** coeffs_out, size_t* coeffs_count_out, uint8_t* qindex_out) {
+static int enc_one(const EncYuv420Image* yuv, int quality, int kind, uint8_t** y_modes_out, size_t* y_modes_count_out, uint8_t** b_modes_out,
+                   size_t* b_modes_count_out, uint8_t** uv_modes_out, size_t* uv_modes_count_out, int16_t** coeffs_out, size_t* coeffs_count_out,
+                   uint8_t* qindex_out) {
 	*coeffs_out = nullptr;
 	*coeffs_count_out = 0;
 	*qindex_out = 0;
 	if (y_modes_out) *y_modes_out = nullptr, *y_modes_count_out = 0;
+	if (b_modes_out) *b_modes_out = nullptr, *b_modes_count_out = 0;
 	if (uv_modes_out) *uv_modes_out = nullptr, *uv_modes_count_out = 0;
 	if (!yuv || !yuv->y || !yuv->u || !yuv->v || yuv->width == 0 || yuv->height == 0) return vp8_set_error(EINVAL, "bad picture", 0);
 	const size_t mb = vp8_gpu_enc_mb_total(yuv->width, yuv->height);
 	int16_t* co = (int16_t*)malloc(mb * 400 * sizeof(int16_t));
 	uint8_t* ym = y_modes_out ? (uint8_t*)malloc(mb) : nullptr;
+	uint8_t* bm = b_modes_out ? (uint8_t*)malloc(mb * 16) : nullptr;
 	uint8_t* cm = uv_modes_out ? (uint8_t*)malloc(mb) : nullptr;
-	if (!co || (y_modes_out && !ym) || (uv_modes_out && !cm)) {
-		free(co), free(ym), free(cm);
+	if (!co || (y_modes_out && !ym) || (b_modes_out && !bm) || (uv_modes_out && !cm)) {
+		free(co), free(ym), free(bm), free(cm);
 		return vp8_set_error(ENOMEM, "encoder output arrays", 0);
 	}
-	if (vp8_gpu_enc_i16_inloop(-1, &yuv, 1, quality, search, &co, ym ? &ym : nullptr, cm ? &cm : nullptr, nullptr, nullptr, nullptr, qindex_out)) {
+	if (enc_run(-1, &yuv, 1, quality, kind, &co, ym ? &ym : nullptr, bm ? &bm : nullptr, cm ? &cm : nullptr, nullptr, nullptr, nullptr, qindex_out)) {
 		const int saved = errno;
-		free(co), free(ym), free(cm);
+		free(co), free(ym), free(bm), free(cm);
 		errno = saved;
 		return -1;
 	}
 	*coeffs_out = co;
 	*coeffs_count_out = mb * 400;
 	if (y_modes_out) *y_modes_out = ym, *y_modes_count_out = mb;
+	if (b_modes_out) *b_modes_out = bm, *b_modes_count_out = mb * 16;
 	if (uv_modes_out) *uv_modes_out = cm, *uv_modes_count_out = mb;
 	return 0;
 }
 
+int enc_vp8_encode_bpred_uv_sad_inloop(const EncYuv420Image* yuv, int quality, uint8_t** y_modes_out, size_t* y_modes_count_out,
+                                       uint8_t** b_modes_out, size_t* b_modes_count_out, uint8_t** uv_modes_out, size_t* uv_modes_count_out,
+                                       int16_t** coeffs_out, size_t* coeffs_count_out, uint8_t* qindex_out) {
+	if (!y_modes_out || !y_modes_count_out || !b_modes_out || !b_modes_count_out || !uv_modes_out || !uv_modes_count_out || !coeffs_out ||
+	    !coeffs_count_out || !qindex_out)
+		return vp8_set_error(EINVAL, "null output", 0);
+	return enc_one(yuv, quality, 2, y_modes_out, y_modes_count_out, b_modes_out, b_modes_count_out, uv_modes_out, uv_modes_count_out, coeffs_out,
+	               coeffs_count_out, qindex_out);
+}
+
 int enc_vp8_encode_dc_pred_inloop(const EncYuv420Image* yuv, int quality, int16_t** coeffs_out, size_t* coeffs_count_out, uint8_t* qindex_out) {
 	if (!coeffs_out || !coeffs_count_out || !qindex_out) return vp8_set_error(EINVAL, "null output", 0);
-	return enc_one(yuv, quality, 0, nullptr, nullptr, nullptr, nullptr, coeffs_out, coeffs_count_out, qindex_out);
+	return enc_one(yuv, quality, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, coeffs_out, coeffs_count_out, qindex_out);
 }
 
 int enc_vp8_encode_i16x16_uv_sad_inloop(const EncYuv420Image* yuv, int quality, uint8_t** y_modes_out, size_t* y_modes_count_out,
@@ -504,11 +764,12 @@ int enc_vp8_encode_i16x16_uv_sad_inloop(const EncYuv420Image* yuv, int quality, 
                                         size_t* coeffs_count_out, uint8_t* qindex_out) {
 	if (!y_modes_out || !y_modes_count_out || !uv_modes_out || !uv_modes_count_out || !coeffs_out || !coeffs_count_out || !qindex_out)
 		return vp8_set_error(EINVAL, "null output", 0);
-	return enc_one(yuv, quality, 1, y_modes_out, y_modes_count_out, uv_modes_out, uv_modes_count_out, coeffs_out, coeffs_count_out, qindex_out);
+	return enc_one(yuv, quality, 1, y_modes_out, y_modes_count_out, nullptr, nullptr, uv_modes_out, uv_modes_count_out, coeffs_out, coeffs_count_out,
+	               qindex_out);
 }
 
 int enc_vp8_encode_i16x16_sad_inloop(const EncYuv420Image* yuv, int quality, uint8_t** y_modes_out, size_t* y_modes_count_out,
                                      int16_t** coeffs_out, size_t* coeffs_count_out, uint8_t* qindex_out) {
 	if (!y_modes_out || !y_modes_count_out || !coeffs_out || !coeffs_count_out || !qindex_out) return vp8_set_error(EINVAL, "null output", 0);
-	return enc_one(yuv, quality, 1, y_modes_out, y_modes_count_out, nullptr, nullptr, coeffs_out, coeffs_count_out, qindex_out);
+	return enc_one(yuv, quality, 1, y_modes_out, y_modes_count_out, nullptr, nullptr, nullptr, nullptr, coeffs_out, coeffs_count_out, qindex_out);
 }
