@@ -662,8 +662,31 @@ def other_configs(ctx, W, P, S, torch, dist, world, rank, local, stream, job_max
                                      "note": "enc_vp8_encode_i16x16_uv_sad_inloop (reference enc_recon.c:1189-1483) for 1920x1080 noise / gradient "
                                              "pictures, quality 75: mode search + forward transforms + quantisation + reconstruction, one kernel"}
         del outs
+        # the 4x4 sub-block front end (--mode bpred) on the same pictures
+        bkeys = ["900_1920x1080_k0_q75_s2", "901_1920x1080_k1_q75_s2"]
+        pin_out2 = W.PinnedBuffer(E.batch_out_bytes(pics, bpred=True))
+        E.encode_batch(pics, 75, "bpred", device=local, out_buffer=pin_out2.array)
+        sync_all()
+        t0 = time.perf_counter()
+        outs, qi = E.encode_batch(pics, 75, "bpred", device=local, out_buffer=pin_out2.array)
+        sync_all()
+        wall_b = job_max((time.perf_counter() - t0) * 1e3)
+        kb_ms = job_max(E.last_kernel_ms())
+        ok_b = all(enc_digest(o["coeffs"], o["y_modes"], o["uv_modes"], o["b_modes"]) == gd[bkeys[i % 2]]["digest"] for i, o in enumerate(outs))
+        out["encoder_inloop_bpred"] = {"value": world * px / (kb_ms / 1e3) / 1e6, "unit": "Mpixel/s", "kernel_ms": kb_ms, "pictures_per_gpu": n_pic,
+                                       "e2e": {"value": world * px / (wall_b / 1e3) / 1e6, "unit": "Mpixel/s", "ms_per_step": wall_b},
+                                       "bit_exact_all_pictures_vs_reference_digests": ok_b,
+                                       "note": "enc_vp8_encode_bpred_uv_sad_inloop (reference enc_recon.c:1507-1831), same pictures"}
+        del outs
+        pin_out2.close()
         pin_in.close()
         pin_out.close()
+        if rank == 0 and not args.no_cpu_baseline:
+            r = subprocess.run([sys.executable, str(ROOT / "oracle" / "cpu_baseline.py"), "--encoder-bpred", "--seconds", "3"], capture_output=True, text=True)
+            try:
+                out["encoder_inloop_bpred"]["cpu_baseline"] = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception:
+                out["encoder_inloop_bpred"]["cpu_baseline"] = {"unavailable": (r.stderr or r.stdout)[-200:]}
         if rank == 0 and not args.no_cpu_baseline:
             r = subprocess.run([sys.executable, str(ROOT / "oracle" / "cpu_baseline.py"), "--encoder", "--seconds", "4"], capture_output=True, text=True)
             try:

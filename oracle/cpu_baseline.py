@@ -117,31 +117,31 @@ def _worker(args):
 def _enc_worker(args):
     """The encoder row: enc_vp8_encode_i16x16_uv_sad_inloop of the reference (oracle/_ref/libref_enc.so), or of
     the oracle port where that is absent, on the benchmark's two 1920x1080 pictures."""
-    reps, kind = args
+    reps, kind, search = args
     from encfix import EncOracle, EncReference, picture
     impl = EncReference() if kind == "reference" else EncOracle()
     pics = [picture(900, 1920, 1080, 0), picture(901, 1920, 1080, 1)]
     t0 = time.perf_counter()
     for _ in range(reps):
         for y, u, v in pics:
-            impl.run(y, u, v, 75, 1)
+            impl.run(y, u, v, 75, search)
     return reps * len(pics) * 1920 * 1080, time.perf_counter() - t0, reps * len(pics)
 
 
-def run_encoder(procs=None, seconds=4.0):
+def run_encoder(procs=None, seconds=4.0, search=1):
     from encfix import EncReference
     kind = "reference" if EncReference.available() else "port"
     procs = procs or len(os.sched_getaffinity(0)) or 1
     ctx = mp.get_context("spawn")
     with ctx.Pool(procs) as pool:
-        cal = pool.map(_enc_worker, [(1, kind)] * procs)
+        cal = pool.map(_enc_worker, [(1, kind, search)] * procs)
         reps = max(1, int(seconds / max(max(t for _, t, _ in cal), 1e-3)))
-        res = pool.map(_enc_worker, [(reps, kind)] * procs)
+        res = pool.map(_enc_worker, [(reps, kind, search)] * procs)
     slowest = max(r[1] for r in res)
     return {"value": sum(r[0] for r in res) / slowest / 1e6, "unit": "Mpixel/s", "cores": procs, "kind": kind,
             "flags": "gcc -O3 (x86-64 baseline)" if kind == "reference" else "gcc -O2 (oracle/Makefile)",
             "sample": f"{sum(r[2] for r in res)} pictures ({reps} passes over 2 distinct 1920x1080 inputs on each of {procs} processes), {slowest:.1f} s, "
-                      "enc_vp8_encode_i16x16_uv_sad_inloop, quality 75"}
+                      + ("enc_vp8_encode_bpred_uv_sad_inloop" if search == "bpred" else "enc_vp8_encode_i16x16_uv_sad_inloop") + ", quality 75"}
 
 
 def run(files, mode="yuvf", procs=None, seconds=12.0, whole=False):
@@ -172,12 +172,13 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("files", nargs="*")
     ap.add_argument("--encoder", action="store_true", help="time the reference encoder's i16 in-loop front end instead of the decoder")
+    ap.add_argument("--encoder-bpred", action="store_true", help="... its 4x4 sub-block SAD front end")
     ap.add_argument("--mode", default="yuvf", choices=["yuv", "yuvf", "ppm"])
     ap.add_argument("--procs", type=int, default=0)
     ap.add_argument("--seconds", type=float, default=12.0)
     ap.add_argument("--whole", action="store_true", help="time the whole decoder (.webp bytes -> pixels), not just m06+m07")
     a = ap.parse_args()
-    if a.encoder:
-        print(json.dumps(run_encoder(a.procs or None, a.seconds)))
+    if a.encoder or a.encoder_bpred:
+        print(json.dumps(run_encoder(a.procs or None, a.seconds, "bpred" if a.encoder_bpred else 1)))
     else:
         print(json.dumps(run(a.files, a.mode, a.procs or None, a.seconds, a.whole)))
