@@ -621,6 +621,9 @@ def other_configs(ctx, W, P, S, torch, dist, world, rank, local, stream, job_max
         host_out.close()
         cf.free()
         ctx.trim()
+        if rank == 0 and not args.no_cpu_baseline:
+            # BASELINE config 5 asks for it "vs the reference CPU decoder on all host cores": the whole decoder, .webp bytes to pixels
+            out["mixed_batch"]["cpu_baseline_whole"] = cpu_arm([str(mixed_dir / n) for n in sorted(mdg)], "yuvf", 4.0, whole=True)
 
     # ---- the encoder's in-loop reconstruction (whole-macroblock mode search), 1080p pictures per launch
     enc_gold = ROOT / "tests" / "golden" / "enc.json"
