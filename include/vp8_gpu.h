@@ -150,7 +150,10 @@ int vp8_gpu_download_padded(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, int i, uint8_t* 
  * chunks are a quarter of that and the third a half, so that the first download starts early) whose host->device
  * copies, kernels and device->host copies overlap on internal streams. dst (ideally pinned, as the
  * frames' arrays) receives frame i at offsets[i]: the -yuv (filtered=0) / -yuvf bytes, resp. the -ppm bytes.
- * vp8_gpu_decode_bytes gives the capacity needed. Blocking. */
+ * Frames of one size lie in dst in the caller's order; when the sizes differ by more than a factor of two the call
+ * processes - and lays out - the biggest frames first (a chunk's kernels take as long as its biggest frame, so the big
+ * ones share the first chunks, each on a cluster of SMs): always read offsets[]. vp8_gpu_decode_bytes gives the capacity
+ * needed. Blocking. */
 int vp8_gpu_decode_i420(vp8_gpu_ctx* ctx, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,
                         int filtered, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk);
 int vp8_gpu_decode_ppm(vp8_gpu_ctx* ctx, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,

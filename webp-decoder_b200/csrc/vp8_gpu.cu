@@ -1987,6 +1987,47 @@ static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const 
 	return 0;
 }
 
+// A chunk's kernels take as long as its biggest frame needs (one frame is a dependency chain, spread over a cluster at best),
+// so a call whose frames differ a lot in size processes them biggest first: the 4K frames share the first chunks, each on a
+// cluster of several SMs, instead of putting their latency into every chunk. Returns the processing order; empty = as given.
+static std::vector<int> processing_order(const FrameGeom* g, int n) {
+	size_t lo = ~(size_t)0, hi = 0;
+	for (int i = 0; i < n; i++) {
+		const size_t px = (size_t)g[i].width * g[i].height;
+		lo = std::min(lo, px);
+		hi = std::max(hi, px);
+	}
+	if (n < 2 || hi < 2 * lo) return {};
+	std::vector<int> ord(n);
+	for (int i = 0; i < n; i++) ord[i] = i;
+	std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return (size_t)g[a].width * g[a].height > (size_t)g[b].width * g[b].height; });
+	return ord;
+}
+
+// Runs `call(geometry, index map, offsets, sizes)` on the frames in processing order and hands offsets / sizes back in the
+// caller's order. idx[j] = caller's index of the j-th processed frame.
+extern "C++" {
+template <class Call>
+static int in_processing_order(std::vector<FrameGeom>& g, int n, size_t* offsets, size_t* sizes, Call call) {
+	std::vector<int> ord = processing_order(g.data(), n);
+	if (ord.empty()) {
+		ord.resize(n);
+		for (int i = 0; i < n; i++) ord[i] = i;
+		return call(g.data(), ord, offsets, sizes);
+	}
+	std::vector<FrameGeom> gp(n);
+	for (int j = 0; j < n; j++) gp[j] = g[ord[j]];
+	std::vector<size_t> op(n), sp(n);
+	const int rc = call(gp.data(), ord, op.data(), sp.data());
+	if (rc) return rc;
+	for (int j = 0; j < n; j++) {
+		if (offsets) offsets[ord[j]] = op[j];
+		if (sizes) sizes[ord[j]] = sp[j];
+	}
+	return 0;
+}
+} // extern "C++"
+
 // The reference's contract: dense Vp8DecodedFrames in host memory. Which transport carries them is a host question: the
 // compact one needs every frame's 6.7 MB (1080p) read by host threads and then moves a third of the bytes, the dense one
 // is pure DMA of all of them. Measured (profiles/README.md, r2 transport): with 16+ host threads per GPU compact wins
@@ -2006,14 +2047,19 @@ static int decode_dense(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, cons
 	const int threads = c->host_threads > 0 ? c->host_threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
 	const bool compact = c->transport_mode == 1 || (c->transport_mode == 2 && threads >= kCompactMinThreads);
 	c->last_dense_chunks = c->last_compact_chunks = 0;
-	return decode_pipelined(
-	    c, g.data(), n,
-	    [&](int first, int cnt, int slot, cudaStream_t s_up, bool, vp8_gpu_batch** out) {
-		    (compact ? c->last_compact_chunks : c->last_dense_chunks)++;
-		    return compact ? batch_create_compact(c, kf + first, frames + first, cnt, slot, s_up, out)
-		                   : batch_create(c, kf + first, frames + first, cnt, true, out, s_up, true);
-	    },
-	    filtered, want_ppm, dst, cap, offsets, sizes, chunk);
+	return in_processing_order(g, n, offsets, sizes, [&](const FrameGeom* gp, const std::vector<int>& idx, size_t* op, size_t* sp) {
+		std::vector<const Vp8KeyFrameHeader*> kfp(n);
+		std::vector<const Vp8DecodedFrame*> frp(n);
+		for (int j = 0; j < n; j++) kfp[j] = kf[idx[j]], frp[j] = frames[idx[j]];
+		return decode_pipelined(
+		    c, gp, n,
+		    [&](int first, int cnt, int slot, cudaStream_t s_up, bool, vp8_gpu_batch** out) {
+			    (compact ? c->last_compact_chunks : c->last_dense_chunks)++;
+			    return compact ? batch_create_compact(c, kfp.data() + first, frp.data() + first, cnt, slot, s_up, out)
+			                   : batch_create(c, kfp.data() + first, frp.data() + first, cnt, true, out, s_up, true);
+		    },
+		    filtered, want_ppm, dst, cap, op, sp, chunk);
+	});
 }
 
 int vp8_gpu_decode_i420(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n, int filtered,
@@ -2034,10 +2080,16 @@ int vp8_gpu_decode_compact(vp8_gpu_ctx* c, const Vp8CompactFrame* const* frames,
 		if (validate_compact(frames[i])) return -1;
 		g[i] = {frames[i]->width, frames[i]->height};
 	}
-	return decode_pipelined(
-	    c, g.data(), n,
-	    [&](int first, int cnt, int slot, cudaStream_t s_up, bool, vp8_gpu_batch** out) { return batch_create_precompact(c, frames + first, cnt, slot, s_up, out); },
-	    ppm ? 1 : filtered, ppm != 0, dst, cap, offsets, sizes, chunk);
+	return in_processing_order(g, n, offsets, sizes, [&](const FrameGeom* gp, const std::vector<int>& idx, size_t* op, size_t* sp) {
+		std::vector<const Vp8CompactFrame*> frp(n);
+		for (int j = 0; j < n; j++) frp[j] = frames[idx[j]];
+		return decode_pipelined(
+		    c, gp, n,
+		    [&](int first, int cnt, int slot, cudaStream_t s_up, bool, vp8_gpu_batch** out) {
+			    return batch_create_precompact(c, frp.data() + first, cnt, slot, s_up, out);
+		    },
+		    ppm ? 1 : filtered, ppm != 0, dst, cap, op, sp, chunk);
+	});
 }
 
 int vp8_gpu_decode_webp(vp8_gpu_ctx* c, const uint8_t* const* files, const size_t* file_sizes, int n, int filtered, int ppm, uint8_t* dst,
@@ -2049,12 +2101,17 @@ int vp8_gpu_decode_webp(vp8_gpu_ctx* c, const uint8_t* const* files, const size_
 		if (vp8_parse_webp_size(files[i], file_sizes[i], &w, &h)) return fail(errno ? errno : EINVAL, "not a simple lossy WebP key frame");
 		g[i] = {w, h};
 	}
-	return decode_pipelined(
-	    c, g.data(), n,
-	    [&](int first, int cnt, int slot, cudaStream_t s_up, bool, vp8_gpu_batch** out) {
-		    return batch_create_webp(c, files + first, file_sizes + first, g.data() + first, cnt, slot, s_up, out);
-	    },
-	    ppm ? 1 : filtered, ppm != 0, dst, cap, offsets, sizes, chunk, /*ramp*/ false);
+	return in_processing_order(g, n, offsets, sizes, [&](const FrameGeom* gp, const std::vector<int>& idx, size_t* op, size_t* sp) {
+		std::vector<const uint8_t*> fp(n);
+		std::vector<size_t> fs(n);
+		for (int j = 0; j < n; j++) fp[j] = files[idx[j]], fs[j] = file_sizes[idx[j]];
+		return decode_pipelined(
+		    c, gp, n,
+		    [&](int first, int cnt, int slot, cudaStream_t s_up, bool, vp8_gpu_batch** out) {
+			    return batch_create_webp(c, fp.data() + first, fs.data() + first, gp + first, cnt, slot, s_up, out);
+		    },
+		    ppm ? 1 : filtered, ppm != 0, dst, cap, op, sp, chunk, /*ramp*/ false);
+	});
 }
 
 size_t vp8_gpu_decode_webp_bytes(const uint8_t* const* files, const size_t* file_sizes, int n, int ppm) {
