@@ -917,6 +917,7 @@ int rgb_of_host_image(vp8_gpu_ctx* c, const Yuv420Image* img, std::vector<uint8_
 // a zlib stream of stored blocks of at most 65535 bytes over filter-0 scanlines, Adler-32, IEND.
 uint32_t g_crc_tab[8][256];
 std::once_flag g_crc_once;
+void checksum_selftest();
 void crc_build() {
 	for (uint32_t i = 0; i < 256; i++) {
 		uint32_t v = i;
@@ -925,8 +926,9 @@ void crc_build() {
 	}
 	for (uint32_t i = 0; i < 256; i++)
 		for (int t = 1; t < 8; t++) g_crc_tab[t][i] = g_crc_tab[0][g_crc_tab[t - 1][i] & 255] ^ (g_crc_tab[t - 1][i] >> 8);
+	checksum_selftest();
 }
-uint32_t crc_update(uint32_t crc, const uint8_t* p, size_t n) { // slice-by-8
+uint32_t crc_update_table(uint32_t crc, const uint8_t* p, size_t n) { // slice-by-8
 	while (n && ((uintptr_t)p & 7)) {
 		crc = g_crc_tab[0][(crc ^ *p++) & 255] ^ (crc >> 8);
 		n--;
@@ -943,7 +945,7 @@ uint32_t crc_update(uint32_t crc, const uint8_t* p, size_t n) { // slice-by-8
 	while (n--) crc = g_crc_tab[0][(crc ^ *p++) & 255] ^ (crc >> 8);
 	return crc;
 }
-void adler_update(uint32_t& a, uint32_t& b, const uint8_t* p, size_t n) {
+void adler_update_scalar(uint32_t& a, uint32_t& b, const uint8_t* p, size_t n) {
 	while (n) {
 		size_t k = std::min<size_t>(n, 5552); // largest run that cannot overflow 32 bits
 		n -= k;
@@ -954,6 +956,154 @@ void adler_update(uint32_t& a, uint32_t& b, const uint8_t* p, size_t n) {
 		a %= 65521;
 		b %= 65521;
 	}
+}
+
+#if defined(__x86_64__)
+// CRC-32 (reflected 0xEDB88320) by carry-less multiplication: four 128-bit lanes folded 64 bytes at a time, then 16 bytes at a
+// time, then the Barrett reduction (the folding constants are x^(n) mod P for the distances involved: the widely published
+// set of Intel's "Fast CRC computation using PCLMULQDQ" for this polynomial). Needs n >= 64 and n % 16 == 0; crc in and out
+// are the running (pre-inverted) values, like crc_update_table. Checked against the table version at start-up.
+__attribute__((target("pclmul,sse4.1"))) uint32_t crc_fold_pclmul(uint32_t crc, const uint8_t* p, size_t n) {
+	alignas(16) static const uint64_t k1k2[2] = {0x0154442bd4ull, 0x01c6e41596ull};
+	alignas(16) static const uint64_t k3k4[2] = {0x01751997d0ull, 0x00ccaa009eull};
+	alignas(16) static const uint64_t k5k0[2] = {0x0163cd6124ull, 0};
+	alignas(16) static const uint64_t poly[2] = {0x01db710641ull, 0x01f7011641ull};
+	__m128i x1 = _mm_loadu_si128((const __m128i*)(p + 0)), x2 = _mm_loadu_si128((const __m128i*)(p + 16));
+	__m128i x3 = _mm_loadu_si128((const __m128i*)(p + 32)), x4 = _mm_loadu_si128((const __m128i*)(p + 48));
+	x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
+	__m128i x0 = _mm_load_si128((const __m128i*)k1k2), x5, x6, x7, x8;
+	p += 64;
+	n -= 64;
+	while (n >= 64) {
+		x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+		x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+		x7 = _mm_clmulepi64_si128(x3, x0, 0x00);
+		x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+		x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+		x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+		x3 = _mm_clmulepi64_si128(x3, x0, 0x11);
+		x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+		x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), _mm_loadu_si128((const __m128i*)(p + 0)));
+		x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), _mm_loadu_si128((const __m128i*)(p + 16)));
+		x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), _mm_loadu_si128((const __m128i*)(p + 32)));
+		x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), _mm_loadu_si128((const __m128i*)(p + 48)));
+		p += 64;
+		n -= 64;
+	}
+	x0 = _mm_load_si128((const __m128i*)k3k4);
+	x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+	x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+	x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+	x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+	x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+	x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+	x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+	x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+	x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+	while (n >= 16) {
+		x2 = _mm_loadu_si128((const __m128i*)p);
+		x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+		x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+		x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+		p += 16;
+		n -= 16;
+	}
+	x2 = _mm_clmulepi64_si128(x1, x0, 0x10); // 128 -> 64 bits
+	x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+	x1 = _mm_srli_si128(x1, 8);
+	x1 = _mm_xor_si128(x1, x2);
+	x0 = _mm_loadl_epi64((const __m128i*)k5k0);
+	x2 = _mm_srli_si128(x1, 4);
+	x1 = _mm_and_si128(x1, x3);
+	x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
+	x1 = _mm_xor_si128(x1, x2);
+	x0 = _mm_load_si128((const __m128i*)poly); // Barrett
+	x2 = _mm_and_si128(x1, x3);
+	x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
+	x2 = _mm_and_si128(x2, x3);
+	x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+	x1 = _mm_xor_si128(x1, x2);
+	return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+
+// Adler-32, 32 bytes per step: a += sum(bytes); b += 32 * a_before + sum((32 - i) * byte_i) (blocks of 5536 bytes between the
+// reductions modulo 65521, as in the scalar loop).
+__attribute__((target("avx2"))) void adler_update_avx2(uint32_t& a_io, uint32_t& b_io, const uint8_t* p, size_t n) {
+	uint32_t a = a_io, b = b_io;
+	const __m256i weights = _mm256_setr_epi8(32, 31, 30, 29, 28, 27, 26, 25, 24, 23, 22, 21, 20, 19, 18, 17, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5,
+	                                         4, 3, 2, 1);
+	const __m256i zero = _mm256_setzero_si256(), ones16 = _mm256_set1_epi16(1);
+	while (n >= 32) {
+		const size_t blk = std::min<size_t>(n, 5536) / 32; // 173 steps: b grows by at most 173 * 32 * 65520 + ... < 2^32
+		__m256i va = zero, vb = zero, vprev = zero;        // va: byte sums (4 x 64-bit), vb: weighted sums, vprev: sum of a_before
+		for (size_t i = 0; i < blk; i++) {
+			const __m256i v = _mm256_loadu_si256((const __m256i*)(p + 32 * i));
+			vprev = _mm256_add_epi32(vprev, va);
+			va = _mm256_add_epi32(va, _mm256_sad_epu8(v, zero));
+			vb = _mm256_add_epi32(vb, _mm256_madd_epi16(_mm256_maddubs_epi16(v, weights), ones16));
+		}
+		// horizontal sums
+		alignas(32) uint32_t ta[8], tb[8], tp[8];
+		_mm256_store_si256((__m256i*)ta, va);
+		_mm256_store_si256((__m256i*)tb, vb);
+		_mm256_store_si256((__m256i*)tp, vprev);
+		uint64_t sa = 0, sb = 0, sp = 0;
+		for (int i = 0; i < 8; i++) sa += ta[i], sb += tb[i], sp += tp[i];
+		// b_new = b + blk*32*a (a before the block) + 32 * (sum over steps of the bytes before that step) + weighted sums
+		b = (uint32_t)((b + (uint64_t)blk * 32 * a + 32 * sp + sb) % 65521);
+		a = (uint32_t)((a + sa) % 65521);
+		p += 32 * blk;
+		n -= 32 * blk;
+	}
+	a_io = a;
+	b_io = b;
+	if (n) adler_update_scalar(a_io, b_io, p, n);
+}
+
+bool g_fast_crc = false, g_fast_adler = false;
+// the fast paths are used only if this CPU has the instructions AND they reproduce the plain versions on a test pattern
+void checksum_selftest() {
+	std::vector<uint8_t> buf(5000 + 37);
+	uint32_t x = 12345;
+	for (auto& v : buf) v = (uint8_t)((x = x * 1664525u + 1013904223u) >> 24);
+	__builtin_cpu_init();
+	if (__builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1")) {
+		bool ok = true;
+		for (size_t n : {(size_t)64, (size_t)80, (size_t)4992}) ok = ok && crc_fold_pclmul(0xFFFFFFFFu, buf.data() + 3, n) == crc_update_table(0xFFFFFFFFu, buf.data() + 3, n);
+		g_fast_crc = ok && crc_fold_pclmul(0x1234abcdu, buf.data(), 128) == crc_update_table(0x1234abcdu, buf.data(), 128);
+	}
+	if (__builtin_cpu_supports("avx2")) {
+		uint32_t a1 = 1, b1 = 0, a2 = 1, b2 = 0;
+		adler_update_scalar(a1, b1, buf.data(), buf.size());
+		adler_update_avx2(a2, b2, buf.data(), buf.size());
+		uint32_t a3 = 65520, b3 = 65519, a4 = 65520, b4 = 65519;
+		std::vector<uint8_t> ff(20000, 0xff);
+		adler_update_scalar(a3, b3, ff.data(), ff.size());
+		adler_update_avx2(a4, b4, ff.data(), ff.size());
+		g_fast_adler = a1 == a2 && b1 == b2 && a3 == a4 && b3 == b4;
+	}
+}
+#else
+void checksum_selftest() {}
+constexpr bool g_fast_crc = false, g_fast_adler = false;
+#endif
+
+uint32_t crc_update(uint32_t crc, const uint8_t* p, size_t n) {
+#if defined(__x86_64__)
+	if (g_fast_crc && n >= 64) {
+		const size_t body = n & ~(size_t)15;
+		crc = crc_fold_pclmul(crc, p, body);
+		p += body;
+		n -= body;
+	}
+#endif
+	return crc_update_table(crc, p, n);
+}
+void adler_update(uint32_t& a, uint32_t& b, const uint8_t* p, size_t n) {
+#if defined(__x86_64__)
+	if (g_fast_adler && n >= 64) return adler_update_avx2(a, b, p, n);
+#endif
+	adler_update_scalar(a, b, p, n);
 }
 void be32(uint8_t* p, uint32_t v) {
 	p[0] = (uint8_t)(v >> 24);
