@@ -34,7 +34,8 @@ struct EncImgDesc {
 	uint8_t *y_modes, *uv_modes;          // mb_total each
 	uint8_t* b_modes;                     // mb_total * 16 (sub-block front end only)
 	uint32_t width, height, mb_cols, mb_rows;
-	int32_t q[6]; // y1dc y1ac uvdc uvac y2dc y2ac
+	int32_t q[6];  // y1dc y1ac uvdc uvac y2dc y2ac
+	uint32_t qm[6]; // 2^32 / q + 1: n / q == umulhi(n, qm) for every n this path can meet (checked exhaustively up to 70000 for q < 1000)
 };
 
 struct EncWarpWs {
@@ -43,9 +44,9 @@ struct EncWarpWs {
 	int16_t ydc[16];   // and back, after quantise / dequantise / inverse WHT
 };
 
-// round-half-away division saturated to int16 (enc_quant.c:62-76)
-__device__ __forceinline__ int quantise(int c, int step) {
-	const int mag = (int)((uint32_t)(abs(c) + (step >> 1)) / (uint32_t)step);
+// round-half-away division saturated to int16 (enc_quant.c:62-76); the division is a multiplication by the step's reciprocal
+__device__ __forceinline__ int quantise(int c, int step, uint32_t magic) {
+	const int mag = (int)__umulhi((uint32_t)(abs(c) + (step >> 1)), magic);
 	return max(min(c < 0 ? -mag : mag, 32767), -32768);
 }
 
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) vp8_enc_i16(const EncImgDesc* 
 		const int pw = plane == 0 ? (int)d.width : (int)((d.width + 1) >> 1), ph = plane == 0 ? (int)d.height : (int)((d.height + 1) >> 1);
 		const int rstride = cols * n;
 		const int q_dc = plane == 0 ? d.q[0] : d.q[2], q_ac = plane == 0 ? d.q[1] : d.q[3];
+		const uint32_t m_dc = plane == 0 ? d.qm[0] : d.qm[2], m_ac = plane == 0 ? d.qm[1] : d.qm[3];
 		uint8_t* const lcol = ws.lcol + (plane == 0 ? 0 : (plane == 1 ? 16 : 24));
 
 		for (int row = warp; row < rows; row += kEncWarps) {
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) vp8_enc_i16(const EncImgDesc* 
 					cf[0] = 0;
 				}
 #pragma unroll
-				for (int i = 0; i < 16; i++) cf[i] = quantise(cf[i], i ? q_ac : q_dc);
+				for (int i = 0; i < 16; i++) cf[i] = quantise(cf[i], i ? q_ac : q_dc, i ? m_ac : m_dc);
 				__syncwarp();
 				const size_t mb = (size_t)row * cols + x;
 				int16_t* const out = d.coeffs + mb * 400;
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) vp8_enc_i16(const EncImgDesc* 
 					fwht4x4(dcv, y2);
 					uint32_t pk[8];
 #pragma unroll
-					for (int i = 0; i < 16; i++) y2[i] = quantise(y2[i], i ? d.q[5] : d.q[4]);
+					for (int i = 0; i < 16; i++) y2[i] = quantise(y2[i], i ? d.q[5] : d.q[4], i ? d.qm[5] : d.qm[4]);
 #pragma unroll
 					for (int i = 0; i < 8; i++) pk[i] = (uint32_t)(y2[2 * i] & 0xffff) | ((uint32_t)y2[2 * i + 1] << 16);
 					reinterpret_cast<uint4*>(out)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) vp8_enc_bpred(const EncImgDesc
 					fdct4x4(dd, cf);
 					uint32_t pk[8];
 #pragma unroll
-					for (int i = 0; i < 16; i++) cf[i] = quantise(cf[i], i ? d.q[3] : d.q[2]);
+					for (int i = 0; i < 16; i++) cf[i] = quantise(cf[i], i ? d.q[3] : d.q[2], i ? d.qm[3] : d.qm[2]);
 #pragma unroll
 					for (int i = 0; i < 8; i++) pk[i] = (uint32_t)(cf[2 * i] & 0xffff) | ((uint32_t)cf[2 * i + 1] << 16);
 					uint4* o = reinterpret_cast<uint4*>(out + 16 + (plane == 1 ? 256 : 320) + 16 * cb);
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) vp8_enc_bpred(const EncImgDesc
 					__syncwarp();
 					if (lane < 16) { // one coefficient per lane: quantise, store, dequantise
 						const int step = lane ? d.q[1] : d.q[0];
-						const int qc = quantise(ws.buf[lane], step);
+						const int qc = quantise(ws.buf[lane], step, lane ? d.qm[1] : d.qm[0]);
 						out[16 + 16 * sb + lane] = (int16_t)qc;
 						ws.buf[lane] = (int16_t)(qc * step);
 					}
@@ -668,6 +670,7 @@ static int enc_run(int device, const EncYuv420Image* const* yuv, int n, int qual
 		d.mb_cols = (w + 15) >> 4;
 		d.mb_rows = (hgt + 15) >> 4;
 		memcpy(d.q, q, sizeof(q));
+		for (int k = 0; k < 6; k++) d.qm[k] = (uint32_t)((1ull << 32) / (uint32_t)q[k] + 1);
 	}
 	ECU(cudaMemcpyAsync(s.dev + desc_off, s.pin_desc, sizeof(EncImgDesc) * (size_t)n, cudaMemcpyHostToDevice, s.stream));
 

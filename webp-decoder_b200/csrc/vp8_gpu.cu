@@ -144,7 +144,7 @@ struct vp8_gpu_ctx {
 	int tune_cluster = 0; // CTAs per image in cluster mode: 0 = automatic, 1 = never, 2/4/8 = at most that many
 	int last_cluster = 1;
 	int kernel_version = 3; // 2: vp8_mb_pairs for every batch size, 3: big batches run vp8_mb_lockstep (several images
-	                        // per CTA, barrier every second step)
+	                        // per CTA, barrier every third step)
 	bool lockstep_small = true; // kernel 3: 8-warp CTAs also walk their steps in lockstep (VP8_GPU_LOCKSTEP_SMALL=0: no)
 	int last_groups = 0;    // images per CTA of the last launch when it was the lockstep flavour, else 0
 	uint8_t* bounce[2] = {nullptr, nullptr};

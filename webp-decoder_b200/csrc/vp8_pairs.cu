@@ -330,7 +330,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 #define VP8P_LOCK_GROUPS 7
 #endif
 constexpr int kLockMaxGroups = VP8P_LOCK_GROUPS;
-constexpr int kLockBarrierEvery = 2; // the lockstep kernel's warps meet every N-th step (measured: 1 -> 14.37 ms, 2 -> 14.11, 4 -> 14.32)
+constexpr int kLockBarrierEvery = 3; // the lockstep kernel's warps meet every N-th step (round 2 kernel, ms per 1024 x 1080p: 1 -> 12.87, 2 -> 12.45, 3 -> 12.21, 4 -> 12.39)
 
 // Per-image values every warp of a group needs but only now and then: kept in shared memory, not in registers.
 struct LockImage {
