@@ -50,27 +50,9 @@ __device__ __forceinline__ int sclamp(int v) { return min(max(v, -128), 127); }
 __device__ __forceinline__ int absdiff(int a, int b) { return (int)__sad(a, b, 0u); }               // VABSDIFF
 __device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
 __device__ __forceinline__ void st32(uint8_t* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
-// Final pixels leave through here. VP8P_STORE_HINT picks the cache operator (measured with ncu dram__bytes_*, profiles/README.md r2):
-// 0 plain st.global, 1 .cg, 2 L2::evict_last policy, 3 .wt, 4 .cs
-#ifndef VP8P_STORE_HINT
-#define VP8P_STORE_HINT 0
-#endif
-__device__ __forceinline__ void st_pix32(uint8_t* p, uint32_t v) {
-#if VP8P_STORE_HINT == 1
-	__stcg(reinterpret_cast<uint32_t*>(p), v);
-#elif VP8P_STORE_HINT == 2
-	uint64_t pol;
-	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-	asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
-#elif VP8P_STORE_HINT == 3
-	__stwt(reinterpret_cast<uint32_t*>(p), v);
-#elif VP8P_STORE_HINT == 4
-	__stcs(reinterpret_cast<uint32_t*>(p), v);
-#else
-	*reinterpret_cast<uint32_t*>(p) = v;
-#endif
-}
-
+// Final pixels leave through here: plain stores (cache operators .cg / .wt / .cs and an evict_last policy were measured on the word
+// stores in round 2, .cs / .cg again on the 16-byte strip stores: no difference in time or DRAM bytes, profiles/README.md).
+__device__ __forceinline__ void st_pix32(uint8_t* p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
 __device__ __forceinline__ void st_pix128(uint8_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
 
 // selp: selects the compiler will not turn into branches; the condition is tested inside (sign bit / a bit mask of x)
