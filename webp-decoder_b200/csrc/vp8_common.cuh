@@ -214,14 +214,11 @@ __device__ __forceinline__ bool lf_position(int p3, int& p2, int& p1, int& p0, i
 	return true;
 }
 
-// Filter across a vertical edge: q points at the word holding q0..q3 of this lane's pixel row (4-byte aligned).
-#ifndef VP8P_LF_PRMT
-#define VP8P_LF_PRMT 1 // taps leave and enter their words through PRMT (one instruction per byte) instead of shift + mask
-#endif
+// Filter across a vertical edge: q points at the word holding q0..q3 of this lane's pixel row (4-byte aligned). The taps leave
+// and enter their words through PRMT (one instruction per byte).
 template <int KIND>
 __device__ __forceinline__ void lf_across_columns(uint8_t* q, int lim, int interior, int hev_thr) {
 	uint32_t wp = ld32(q - 4), wq = ld32(q);
-#if VP8P_LF_PRMT
 	int p3 = __byte_perm(wp, 0, 0x4440), p2 = __byte_perm(wp, 0, 0x4441), p1 = __byte_perm(wp, 0, 0x4442), p0 = __byte_perm(wp, 0, 0x4443);
 	int q0 = __byte_perm(wq, 0, 0x4440), q1 = __byte_perm(wq, 0, 0x4441), q2 = __byte_perm(wq, 0, 0x4442), q3 = __byte_perm(wq, 0, 0x4443);
 	if (lf_position<KIND>(p3, p2, p1, p0, q0, q1, q2, q3, lim, interior, hev_thr)) {
@@ -229,14 +226,6 @@ __device__ __forceinline__ void lf_across_columns(uint8_t* q, int lim, int inter
 		st32(q - 4, __byte_perm(__byte_perm(p3, p2, 0x4040), __byte_perm(p1, p0, 0x4040), 0x5410));
 		st32(q, __byte_perm(__byte_perm(q0, q1, 0x4040), __byte_perm(q2, q3, 0x4040), 0x5410));
 	}
-#else
-	int p3 = wp & 255, p2 = (wp >> 8) & 255, p1 = (wp >> 16) & 255, p0 = wp >> 24;
-	int q0 = wq & 255, q1 = (wq >> 8) & 255, q2 = (wq >> 16) & 255, q3 = wq >> 24;
-	if (lf_position<KIND>(p3, p2, p1, p0, q0, q1, q2, q3, lim, interior, hev_thr)) {
-		st32(q - 4, (uint32_t)p3 | (p2 << 8) | (p1 << 16) | ((uint32_t)p0 << 24));
-		st32(q, (uint32_t)q0 | (q1 << 8) | (q2 << 16) | ((uint32_t)q3 << 24));
-	}
-#endif
 }
 
 // Filter across a horizontal edge: q points at q0 of this lane's pixel column, s = row stride.

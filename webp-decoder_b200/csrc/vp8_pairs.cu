@@ -32,9 +32,7 @@
 
 // B_PRED lane table, byte 3: what a sub-block mode needs besides its three taps, as bits the step can test directly
 #define VP8P_KIND_CODE(k) ((k) == 1 ? 0x40u : (k) == 2 ? 0x80u : (k) == 3 ? 0xc0u : 0u)
-#ifndef VP8P_HALF_SKEW
-#define VP8P_HALF_SKEW 64
-#endif
+constexpr int kHalfSkew = 64; // see HalfWs::skew_
 // vp8_pairs_step_a.inc asks for the filtered rows of the row above here; who owns the two words depends on the loop structure
 #define VP8P_TA_DECL uint32_t ta_y = 0, ta_c = 0;
 
@@ -56,11 +54,11 @@ struct __align__(16) HalfWs {
 	uint4 coef[52];
 	uint8_t so_y[16 * 32];    // output strip, luma: rows -4..11 of a PAIR of macroblocks, i.e. whole 32-byte sectors (vp8_pairs_step_c.inc)
 	uint8_t so_c[2 * 8 * 16]; // output strip, U then V: rows -4..3 of the pair
-	uint8_t skew_[VP8P_HALF_SKEW]; // the two halves of a warp touch the same offsets of their workspaces in the same instruction:
+	uint8_t skew_[kHalfSkew]; // the two halves of a warp touch the same offsets of their workspaces in the same instruction:
 	                               // with sizeof(HalfWs) = 64 mod 128 they do so on complementary shared-memory banks
 };
 static_assert(sizeof(HalfWs) % 16 == 0 && offsetof(HalfWs, res) % 16 == 0 && offsetof(HalfWs, coef) % 16 == 0 && offsetof(HalfWs, so_y) % 16 == 0 &&
-                  offsetof(HalfWs, so_c) % 16 == 0 && sizeof(HalfWs) % 128 == VP8P_HALF_SKEW,
+                  offsetof(HalfWs, so_c) % 16 == 0 && sizeof(HalfWs) % 128 == kHalfSkew,
               "HalfWs alignment");
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -326,10 +324,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 // a warp whose dependency (stamp of the row above) or next image is not ready yet simply sits the step out, and the
 // loop ends when no warp has work left (__syncthreads_or). Image hand-over inside a group: warps count themselves out
 // (ctl[0]); when all NW have, the group's first warp loads the next descriptor and publishes it (ctl[1]).
-#ifndef VP8P_LOCK_GROUPS
-#define VP8P_LOCK_GROUPS 7
-#endif
-constexpr int kLockMaxGroups = VP8P_LOCK_GROUPS;
+constexpr int kLockMaxGroups = 7;
 constexpr int kLockBarrierEvery = 3; // the lockstep kernel's warps meet every N-th step (round 2 kernel, ms per 1024 x 1080p: 1 -> 12.87, 2 -> 12.45, 3 -> 12.21, 4 -> 12.39)
 
 // Per-image values every warp of a group needs but only now and then: kept in shared memory, not in registers.
