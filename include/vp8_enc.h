@@ -76,7 +76,7 @@ int vp8_gpu_enc_bpred_inloop(int device, const EncYuv420Image* const* yuv, int n
                              uint8_t* const* y_modes, uint8_t* const* b_modes, uint8_t* const* uv_modes, uint8_t* const* rec_y,
                              uint8_t* const* rec_u, uint8_t* const* rec_v, uint8_t* qindex_out);
 size_t vp8_gpu_enc_mb_total(uint32_t width, uint32_t height);
-/* device time of the kernel of the last vp8_gpu_enc_i16_inloop call of this thread, in milliseconds */
+/* device time of the kernel of the last vp8_gpu_enc_*_inloop call of this thread, in milliseconds */
 double vp8_gpu_enc_last_kernel_ms(void);
 
 #ifdef __cplusplus

@@ -112,6 +112,20 @@ def test_gpu_batch_matches_oracle_with_reconstruction_planes(lib, enc_oracle):
 
 
 @pytest.mark.gpu
+def test_gpu_more_pictures_than_resident_ctas(lib, enc_oracle):
+    """A launch holds 4 CTAs per SM; with more pictures than that every CTA walks several (stamps and shared state are reset
+    in between), and a wide flat picture exercises the longest rows."""
+    from webp_decoder_b200 import enc
+    pics = [picture(2000 + i, 16 + 16 * (i % 3), 16 + 16 * (i % 2), i % 4) for i in range(1300)] + [picture(9, 4000, 16, 0)]
+    for s in (1, "bpred"):
+        outs, qi = enc.encode_batch(pics, 40, s)
+        for i in list(range(0, 1300, 37)) + [1299, 1300]:
+            o = enc_oracle.run(*pics[i], 40, s)
+            outs[i]["qindex"] = qi
+            assert same(outs[i], o, s), (i, s)
+
+
+@pytest.mark.gpu
 def test_gpu_matches_reference_encoder_digests(lib, enc_golden):
     from webp_decoder_b200 import enc
     for k, g in enc_golden.items():
