@@ -27,7 +27,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / "webp-decoder_b200" / "csrc"
-OURS = ("vp8_pairs_step_a.inc", "vp8_pairs_step_b.inc", "vp8_pairs_step_c.inc", "vp8_pairs_row.inc", "vp8_pairs_image.inc", "vp8_pairs.cu")
+OURS = ("vp8_pairs_step_a.inc", "vp8_pairs_step_b.inc", "vp8_pairs_step_c.inc", "vp8_pairs_step_c1.inc", "vp8_pairs_step_c2.inc", "vp8_pairs_step_c3.inc", "vp8_pairs_row.inc", "vp8_pairs_image.inc", "vp8_pairs.cu")
 
 
 def ncu_sass(rep: str, kernel: str):

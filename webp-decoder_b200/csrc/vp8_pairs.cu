@@ -35,6 +35,14 @@
 constexpr int kHalfSkew = 64; // see HalfWs::skew_
 // vp8_pairs_step_a.inc asks for the filtered rows of the row above here; who owns the two words depends on the loop structure
 #define VP8P_TA_DECL uint32_t ta_y = 0, ta_c = 0;
+// The reconstruction tile of the macroblock in hand and of the one after it (where the left border and the corner of the next
+// macroblock are written): one and the same tile, except in vp8_mb_split, whose reconstruction warps alternate between two.
+#define RT_Y ws.rt_y
+#define RT_U ws.rt_u
+#define RT_V ws.rt_v
+#define RTN_Y RT_Y
+#define RTN_U RT_U
+#define RTN_V RT_V
 
 namespace {
 
