@@ -89,6 +89,12 @@ int vp8_gpu_last_segments(const vp8_gpu_ctx* ctx);
  * otherwise leave most SMs idle), 1 = never, 2/4/8 = at most that many CTAs per image. */
 int vp8_gpu_set_cluster(vp8_gpu_ctx* ctx, int ctas_per_image);
 int vp8_gpu_last_cluster(const vp8_gpu_ctx* ctx); /* CTAs per image of the last wavefront launch */
+/* Clusters of 4 or 8 CTAs in the fused mode run vp8_mb_split by default: every row pair is served by a reconstruction warp
+ * and a filter warp that trails it by one macroblock, so the frame's dependency chain advances at the pace of the longer of
+ * the two parts instead of their sum (one 3840x2160 frame 4.6 -> 3.4 ms). split = 0 keeps the one-warp-per-row-pair kernel
+ * for every cluster size; the environment variable VP8_GPU_SPLIT presets it. Both are bit-exact. */
+int vp8_gpu_set_cluster_split(vp8_gpu_ctx* ctx, int split);
+int vp8_gpu_last_split(const vp8_gpu_ctx* ctx); /* 1 if the last wavefront launch was vp8_mb_split */
 
 /* Transport of vp8_gpu_decode_i420 / _ppm (dense Vp8DecodedFrames in). compact = 1: every chunk is shipped without its
  * all-zero 4x4 blocks (per-macroblock presence mask + packed blocks, built by host_threads workers; 0 = all cores, at

@@ -172,11 +172,12 @@ def test_batch_of_more_than_a_wave_is_cut_into_segments(gpu_ctx, oracle):
     assert not bad, bad[:8]
 
 
-@pytest.mark.parametrize("ctas", [1, 2, 4, 8])
-def test_cluster_mode_one_image_over_several_ctas(gpu_ctx, oracle, ctas):
+@pytest.mark.parametrize("ctas,split", [(1, False), (2, False), (4, False), (8, False), (4, True), (8, True)])
+def test_cluster_mode_one_image_over_several_ctas(gpu_ctx, oracle, ctas, split):
     """Few big frames: each image is decoded by a thread-block cluster (row pairs dealt to the warps of 2/4/8 co-scheduled
-    CTAs, line buffers and progress stamps exchanged through L2). Same bytes as the single-CTA path and the oracle."""
-    gpu_ctx.set_cluster(ctas)
+    CTAs, line buffers and progress stamps exchanged through L2). split: the fused mode on 4 / 8 CTAs runs vp8_mb_split (a
+    reconstruction warp and a filter warp per row pair). Same bytes as the single-CTA path and the oracle."""
+    gpu_ctx.set_cluster(ctas, split)
     try:
         frames = [fuzz_frame(600 + s, 400 + 64 * s, 1100 + 200 * s, density=0.15, lf_level=20 + s, lf_use_simple=0) for s in range(3)]
         frames.append(fuzz_frame(610, 64, 4000, density=0.2))          # 250 macroblock rows, 4 columns
@@ -187,7 +188,7 @@ def test_cluster_mode_one_image_over_several_ctas(gpu_ctx, oracle, ctas):
             for f, o in zip(frames, outs):
                 assert np.array_equal(o, oracle.decode_i420(f, filtered)), (ctas, f.width, f.height, filtered)
         cfg = gpu_ctx.last_launch_config()
-        assert cfg["ctas_per_image"] == ctas and cfg["grid"] == len(frames) * ctas
+        assert cfg["ctas_per_image"] == ctas and cfg["grid"] == len(frames) * ctas and cfg["split"] == split, cfg
         # stand-alone loop filter (stage API) through the cluster path as well
         b = gpu_ctx.recon(kfs[:2], ds[:2])
         gpu_ctx.filter(b)
@@ -198,7 +199,7 @@ def test_cluster_mode_one_image_over_several_ctas(gpu_ctx, oracle, ctas):
                 assert np.array_equal(got, want)
         b.free()
     finally:
-        gpu_ctx.set_cluster(0)
+        gpu_ctx.set_cluster(0, True)
 
 
 def test_all_zero_and_saturated_inputs(gpu_ctx, oracle):

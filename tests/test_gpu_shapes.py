@@ -104,6 +104,6 @@ def test_seeded_soak_of_batch_and_launch_shapes(lib, gpu_ctx, oracle):
     finally:
         gpu_ctx.set_kernel(3)
         gpu_ctx.set_tuning(0, 0)
-        gpu_ctx.set_cluster(0)
+        gpu_ctx.set_cluster(0, True)
         gpu_ctx.set_transport("auto", 0)
     assert rounds == 150 and frames > 3000

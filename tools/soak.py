@@ -35,7 +35,8 @@ def soak(ctx, orc, rng, seconds=None, rounds=None):
         filtered = bool(rng.integers(2))
         ctx.set_kernel(kernel)
         ctx.set_tuning(warps, per_sm)
-        ctx.set_cluster(cluster)
+        split = bool(rng.integers(2))  # clusters of 4 / 8 CTAs, fused mode: vp8_mb_split or the one-warp-per-row-pair kernel
+        ctx.set_cluster(cluster, split)
         kfs, ds = [f.header() for f in frames], [f.cstruct() for f in frames]
         want = [orc.decode_i420(f, filtered) for f in frames]
         api = str(rng.choice(["batch", "batch", "pipelined", "ppm"]))
@@ -52,7 +53,7 @@ def soak(ctx, orc, rng, seconds=None, rounds=None):
             outs = [np.frombuffer(p, np.uint8) for p in ctx.decode_ppm(kfs, ds)]
         cfg = ctx.last_launch_config()
         bad = [i for i, (w, o) in enumerate(zip(want, outs)) if not np.array_equal(o, w)]
-        assert not bad, (f"MISMATCH round {done} ({api}): kernel {kernel} warps {warps} per_sm {per_sm} cluster {cluster} filtered {filtered} "
+        assert not bad, (f"MISMATCH round {done} ({api}): kernel {kernel} warps {warps} per_sm {per_sm} cluster {cluster} split {split} filtered {filtered} "
                          f"launch {cfg}: frames {bad[:8]} of {n}, e.g. {frames[bad[0]].width}x{frames[bad[0]].height}")
         done += 1
         frames_done += n

@@ -43,7 +43,7 @@ EXPORTS = [
     "vp8_gpu_last_launch_config", "vp8_gpu_frame_params", "vp8_gpu_kernel_time", "vp8_gpu_rgb_time",
     "vp8_gpu_decode_i420", "vp8_gpu_decode_ppm", "vp8_gpu_decode_bytes", "vp8_gpu_set_kernel",
     "vp8_gpu_png_bound", "vp8_gpu_png_frame", "vp8_gpu_set_transport",
-    "vp8_gpu_set_cluster", "vp8_gpu_last_cluster", "vp8_gpu_last_groups", "vp8_gpu_last_segments",
+    "vp8_gpu_set_cluster", "vp8_gpu_set_cluster_split", "vp8_gpu_last_split", "vp8_gpu_last_cluster", "vp8_gpu_last_groups", "vp8_gpu_last_segments",
     "vp8_gpu_decode_compact", "vp8_gpu_decode_webp", "vp8_gpu_decode_webp_bytes", "vp8_gpu_last_call_profile", "vp8_gpu_bind_host", "vp8_gpu_last_transport", "vp8_gpu_last_dense_frames",
     # encoder in-loop reconstruction (include/vp8_enc.h)
     "enc_vp8_encode_dc_pred_inloop", "enc_vp8_encode_i16x16_uv_sad_inloop", "enc_vp8_encode_i16x16_sad_inloop",
@@ -79,6 +79,8 @@ def load_library() -> C.CDLL:
     L.vp8_gpu_set_kernel.argtypes = [vp, C.c_int]
     L.vp8_gpu_set_transport.argtypes = [vp, C.c_int, C.c_int]
     L.vp8_gpu_set_cluster.argtypes = [vp, C.c_int]
+    L.vp8_gpu_set_cluster_split.argtypes = [vp, C.c_int]
+    L.vp8_gpu_last_split.argtypes = [vp]
     L.vp8_gpu_last_cluster.argtypes = [vp]
     L.vp8_gpu_last_groups.argtypes = [vp]
     L.vp8_gpu_last_segments.argtypes = [vp]
@@ -241,9 +243,12 @@ class Context:
         """1 = warp per macroblock, 2 = half-warp per macroblock (two rows per warp)."""
         _check(self._L.vp8_gpu_set_kernel(self._h, version), "vp8_gpu_set_kernel")
 
-    def set_cluster(self, ctas_per_image: int = 0):
-        """CTAs per image in cluster mode: 0 automatic, 1 never, 2/4/8 upper bound."""
+    def set_cluster(self, ctas_per_image: int = 0, split: bool | None = None):
+        """CTAs per image in cluster mode: 0 automatic, 1 never, 2/4/8 upper bound. split: clusters of 4 / 8 CTAs in the fused
+        mode run vp8_mb_split (reconstruction warp + filter warp per row pair; the default) or not."""
         _check(self._L.vp8_gpu_set_cluster(self._h, ctas_per_image), "vp8_gpu_set_cluster")
+        if split is not None:
+            _check(self._L.vp8_gpu_set_cluster_split(self._h, int(bool(split))), "vp8_gpu_set_cluster_split")
 
     def set_transport(self, compact=True, host_threads: int = 0):
         """compact: True / False, or "auto" (chosen chunk by chunk, the library's default)."""
@@ -426,6 +431,7 @@ class Context:
         _check(self._L.vp8_gpu_last_launch_config(self._h, C.byref(w), C.byref(g), C.byref(s)), "launch config")
         return {"warps_per_image": w.value, "grid": g.value, "smem_bytes": s.value,
                 "ctas_per_image": int(self._L.vp8_gpu_last_cluster(self._h)),
+                "split": bool(self._L.vp8_gpu_last_split(self._h)),
                 "images_per_cta": int(self._L.vp8_gpu_last_groups(self._h)),
                 "segments": int(self._L.vp8_gpu_last_segments(self._h))}
 

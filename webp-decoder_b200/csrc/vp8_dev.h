@@ -71,10 +71,13 @@ enum Vp8KernelMode {
 // scratch: vp8_pairs_scratch_bytes(grid, max_mb_cols) bytes of device memory private to this launch.
 // cluster > 1 (2, 4 or 8; needs warps_per_image == 16): every image is processed by a thread-block cluster of that many
 // CTAs; grid_ctas must be a multiple of it and scratch sized for grid_ctas / cluster slots.
-// lockstep != 0 (honoured for 8 warps per image): the warps of a CTA meet at a barrier once per macroblock step.
+// lockstep = 1 (honoured for 8 warps per image): the warps of a CTA meet at a barrier once per macroblock step.
+// lockstep = 2 (fused mode on a cluster, 16 warps): vp8_mb_split - a reconstruction warp and a filter warp per row pair, the
+// shape for ONE big frame's latency; 8 row pairs per CTA.
 int vp8_launch_pairs(int mode, int warps_per_image, const Vp8ImgDesc* descs_dev, int n_images, int max_mb_cols, int grid_ctas,
                      uint8_t* scratch, int cluster, int lockstep, void* stream);
 int vp8_pairs_smem_bytes(int warps_per_image, int max_mb_cols);
+int vp8_pairs_max_active_clusters(int mode, int cluster, int split, int max_mb_cols); // co-resident clusters of that size
 int vp8_pairs_max_ctas_per_sm(int mode, int warps_per_image, int max_mb_cols);
 size_t vp8_pairs_scratch_bytes(int slots, int max_mb_cols);
 // Lockstep flavour of the pair kernel (vp8_pairs.cu): one CTA carries `groups` images (1..7, 4 warps each) and all its warps

@@ -23,6 +23,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -143,9 +144,12 @@ struct vp8_gpu_ctx {
 	int tune_warps = 0, tune_imgs_per_sm = 0;
 	int tune_cluster = 0; // CTAs per image in cluster mode: 0 = automatic, 1 = never, 2/4/8 = at most that many
 	int last_cluster = 1;
+	bool last_split = false;
 	int kernel_version = 3; // 2: vp8_mb_pairs for every batch size, 3: big batches run vp8_mb_lockstep (several images
 	                        // per CTA, barrier every third step)
 	bool lockstep_small = true; // kernel 3: 8-warp CTAs also walk their steps in lockstep (VP8_GPU_LOCKSTEP_SMALL=0: no)
+	mutable std::unordered_map<uint64_t, int> cluster_fit; // clusters_resident()
+	bool split = true;          // cluster launches of the fused mode run vp8_mb_split: a reconstruction and a filter warp per row pair (VP8_GPU_SPLIT)
 	int last_groups = 0;    // images per CTA of the last launch when it was the lockstep flavour, else 0
 	uint8_t* bounce[2] = {nullptr, nullptr};
 	cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
@@ -719,8 +723,21 @@ int pick_warps(const vp8_gpu_ctx* c, int n_images) {
 // How `n` images (frames of at most max_mb_cols x max_rows macroblocks) are put on the GPU.
 struct LaunchPlan {
 	int warps = 4, grid = 0, cluster = 1, groups = 0;
+	bool split = false; // cluster launch in the split flavour (two warps per row pair, 8 row pairs per CTA)
 	int slots() const { return groups ? grid * groups : cluster > 1 ? grid / cluster : grid; } // images in flight
 };
+
+// cudaOccupancyMaxActiveClusters of the cluster kernels, asked once per (mode, size, flavour, width)
+int clusters_resident(const vp8_gpu_ctx* c, int kernel_mode, int cluster, bool split, int max_mb_cols) {
+	const uint64_t key = ((uint64_t)max_mb_cols << 16) | ((uint64_t)kernel_mode << 8) | ((uint64_t)cluster << 1) | (split ? 1 : 0);
+	auto it = c->cluster_fit.find(key);
+	if (it != c->cluster_fit.end()) return it->second;
+	int r = vp8_pairs_max_active_clusters(kernel_mode, cluster, split ? 1 : 0, max_mb_cols);
+	if (r <= 0) r = c->sm_count / cluster; // the query failed: the old estimate
+	c->cluster_fit[key] = r;
+	if (getenv("VP8_GPU_TRACE")) fprintf(stderr, "[vp8gpu] clusters of %d CTAs (%s, mode %d, %d columns): %d resident at once\n", cluster, split ? "split" : "fused", kernel_mode, max_mb_cols, r);
+	return r;
+}
 
 int plan_launch(const vp8_gpu_ctx* c, int n, int max_mb_cols, int max_rows, int kernel_mode, LaunchPlan* out) {
 	LaunchPlan p;
@@ -743,12 +760,22 @@ int plan_launch(const vp8_gpu_ctx* c, int n, int max_mb_cols, int max_rows, int 
 	// Few big frames: spread each over a thread-block cluster so that one image can use several SMs. Worth it only when
 	// 16-warp CTAs are already in use, the GPU would otherwise be mostly idle and the frame has rows to hand out.
 	if (p.warps == 16 && c->tune_cluster != 1) {
+		// From 4 CTAs per image on, the fused mode runs the split flavour (vp8_mb_split: a reconstruction warp and a filter warp
+		// per row pair, so a CTA's 16 warps take 16 macroblock rows instead of 32). A cluster size stays as long as that many
+		// clusters are resident at once (a cluster lives inside one GPC: fewer fit than SMs / size, and a second wave costs a
+		// whole frame's latency) and more than half of its CTAs get rows (a 1080p frame, 68 rows, fused flavour: 3 of 4 CTAs
+		// busy beats 2 CTAs that need a second round).
 		int want = c->tune_cluster > 1 ? c->tune_cluster : 8;
-		// a CTA's 16 warps take 32 macroblock rows; a cluster size stays as long as the GPU has room for it and more than
-		// half of its CTAs get rows (a 1080p frame, 68 rows: 3 of 4 CTAs busy beats 2 CTAs that need a second round)
-		while (want > 1 && (n * want > c->sm_count || 32 * (want / 2) >= max_rows)) want /= 2;
+		bool split = false;
+		int resident = 0;
+		for (; want > 1; want /= 2) {
+			split = c->split && kernel_mode == VP8_K_RECON_FILTER && want >= 4;
+			resident = clusters_resident(c, kernel_mode, want, split, max_mb_cols);
+			if (n <= resident && (split ? 16 : 32) * (want / 2) < max_rows) break;
+		}
 		p.cluster = want;
-		if (p.cluster > 1) p.grid = std::min(n, c->sm_count / p.cluster) * p.cluster;
+		p.split = split && want > 1;
+		if (p.cluster > 1) p.grid = std::min(n, resident) * p.cluster;
 	}
 	// Many images: the lockstep flavour packs `groups` of them into one CTA per SM (kernel 3 only, where the classic
 	// choice would be 4 warps per image anyway).
@@ -817,7 +844,7 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 		const Vp8ImgDesc* descs = b->d_desc + sg.first;
 		rc = p.groups ? vp8_launch_lockstep(kernel_mode, descs, sg.count, b->max_mb_cols, p.grid, p.groups, b->d_scratch, b->stream)
 		              : vp8_launch_pairs(kernel_mode, p.warps, descs, sg.count, b->max_mb_cols, p.grid, b->d_scratch, p.cluster,
-		                                 c->kernel_version == 3 && c->lockstep_small, b->stream);
+		                                 p.split ? 2 : (c->kernel_version == 3 && c->lockstep_small), b->stream);
 		if (rc != 0) break;
 		c->launches++;
 	}
@@ -832,6 +859,7 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 	c->last_warps = p.warps;
 	c->last_grid = p.grid;
 	c->last_cluster = p.cluster;
+	c->last_split = p.split;
 	c->last_groups = p.groups;
 	c->last_segments = (int)segs.size();
 	c->last_smem = p.groups ? vp8_lockstep_smem_bytes(p.groups, b->max_mb_cols) : vp8_pairs_smem_bytes(p.warps, b->max_mb_cols);
@@ -1213,6 +1241,7 @@ int vp8_gpu_init(int device, void* stream, vp8_gpu_ctx** out) {
 	if (const char* w = getenv("VP8_GPU_HOST_THREADS")) c->host_threads = atoi(w);
 	if (const char* w = getenv("VP8_GPU_DENSE_PASSTHROUGH")) c->dense_passthrough = atoi(w) != 0;
 	if (const char* w = getenv("VP8_GPU_LOCKSTEP_SMALL")) c->lockstep_small = atoi(w) != 0;
+	if (const char* w = getenv("VP8_GPU_SPLIT")) c->split = atoi(w) != 0;
 	if (const char* w = getenv("VP8_GPU_COMPACT")) c->transport_mode = std::min(2, std::max(0, atoi(w)));
 	if (const char* w = getenv("VP8_GPU_IMAGES_PER_SM")) c->tune_imgs_per_sm = atoi(w);
 	*out = c;
@@ -1285,7 +1314,14 @@ int vp8_gpu_set_cluster(vp8_gpu_ctx* c, int ctas_per_image) {
 	return 0;
 }
 
+int vp8_gpu_set_cluster_split(vp8_gpu_ctx* c, int split) {
+	if (!c) return fail(EINVAL, "no context");
+	c->split = split != 0;
+	return 0;
+}
+
 int vp8_gpu_last_cluster(const vp8_gpu_ctx* c) { return c ? c->last_cluster : 0; }
+int vp8_gpu_last_split(const vp8_gpu_ctx* c) { return c ? (int)c->last_split : 0; }
 int vp8_gpu_last_groups(const vp8_gpu_ctx* c) { return c ? c->last_groups : 0; }
 int vp8_gpu_last_segments(const vp8_gpu_ctx* c) { return c ? c->last_segments : 0; }
 

@@ -43,6 +43,7 @@ constexpr int kHalfSkew = 64; // see HalfWs::skew_
 #define RTN_Y RT_Y
 #define RTN_U RT_U
 #define RTN_V RT_V
+#define VP8P_TILE_TAKEN() // vp8_mb_split: the filter warp has read the reconstruction tile
 
 namespace {
 
@@ -148,6 +149,8 @@ __device__ __forceinline__ bool planes_wide_ok(const Vp8ImgDesc* sd) {
 }
 
 constexpr int kClusterProg = 1024; // progress stamps per image in cluster mode (VP8 frames have at most 1024 macroblock rows)
+// per-slot scratch in global memory (L2): [tf: 8 x line][tu: 2 x line][stamps][second set of stamps: vp8_mb_split's filter chain]
+__host__ __device__ constexpr size_t scratch_stride(int line_px) { return (size_t)10 * line_px + 2 * kClusterProg * 4; }
 
 #ifndef VP8_PAIR_MIN_CTAS
 #define VP8_PAIR_MIN_CTAS(NW) ((NW) == 4 ? 7 : (NW) == 8 ? 3 : 1)
@@ -179,7 +182,7 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 	const int c_rank = CL ? (int)cluster_ctarank() : 0, c_size = CL ? (int)cluster_nctarank() : 1;
 	const int slot = CL ? blockIdx.x / c_size : blockIdx.x, n_slots = CL ? gridDim.x / c_size : gridDim.x;
 	// per-slot scratch in global memory (L2): [tf: 8 x line][tu: 2 x line][progress stamps: one per macroblock row]
-	uint8_t* const sc = tf_scratch + (size_t)slot * ((size_t)10 * line_px + kClusterProg * 4);
+	uint8_t* const sc = tf_scratch + (size_t)slot * scratch_stride(line_px);
 	uint8_t* tf_y = sc; // last four filtered rows of the row above
 	uint8_t* tf_u = tf_y + 4 * line_px;
 	uint8_t* tf_v = tf_u + 2 * line_px;
@@ -320,6 +323,223 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 	}
 }
 
+
+// ------------------------------------------------------------------------------------------------ split flavour (latency)
+// One big frame on a cluster is a dependency chain: 2 x rows + columns macroblock steps, each walked by ONE warp through
+// the whole step (about 2350 mostly dependent instructions, 9 us). Here a row pair is served by TWO warps: the
+// reconstruction warp runs parts A, B, C1, C3 (prediction chain: needs only the UNFILTERED neighbours) and hands the tile to
+// the filter warp, which runs part C2 (filter chain: needs only the FILTERED rows of the row above and that tile) one
+// macroblock behind it. Both chains advance at the pace of their own part of the step. The tile is double-buffered; a pair
+// of sequence counters in shared memory says which macroblock each buffer holds / has been taken out of. Rows are dealt to
+// the cluster's engines (8 per CTA) round-robin; both chains publish their own progress stamps (st.release / ld.acquire).
+struct __align__(16) SplitWs : HalfWs {
+	uint8_t rt2_y[17 * 24]; // second reconstruction tile
+	uint8_t rt2_u[9 * 12];
+	uint8_t rt2_v[9 * 12];
+	int full[2];            // (half 0 of the engine only) sequence number + 1 of the macroblock step buffer b holds
+	int taken[2];           // ... that the filter warp has copied out of buffer b
+	uint8_t hand[2][2];     // [buffer][half]: seg | bpred << 2 | inner << 3 of that macroblock
+	uint8_t pad_[124];      // keeps sizeof % 128 == 64 (see HalfWs::skew_)
+};
+static_assert(sizeof(SplitWs) % 16 == 0 && sizeof(SplitWs) % 128 == 64, "SplitWs layout");
+
+__global__ void __launch_bounds__(16 * 32, 1)
+vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, uint8_t* __restrict__ tf_scratch) {
+	constexpr bool RECON = true, CL = true;
+	constexpr int NW = 16, kEngines = NW / 2;
+	constexpr uint32_t FULL = 0xffffffffu;
+	constexpr int prog_mask = kClusterProg - 1;
+	extern __shared__ __align__(16) uint8_t smem[];
+	Vp8ImgDesc* sd = reinterpret_cast<Vp8ImgDesc*>(smem);
+	uint32_t* btab = reinterpret_cast<uint32_t*>(smem + 256);
+	const int line_c = line_px / 2;
+	const int c_rank = (int)cluster_ctarank(), c_size = (int)cluster_nctarank();
+	const int slot = blockIdx.x / c_size, n_slots = gridDim.x / c_size;
+	uint8_t* const sc = tf_scratch + (size_t)slot * scratch_stride(line_px);
+	uint8_t* tf_y = sc;
+	uint8_t* tf_u = tf_y + 4 * line_px;
+	uint8_t* tf_v = tf_u + 2 * line_px;
+	uint8_t* tu_y = sc + 8 * line_px;
+	uint8_t* tu_u = tu_y + line_px;
+	uint8_t* tu_v = tu_u + line_px / 2;
+	volatile int* const prog_r = reinterpret_cast<volatile int*>(sc + (size_t)10 * line_px); // reconstruction chain
+	volatile int* const prog_f = prog_r + kClusterProg;                                      // filter chain
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int hl = lane & 15, half = lane >> 4, hbit = lane & 16;
+	const int engine = warp >> 1, role = warp & 1; // role 0: reconstruction, 1: filter
+	SplitWs* const wsb = reinterpret_cast<SplitWs*>(smem + 256 + kBtabWords * 4);
+	SplitWs& ws = wsb[engine * 2 + half];
+	SplitWs& eng = wsb[engine * 2]; // the engine's hand-over counters live in its first half
+	volatile int* const v_full = eng.full;
+	volatile int* const v_taken = eng.taken;
+
+	for (int i = tid; i < kBtabWords; i += NW * 32) {
+		const int h = i / 176, m = (i % 176) / 16, p = i % 16, base = h * 16;
+		uint32_t a = 0, b = 0, c = 0, kind = 0;
+		if (m == 0) kind = 2;
+		else if (m == 1) { a = 5 - (p >> 2); b = 7 + (p & 3); c = 6; kind = 1; }
+		else if (m == 10) kind = 3;
+		else {
+			const int tap = c_bpred_taps[m * 16 + p], t0 = tap & 15;
+			a = t0; b = t0 + 1; c = (tap & 16) ? t0 : t0 + 2;
+		}
+		btab[i] = (base + a) | ((base + b) << 8) | ((base + c) << 16) | (VP8P_KIND_CODE(kind) << 24);
+	}
+
+	const bool tl_luma = hl < 8;
+	const int tl_by = tl_luma ? (hl >> 1) * 4 : (hl & 1) * 4;
+	const int tl_bx0 = tl_luma ? (hl & 1) * 8 : 0;
+	const int bit0 = tl_luma ? 2 * hl : (hl < 10 ? 16 + 2 * (hl - 8) : (hl < 12 ? 20 + 2 * (hl - 10) : 24));
+	const int px_r = hl >> 2, px_c = hl & 3;
+	const int e_dy = hl <= 2 ? 3 : (hl <= 5 ? 5 - hl : -1);
+	const int e_dx = hl <= 6 ? -1 : (hl == 15 ? 7 : hl - 7);
+	const int16_t* const bp_res = &ws.res[0][0] + hl;
+	const uint8_t* const bp_tab = reinterpret_cast<const uint8_t*>(btab + half * 176 + hl);
+	const bool dc_tap = (hl >= 2 && hl <= 5) || (hl >= 7 && hl <= 10);
+
+#undef RT_Y
+#undef RT_U
+#undef RT_V
+#undef RTN_Y
+#undef RTN_U
+#undef RTN_V
+#define RT_Y rt_y
+#define RT_U rt_u
+#define RT_V rt_v
+#define RTN_Y rtn_y
+#define RTN_U rtn_u
+#define RTN_V rtn_v
+
+	for (int img = slot; img < n_images; img += n_slots) {
+		cluster_sync_all(); // previous image fully retired before its lines, stamps and descriptor are reused
+		{
+			const uint32_t* src = reinterpret_cast<const uint32_t*>(descs + img);
+			uint32_t* dst = reinterpret_cast<uint32_t*>(sd);
+			for (int i = tid; i < (int)(sizeof(Vp8ImgDesc) / 4); i += NW * 32) dst[i] = src[i];
+			if (c_rank == 0)
+				for (int i = tid; i < 2 * kClusterProg; i += NW * 32) prog_r[i] = 0;
+			if (role == 0 && lane < 2) v_full[lane] = v_taken[lane] = 0;
+		}
+		__threadfence();
+		cluster_sync_all();
+
+		int cols, rows;
+		OutPlane oy, ou, ov;
+		bool words_ok, wide_ok, lf_simple;
+		const uint8_t *g_ymode, *g_seg, *g_hc;
+#include "vp8_pairs_image.inc"
+
+		int seq = 0; // macroblock steps this engine has begun in this image: both of its warps count alike
+		for (int p = c_rank * kEngines + engine; 2 * p < rows; p += kEngines * c_size) {
+			int y;
+			bool row_ok, last_row;
+			size_t mb_row0;
+			uint32_t staged_nz = 0;
+			if (role == 0) {
+				uint8_t* const rt_y = (seq & 1) ? ws.rt2_y : ws.rt_y;
+				uint8_t* const rt_u = (seq & 1) ? ws.rt2_u : ws.rt_u;
+				uint8_t* const rt_v = (seq & 1) ? ws.rt2_v : ws.rt_v;
+				// the first tile of the row is written here (left border): the filter warp must be done with what it held
+				if (lane == 0)
+					while (v_taken[seq & 1] < seq - 1) __nanosleep(20);
+				__syncwarp();
+#include "vp8_pairs_row.inc"
+			} else {
+				y = 2 * p + half;
+				row_ok = y < rows;
+				last_row = (y == rows - 1);
+				mb_row0 = 0;
+			}
+			(void)mb_row0;
+
+			for (int t = 0; t < cols + 2; t++, seq++) {
+				const int b = seq & 1;
+				uint8_t* const rt_y = b ? ws.rt2_y : ws.rt_y;
+				uint8_t* const rt_u = b ? ws.rt2_u : ws.rt_u;
+				uint8_t* const rt_v = b ? ws.rt2_v : ws.rt_v;
+				if (role == 0) {
+					// ================================================= reconstruction warp: parts A, B, C1, C3
+					constexpr bool FILTER = false; // (part A: the filtered rows of the row above are the other warp's business)
+#undef VP8P_TA_DECL
+#define VP8P_TA_DECL [[maybe_unused]] uint32_t ta_y = 0, ta_c = 0;
+					volatile int* const prog = prog_r;
+					uint8_t* const rtn_y = b ? ws.rt_y : ws.rt2_y;
+					uint8_t* const rtn_u = b ? ws.rt_u : ws.rt2_u;
+					uint8_t* const rtn_v = b ? ws.rt_v : ws.rt2_v;
+					uint8_t* const bp_edge = rt_y + e_dy * 24 + e_dx;
+					uint8_t* const bp_out = rt_y + px_r * 24 + px_c;
+					// buffer b last held the macroblock of step seq - 2: taken out by now?
+					if (lane == 0)
+						while (v_taken[b] < seq - 1) __nanosleep(20);
+					__syncwarp();
+#define VP8P_STEP_ACTIVE true
+#include "vp8_pairs_step_a.inc"
+#include "vp8_pairs_step_b.inc"
+#include "vp8_pairs_step_c1.inc"
+#include "vp8_pairs_step_c3.inc"
+#undef VP8P_STEP_ACTIVE
+#undef VP8P_TA_DECL
+#define VP8P_TA_DECL uint32_t ta_y = 0, ta_c = 0;
+					if (hl == 0) eng.hand[b][half] = (uint8_t)(seg | (bpred ? 4 : 0) | (inner ? 8 : 0));
+					__syncwarp();
+					if (lane == 0) {
+						__threadfence_block();
+						v_full[b] = seq + 1;
+					}
+				} else {
+					// ================================================= filter warp: part C2, one hand-over behind
+					constexpr bool FILTER = true;
+					const int x = t - 2 * half;
+					const bool v = row_ok && x >= 0 && x < cols, last_col = (x == cols - 1);
+					if (p > 0 && t < cols) { // row y (half 0) needs the filtered rows of MB(x+1, y-1)
+						if (lane == 0) {
+							const int target = 2 * p * kStampRow + min(t + 2, cols);
+							while (ld_acquire_gpu(&prog_f[(2 * p - 1) & prog_mask]) < target) __nanosleep(20);
+						}
+					}
+					__syncwarp();
+					uint32_t ta_y = 0, ta_c = 0;
+					if (v && y > 0) {
+						ta_y = ldcg32(tf_y + (hl >> 2) * line_px + 16 * x + 4 * (hl & 3));
+						ta_c = ldcg32((hl < 8 ? tf_u : tf_v) + ((hl & 7) >> 1) * line_c + 8 * x + 4 * (hl & 1));
+					}
+					if (lane == 0)
+						while (v_full[b] < seq + 1) __nanosleep(20);
+					__syncwarp();
+					__threadfence_block();
+					const int hb = eng.hand[b][half];
+					const int seg = hb & 3;
+					const bool bpred = (hb & 4) != 0, inner = (hb & 8) != 0;
+#undef VP8P_TILE_TAKEN
+#define VP8P_TILE_TAKEN()                                                                                      \
+	if (lane == 0) { /* the tile has been read (ordered by the __syncwarp before): the buffer may be written again */ \
+		__threadfence_block();                                                                                 \
+		v_taken[b] = seq + 1;                                                                                  \
+	}
+#include "vp8_pairs_step_c2.inc"
+#undef VP8P_TILE_TAKEN
+#define VP8P_TILE_TAKEN()
+					__syncwarp();
+					if (hl == 0 && v) st_release_gpu(&prog_f[y & prog_mask], (y + 1) * kStampRow + x + 1);
+				}
+			}
+		}
+	}
+#undef RT_Y
+#undef RT_U
+#undef RT_V
+#undef RTN_Y
+#undef RTN_U
+#undef RTN_V
+#define RT_Y ws.rt_y
+#define RT_U ws.rt_u
+#define RT_V ws.rt_v
+#define RTN_Y RT_Y
+#define RTN_U RT_U
+#define RTN_V RT_V
+}
+
 // ------------------------------------------------------------------------------------------------ lockstep flavour
 // Same warps, same step (vp8_pairs_step_a/_b.inc), different schedule. The step is ~2500 instructions of mostly straight-line
 // code, far beyond the 32 KB instruction cache of an SM: 28 independent warps stream it from L2 at 28 different places
@@ -396,7 +616,7 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 	uint8_t* tu_v = tu_u + line_px / 2;
 	HalfWs& ws = *reinterpret_cast<HalfWs*>(__cvta_shared_to_generic(ws_s));
 	// per-slot scratch in global memory (L2), same layout as the classic kernel: [tf: 8 x line][unused 2 x line][unused stamps]
-	uint8_t* const sc = tf_scratch + (size_t)slot * ((size_t)10 * line_px + kClusterProg * 4);
+	uint8_t* const sc = tf_scratch + (size_t)slot * scratch_stride(line_px);
 	uint8_t* tf_y = sc;
 	uint8_t* tf_u = tf_y + 4 * line_px;
 	uint8_t* tf_v = tf_u + 2 * line_px;
@@ -569,6 +789,29 @@ int launch_pairs_t(const Vp8ImgDesc* descs, int n, int line_px, int grid, size_t
 	return (int)cudaGetLastError();
 }
 
+size_t split_smem_bytes() { return 256 + kBtabWords * 4 + 16 * sizeof(SplitWs); }
+
+int launch_split(const Vp8ImgDesc* descs, int n, int line_px, int grid, uint8_t* scratch, int cluster, cudaStream_t st) {
+	const size_t smem = split_smem_bytes();
+	cudaError_t e = cudaFuncSetAttribute(vp8_mb_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return (int)e;
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3(grid);
+	cfg.blockDim = dim3(16 * 32);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = (unsigned)cluster;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	e = cudaLaunchKernelEx(&cfg, vp8_mb_split, descs, n, line_px, scratch);
+	if (e != cudaSuccess) return (int)e;
+	return (int)cudaGetLastError();
+}
+
 template <int NW, bool RECON, bool FILTER, bool LS>
 int occupancy_pairs_t(size_t smem) {
 	auto k = vp8_mb_pairs<NW, RECON, FILTER, false, LS>;
@@ -578,14 +821,50 @@ int occupancy_pairs_t(size_t smem) {
 	return nb;
 }
 
+template <typename K>
+int max_clusters_of(K k, size_t smem, int cluster) {
+	if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3(cluster);
+	cfg.blockDim = dim3(16 * 32);
+	cfg.dynamicSmemBytes = smem;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = (unsigned)cluster;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	int n = 0;
+	if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) != cudaSuccess) {
+		(void)cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
 } // namespace
+
+// How many clusters of `cluster` CTAs the device keeps resident at once (they must fit inside one GPC each, so this is
+// fewer than SMs / cluster): the cluster kernels of `mode`, or vp8_mb_split.
+int vp8_pairs_max_active_clusters(int mode, int cluster, int split, int max_mb_cols) {
+	if (cluster < 2) return 0;
+	if (split) return max_clusters_of(vp8_mb_split, split_smem_bytes(), cluster);
+	const size_t smem = (size_t)vp8_pairs_smem_bytes(16, max_mb_cols);
+	switch (mode) {
+		case VP8_K_RECON: return max_clusters_of(vp8_mb_pairs<16, true, false, true, false>, smem, cluster);
+		case VP8_K_RECON_FILTER: return max_clusters_of(vp8_mb_pairs<16, true, true, true, false>, smem, cluster);
+		case VP8_K_FILTER: return max_clusters_of(vp8_mb_pairs<16, false, true, true, false>, smem, cluster);
+	}
+	return 0;
+}
 
 int vp8_pairs_smem_bytes(int warps_per_image, int max_mb_cols) {
 	return kSmemFixed + 2 * 16 * max_mb_cols + warps_per_image * 2 * (int)sizeof(HalfWs);
 }
 
 // one scratch slot per CTA (or per cluster): filtered line (8 B/column), unfiltered line (2 B/column, cluster mode), stamps
-size_t vp8_pairs_scratch_bytes(int slots, int max_mb_cols) { return (size_t)slots * ((size_t)10 * 16 * max_mb_cols + kClusterProg * 4); }
+size_t vp8_pairs_scratch_bytes(int slots, int max_mb_cols) { return (size_t)slots * scratch_stride(16 * max_mb_cols); }
 
 // lockstep flavour (LS) only where it pays: 8 warps per image, three such CTAs per SM (+5-6 %). 4 warps per image run
 // vp8_mb_lockstep instead; with 16 warps per image (one image per SM or per cluster) the frame's dependency chain is the
@@ -612,6 +891,10 @@ int vp8_launch_pairs(int mode, int warps_per_image, const Vp8ImgDesc* descs_dev,
 	const size_t smem = (size_t)vp8_pairs_smem_bytes(warps_per_image, max_mb_cols);
 	const int line_px = 16 * max_mb_cols;
 	cudaStream_t st = (cudaStream_t)stream;
+	if (lockstep == 2) { // the split flavour: fused recon + filter on a cluster only
+		if (mode != VP8_K_RECON_FILTER || warps_per_image != 16 || cluster < 2) return (int)cudaErrorInvalidValue;
+		return launch_split(descs_dev, n_images, line_px, grid_ctas, scratch, cluster, st);
+	}
 	if (warps_per_image != 8) lockstep = 0;
 	VP8_PAIRS_DISPATCH(launch_pairs_t, descs_dev, n_images, line_px, grid_ctas, smem, scratch, cluster, st)
 }
