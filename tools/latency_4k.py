@@ -11,6 +11,7 @@ import webp_decoder_b200 as W
 from webp_decoder_b200 import parse as P
 
 quick = "--quick" in sys.argv
+lf0 = "--lf0" in sys.argv  # loop-filter level forced to 0 (bytes then differ from the digests): what the filter ARITHMETIC costs the chain
 dg = json.loads((ROOT / "bench_data" / "digests.json").read_text())
 ctx = W.Context(0)
 cases = [("checker_3840x2160_q75.webp", 1), ("rgbgrad_3840x2160_q75.webp", 1), ("rgbgrad_1920x1080_q75.webp", 1),
@@ -18,6 +19,8 @@ cases = [("checker_3840x2160_q75.webp", 1), ("rgbgrad_3840x2160_q75.webp", 1), (
          ("rgbgrad_1920x1080_q75.webp", 64)]
 for name, copies in cases:
     pf = P.parse_batch([(ROOT / "bench_data" / name).read_bytes()], pinned=True)
+    if lf0:
+        pf.frames[0].lf_level = 0
     b = ctx.upload([pf.kfs[0]] * copies, [pf.frames[0]] * copies)
     for cl in ((0,) if quick or copies > 1 else (1, 2, 4, 8, 0)):
         for filtered in (True, False):

@@ -733,7 +733,8 @@ int clusters_resident(const vp8_gpu_ctx* c, int kernel_mode, int cluster, bool s
 	auto it = c->cluster_fit.find(key);
 	if (it != c->cluster_fit.end()) return it->second;
 	int r = vp8_pairs_max_active_clusters(kernel_mode, cluster, split ? 1 : 0, max_mb_cols);
-	if (r <= 0) r = c->sm_count / cluster; // the query failed: the old estimate
+	if (r < 0) r = 0;                            // this flavour does not fit (frame too wide for its shared-memory lines)
+	else if (r == 0) r = c->sm_count / cluster; // the query failed: the old estimate
 	c->cluster_fit[key] = r;
 	if (getenv("VP8_GPU_TRACE")) fprintf(stderr, "[vp8gpu] clusters of %d CTAs (%s, mode %d, %d columns): %d resident at once\n", cluster, split ? "split" : "fused", kernel_mode, max_mb_cols, r);
 	return r;
@@ -772,6 +773,11 @@ int plan_launch(const vp8_gpu_ctx* c, int n, int max_mb_cols, int max_rows, int 
 			split = c->split && kernel_mode == VP8_K_RECON_FILTER && want >= 4;
 			resident = clusters_resident(c, kernel_mode, want, split, max_mb_cols);
 			if (n <= resident && (split ? 16 : 32) * (want / 2) < max_rows) break;
+			if (split && resident == 0) { // too wide for the split flavour: the fused one at this size
+				split = false;
+				resident = clusters_resident(c, kernel_mode, want, false, max_mb_cols);
+				if (n <= resident && 32 * (want / 2) < max_rows) break;
+			}
 		}
 		p.cluster = want;
 		p.split = split && want > 1;

@@ -43,6 +43,10 @@ constexpr int kHalfSkew = 64; // see HalfWs::skew_
 #define RTN_Y RT_Y
 #define RTN_U RT_U
 #define RTN_V RT_V
+// the unfiltered line buffer (bottom pixel row of the macroblock row above): shared memory, L2 in cluster mode; vp8_mb_split
+// keeps one line per engine in shared memory and writes the next engine's through the cluster's distributed shared memory
+#define VP8P_LINE_LD(p) ld_line<CL>(p)
+#define VP8P_LINE_ST(p, v) st_line<CL>(p, v)
 #define VP8P_TILE_TAKEN() // vp8_mb_split: the filter warp has read the reconstruction tile
 
 namespace {
@@ -149,8 +153,8 @@ __device__ __forceinline__ bool planes_wide_ok(const Vp8ImgDesc* sd) {
 }
 
 constexpr int kClusterProg = 1024; // progress stamps per image in cluster mode (VP8 frames have at most 1024 macroblock rows)
-// per-slot scratch in global memory (L2): [tf: 8 x line][tu: 2 x line][stamps][second set of stamps: vp8_mb_split's filter chain]
-__host__ __device__ constexpr size_t scratch_stride(int line_px) { return (size_t)10 * line_px + 2 * kClusterProg * 4; }
+// per-slot scratch in global memory (L2): [tf: 8 x line][tu: 2 x line][stamps] (vp8_mb_split uses the tf lines only)
+__host__ __device__ constexpr size_t scratch_stride(int line_px) { return (size_t)10 * line_px + kClusterProg * 4; }
 
 #ifndef VP8_PAIR_MIN_CTAS
 #define VP8_PAIR_MIN_CTAS(NW) ((NW) == 4 ? 7 : (NW) == 8 ? 3 : 1)
@@ -325,6 +329,22 @@ vp8_mb_pairs(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 
 
 // ------------------------------------------------------------------------------------------------ split flavour (latency)
+// distributed shared memory: the address of `local` (a shared-window address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local, int rank) {
+	uint32_t r;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+	return r;
+}
+__device__ __forceinline__ void dsmem_st32(uint32_t addr, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void dsmem_st_release(uint32_t addr, int v) {
+	asm volatile("st.release.cluster.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int smem_ld_acquire_cluster(const int* p) {
+	int v;
+	asm volatile("ld.acquire.cluster.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+	return v;
+}
+
 // One big frame on a cluster is a dependency chain: 2 x rows + columns macroblock steps, each walked by ONE warp through
 // the whole step (about 2350 mostly dependent instructions, 9 us). Here a row pair is served by TWO warps: the
 // reconstruction warp runs parts A, B, C1, C3 (prediction chain: needs only the UNFILTERED neighbours) and hands the tile to
@@ -339,16 +359,18 @@ struct __align__(16) SplitWs : HalfWs {
 	int full[2];            // (half 0 of the engine only) sequence number + 1 of the macroblock step buffer b holds
 	int taken[2];           // ... that the filter warp has copied out of buffer b
 	uint8_t hand[2][2];     // [buffer][half]: seg | bpred << 2 | inner << 3 of that macroblock
-	uint8_t pad_[124];      // keeps sizeof % 128 == 64 (see HalfWs::skew_)
+	int above;              // (half 0 only) reconstruction progress of the row above this engine's row pair, written by the
+	                        // engine that owns it (possibly from another CTA of the cluster): (row + 1) * kStampRow + columns done
+	int above_f;            // ... and the same for the filter chain (what it guards, the filtered rows, travels through L2)
+	uint8_t pad_[116];      // keeps sizeof % 128 == 64 (see HalfWs::skew_)
 };
 static_assert(sizeof(SplitWs) % 16 == 0 && sizeof(SplitWs) % 128 == 64, "SplitWs layout");
 
 __global__ void __launch_bounds__(16 * 32, 1)
 vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, uint8_t* __restrict__ tf_scratch) {
-	constexpr bool RECON = true, CL = true;
+	[[maybe_unused]] constexpr bool RECON = true, CL = true;
 	constexpr int NW = 16, kEngines = NW / 2;
 	constexpr uint32_t FULL = 0xffffffffu;
-	constexpr int prog_mask = kClusterProg - 1;
 	extern __shared__ __align__(16) uint8_t smem[];
 	Vp8ImgDesc* sd = reinterpret_cast<Vp8ImgDesc*>(smem);
 	uint32_t* btab = reinterpret_cast<uint32_t*>(smem + 256);
@@ -359,11 +381,6 @@ vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 	uint8_t* tf_y = sc;
 	uint8_t* tf_u = tf_y + 4 * line_px;
 	uint8_t* tf_v = tf_u + 2 * line_px;
-	uint8_t* tu_y = sc + 8 * line_px;
-	uint8_t* tu_u = tu_y + line_px;
-	uint8_t* tu_v = tu_u + line_px / 2;
-	volatile int* const prog_r = reinterpret_cast<volatile int*>(sc + (size_t)10 * line_px); // reconstruction chain
-	volatile int* const prog_f = prog_r + kClusterProg;                                      // filter chain
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int hl = lane & 15, half = lane >> 4, hbit = lane & 16;
@@ -373,6 +390,19 @@ vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 	SplitWs& eng = wsb[engine * 2]; // the engine's hand-over counters live in its first half
 	volatile int* const v_full = eng.full;
 	volatile int* const v_taken = eng.taken;
+	// The unfiltered line (what the row below predicts from) is per ENGINE and in shared memory: row 2p writes its bottom row
+	// into the engine's own line, in place, for row 2p + 1 of the same warp; row 2p + 1 writes its bottom row into the line of
+	// the engine that owns row pair p + 1 - the next engine of this CTA, or engine 0 of the next CTA of the cluster - through
+	// distributed shared memory, and then that engine's `above` stamp (st.release.cluster). The reader polls and reads its own
+	// shared memory: no L2 round trip on the prediction chain.
+	uint8_t* const lines = smem + 256 + kBtabWords * 4 + 2 * kEngines * sizeof(SplitWs);
+	uint8_t* const tu_y = lines + (size_t)engine * 2 * line_px;
+	uint8_t* const tu_u = tu_y + line_px;
+	uint8_t* const tu_v = tu_u + line_px / 2;
+	const int next_engine = (engine + 1) & (kEngines - 1), next_rank = engine == kEngines - 1 ? (c_rank + 1 == c_size ? 0 : c_rank + 1) : c_rank;
+	// this lane's view of the next engine's line (same offset as tu_y) and of its stamp
+	const uint32_t next_line = dsmem_addr((uint32_t)__cvta_generic_to_shared(lines + (size_t)next_engine * 2 * line_px), next_rank);
+	const uint32_t next_above = dsmem_addr((uint32_t)__cvta_generic_to_shared(role ? &wsb[next_engine * 2].above_f : &wsb[next_engine * 2].above), next_rank);
 
 	for (int i = tid; i < kBtabWords; i += NW * 32) {
 		const int h = i / 176, m = (i % 176) / 16, p = i % 16, base = h * 16;
@@ -417,9 +447,8 @@ vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 			const uint32_t* src = reinterpret_cast<const uint32_t*>(descs + img);
 			uint32_t* dst = reinterpret_cast<uint32_t*>(sd);
 			for (int i = tid; i < (int)(sizeof(Vp8ImgDesc) / 4); i += NW * 32) dst[i] = src[i];
-			if (c_rank == 0)
-				for (int i = tid; i < 2 * kClusterProg; i += NW * 32) prog_r[i] = 0;
 			if (role == 0 && lane < 2) v_full[lane] = v_taken[lane] = 0;
+			if (role == 0 && lane == 2) eng.above = eng.above_f = 0;
 		}
 		__threadfence();
 		cluster_sync_all();
@@ -436,6 +465,7 @@ vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 			bool row_ok, last_row;
 			size_t mb_row0;
 			uint32_t staged_nz = 0;
+			uint8_t nx_ymode = 0, nx_seg = 0, nx_hc = 0, nx_uv = 0, nx_bm = 0; // the next macroblock's syntax, asked for a step ahead
 			if (role == 0) {
 				uint8_t* const rt_y = (seq & 1) ? ws.rt2_y : ws.rt_y;
 				uint8_t* const rt_u = (seq & 1) ? ws.rt2_u : ws.rt_u;
@@ -445,6 +475,13 @@ vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 					while (v_taken[seq & 1] < seq - 1) __nanosleep(20);
 				__syncwarp();
 #include "vp8_pairs_row.inc"
+				if (half == 0 && row_ok) { // the first macroblock's syntax (vp8_pairs_step_a.inc, VP8P_SYNTAX_AHEAD)
+					nx_ymode = g_ymode[mb_row0];
+					nx_seg = g_seg ? g_seg[mb_row0] : 0;
+					nx_hc = g_hc ? g_hc[mb_row0] : 0;
+					nx_uv = sd->uv_mode[mb_row0];
+					nx_bm = sd->bmode[mb_row0 * 16 + hl];
+				}
 			} else {
 				y = 2 * p + half;
 				row_ok = y < rows;
@@ -463,21 +500,46 @@ vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 					constexpr bool FILTER = false; // (part A: the filtered rows of the row above are the other warp's business)
 #undef VP8P_TA_DECL
 #define VP8P_TA_DECL [[maybe_unused]] uint32_t ta_y = 0, ta_c = 0;
-					volatile int* const prog = prog_r;
 					uint8_t* const rtn_y = b ? ws.rt_y : ws.rt2_y;
 					uint8_t* const rtn_u = b ? ws.rt_u : ws.rt2_u;
 					uint8_t* const rtn_v = b ? ws.rt_v : ws.rt2_v;
 					uint8_t* const bp_edge = rt_y + e_dy * 24 + e_dx;
 					uint8_t* const bp_out = rt_y + px_r * 24 + px_c;
 					// buffer b last held the macroblock of step seq - 2: taken out by now?
-					if (lane == 0)
+					if (lane == 0) {
 						while (v_taken[b] < seq - 1) __nanosleep(20);
+						// row 2p needs MB(t + 1, 2p - 1): the engine above says so in this engine's own shared memory
+						if (p > 0 && t < cols) {
+							const int target = 2 * p * kStampRow + min(t + 2, cols);
+							while (smem_ld_acquire_cluster(&eng.above) < target) {
+							}
+						}
+					}
 					__syncwarp();
 #define VP8P_STEP_ACTIVE true
+#define VP8P_STEP_NO_SPIN
+#define VP8P_SYNTAX_AHEAD
+#undef VP8P_LINE_LD
+#undef VP8P_LINE_ST
+#define VP8P_LINE_LD(ptr) ld32(ptr)
+#define VP8P_LINE_ST(ptr, val)                                                                       \
+	do {                                                                                             \
+		if (half) dsmem_st32(next_line + (uint32_t)((ptr) - tu_y), val);                             \
+		else st32(ptr, val);                                                                         \
+	} while (0)
+#define VP8P_PUBLISH()                                                                               \
+	if (lane == 16 && v) dsmem_st_release(next_above, (y + 1) * kStampRow + x + 1);
 #include "vp8_pairs_step_a.inc"
 #include "vp8_pairs_step_b.inc"
 #include "vp8_pairs_step_c1.inc"
 #include "vp8_pairs_step_c3.inc"
+#undef VP8P_PUBLISH
+#undef VP8P_LINE_LD
+#undef VP8P_LINE_ST
+#define VP8P_LINE_LD(p) ld_line<CL>(p)
+#define VP8P_LINE_ST(p, v) st_line<CL>(p, v)
+#undef VP8P_SYNTAX_AHEAD
+#undef VP8P_STEP_NO_SPIN
 #undef VP8P_STEP_ACTIVE
 #undef VP8P_TA_DECL
 #define VP8P_TA_DECL uint32_t ta_y = 0, ta_c = 0;
@@ -495,7 +557,8 @@ vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 					if (p > 0 && t < cols) { // row y (half 0) needs the filtered rows of MB(x+1, y-1)
 						if (lane == 0) {
 							const int target = 2 * p * kStampRow + min(t + 2, cols);
-							while (ld_acquire_gpu(&prog_f[(2 * p - 1) & prog_mask]) < target) __nanosleep(20);
+							while (smem_ld_acquire_cluster(&eng.above_f) < target) {
+							}
 						}
 					}
 					__syncwarp();
@@ -517,15 +580,21 @@ vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 		__threadfence_block();                                                                                 \
 		v_taken[b] = seq + 1;                                                                                  \
 	}
+#define VP8P_TA_LATE
 #include "vp8_pairs_step_c2.inc"
+#undef VP8P_TA_LATE
 #undef VP8P_TILE_TAKEN
 #define VP8P_TILE_TAKEN()
 					__syncwarp();
-					if (hl == 0 && v) st_release_gpu(&prog_f[y & prog_mask], (y + 1) * kStampRow + x + 1);
+					if (lane == 16 && v) { // row 2p + 1's filtered rows (written with st.global.cg, read with ld.global.cg) are out: tell the engine below
+						__threadfence();
+						dsmem_st_release(next_above, (y + 1) * kStampRow + x + 1);
+					}
 				}
 			}
 		}
 	}
+	cluster_sync_all(); // a CTA's shared memory is written by its neighbour: nobody leaves before everybody is done
 #undef RT_Y
 #undef RT_U
 #undef RT_V
@@ -789,10 +858,10 @@ int launch_pairs_t(const Vp8ImgDesc* descs, int n, int line_px, int grid, size_t
 	return (int)cudaGetLastError();
 }
 
-size_t split_smem_bytes() { return 256 + kBtabWords * 4 + 16 * sizeof(SplitWs); }
+size_t split_smem_bytes(int line_px) { return 256 + kBtabWords * 4 + 16 * sizeof(SplitWs) + (size_t)8 * 2 * line_px; }
 
 int launch_split(const Vp8ImgDesc* descs, int n, int line_px, int grid, uint8_t* scratch, int cluster, cudaStream_t st) {
-	const size_t smem = split_smem_bytes();
+	const size_t smem = split_smem_bytes(line_px);
 	cudaError_t e = cudaFuncSetAttribute(vp8_mb_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return (int)e;
 	cudaLaunchConfig_t cfg{};
@@ -849,7 +918,10 @@ int max_clusters_of(K k, size_t smem, int cluster) {
 // fewer than SMs / cluster): the cluster kernels of `mode`, or vp8_mb_split.
 int vp8_pairs_max_active_clusters(int mode, int cluster, int split, int max_mb_cols) {
 	if (cluster < 2) return 0;
-	if (split) return max_clusters_of(vp8_mb_split, split_smem_bytes(), cluster);
+	if (split) { // eight unfiltered lines in shared memory: not for the widest frames (-1: does not fit)
+		if (split_smem_bytes(16 * max_mb_cols) > (size_t)227 * 1024) return -1;
+		return max_clusters_of(vp8_mb_split, split_smem_bytes(16 * max_mb_cols), cluster);
+	}
 	const size_t smem = (size_t)vp8_pairs_smem_bytes(16, max_mb_cols);
 	switch (mode) {
 		case VP8_K_RECON: return max_clusters_of(vp8_mb_pairs<16, true, false, true, false>, smem, cluster);
