@@ -72,7 +72,7 @@ enum Vp8KernelMode {
 // cluster > 1 (2, 4 or 8; needs warps_per_image == 16): every image is processed by a thread-block cluster of that many
 // CTAs; grid_ctas must be a multiple of it and scratch sized for grid_ctas / cluster slots.
 // lockstep = 1 (honoured for 8 warps per image): the warps of a CTA meet at a barrier once per macroblock step.
-// lockstep = 2 (fused mode on a cluster, 16 warps): vp8_mb_split - a reconstruction warp and a filter warp per row pair, the
+// lockstep = 2 (reconstruction modes on a cluster, 16 warps): vp8_mb_split - a reconstruction warp and a filter warp per row pair, the
 // shape for ONE big frame's latency; 8 row pairs per CTA.
 int vp8_launch_pairs(int mode, int warps_per_image, const Vp8ImgDesc* descs_dev, int n_images, int max_mb_cols, int grid_ctas,
                      uint8_t* scratch, int cluster, int lockstep, void* stream);

@@ -770,7 +770,7 @@ int plan_launch(const vp8_gpu_ctx* c, int n, int max_mb_cols, int max_rows, int 
 		bool split = false;
 		int resident = 0;
 		for (; want > 1; want /= 2) {
-			split = c->split && kernel_mode == VP8_K_RECON_FILTER && want >= 4;
+			split = c->split && kernel_mode != VP8_K_FILTER && want >= 4;
 			resident = clusters_resident(c, kernel_mode, want, split, max_mb_cols);
 			if (n <= resident && (split ? 16 : 32) * (want / 2) < max_rows) break;
 			if (split && resident == 0) { // too wide for the split flavour: the fused one at this size

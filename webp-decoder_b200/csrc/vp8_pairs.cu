@@ -366,6 +366,7 @@ struct __align__(16) SplitWs : HalfWs {
 };
 static_assert(sizeof(SplitWs) % 16 == 0 && sizeof(SplitWs) % 128 == 64, "SplitWs layout");
 
+template <bool FILT> // FILT = false: -yuv; the second warp of an engine then only stores the reconstruction tile
 __global__ void __launch_bounds__(16 * 32, 1)
 vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, uint8_t* __restrict__ tf_scratch) {
 	[[maybe_unused]] constexpr bool RECON = true, CL = true;
@@ -551,10 +552,10 @@ vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 					}
 				} else {
 					// ================================================= filter warp: part C2, one hand-over behind
-					constexpr bool FILTER = true;
+					constexpr bool FILTER = FILT;
 					const int x = t - 2 * half;
 					const bool v = row_ok && x >= 0 && x < cols, last_col = (x == cols - 1);
-					if (p > 0 && t < cols) { // row y (half 0) needs the filtered rows of MB(x+1, y-1)
+					if (FILT && p > 0 && t < cols) { // row y (half 0) needs the filtered rows of MB(x+1, y-1)
 						if (lane == 0) {
 							const int target = 2 * p * kStampRow + min(t + 2, cols);
 							while (smem_ld_acquire_cluster(&eng.above_f) < target) {
@@ -562,8 +563,8 @@ vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 						}
 					}
 					__syncwarp();
-					uint32_t ta_y = 0, ta_c = 0;
-					if (v && y > 0) {
+					[[maybe_unused]] uint32_t ta_y = 0, ta_c = 0;
+					if (FILT && v && y > 0) {
 						ta_y = ldcg32(tf_y + (hl >> 2) * line_px + 16 * x + 4 * (hl & 3));
 						ta_c = ldcg32((hl < 8 ? tf_u : tf_v) + ((hl & 7) >> 1) * line_c + 8 * x + 4 * (hl & 1));
 					}
@@ -572,11 +573,12 @@ vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 					__syncwarp();
 					__threadfence_block();
 					const int hb = eng.hand[b][half];
-					const int seg = hb & 3;
-					const bool bpred = (hb & 4) != 0, inner = (hb & 8) != 0;
+					[[maybe_unused]] const int seg = hb & 3;
+					[[maybe_unused]] const bool bpred = (hb & 4) != 0, inner = (hb & 8) != 0;
 #undef VP8P_TILE_TAKEN
 #define VP8P_TILE_TAKEN()                                                                                      \
-	if (lane == 0) { /* the tile has been read (ordered by the __syncwarp before): the buffer may be written again */ \
+	__syncwarp();                                                                                              \
+	if (lane == 0) { /* every lane has read the tile: the buffer may be written again */                       \
 		__threadfence_block();                                                                                 \
 		v_taken[b] = seq + 1;                                                                                  \
 	}
@@ -586,7 +588,7 @@ vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 #undef VP8P_TILE_TAKEN
 #define VP8P_TILE_TAKEN()
 					__syncwarp();
-					if (lane == 16 && v) { // row 2p + 1's filtered rows (written with st.global.cg, read with ld.global.cg) are out: tell the engine below
+					if (FILT && lane == 16 && v) { // row 2p + 1's filtered rows (written with st.global.cg, read with ld.global.cg) are out: tell the engine below
 						__threadfence();
 						dsmem_st_release(next_above, (y + 1) * kStampRow + x + 1);
 					}
@@ -860,9 +862,10 @@ int launch_pairs_t(const Vp8ImgDesc* descs, int n, int line_px, int grid, size_t
 
 size_t split_smem_bytes(int line_px) { return 256 + kBtabWords * 4 + 16 * sizeof(SplitWs) + (size_t)8 * 2 * line_px; }
 
-int launch_split(const Vp8ImgDesc* descs, int n, int line_px, int grid, uint8_t* scratch, int cluster, cudaStream_t st) {
+int launch_split(bool filter, const Vp8ImgDesc* descs, int n, int line_px, int grid, uint8_t* scratch, int cluster, cudaStream_t st) {
 	const size_t smem = split_smem_bytes(line_px);
-	cudaError_t e = cudaFuncSetAttribute(vp8_mb_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	auto k = filter ? vp8_mb_split<true> : vp8_mb_split<false>;
+	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return (int)e;
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3(grid);
@@ -876,7 +879,7 @@ int launch_split(const Vp8ImgDesc* descs, int n, int line_px, int grid, uint8_t*
 	attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
-	e = cudaLaunchKernelEx(&cfg, vp8_mb_split, descs, n, line_px, scratch);
+	e = cudaLaunchKernelEx(&cfg, k, descs, n, line_px, scratch);
 	if (e != cudaSuccess) return (int)e;
 	return (int)cudaGetLastError();
 }
@@ -920,7 +923,9 @@ int vp8_pairs_max_active_clusters(int mode, int cluster, int split, int max_mb_c
 	if (cluster < 2) return 0;
 	if (split) { // eight unfiltered lines in shared memory: not for the widest frames (-1: does not fit)
 		if (split_smem_bytes(16 * max_mb_cols) > (size_t)227 * 1024) return -1;
-		return max_clusters_of(vp8_mb_split, split_smem_bytes(16 * max_mb_cols), cluster);
+		if (mode == VP8_K_FILTER) return -1;
+		return mode == VP8_K_RECON ? max_clusters_of(vp8_mb_split<false>, split_smem_bytes(16 * max_mb_cols), cluster)
+		                           : max_clusters_of(vp8_mb_split<true>, split_smem_bytes(16 * max_mb_cols), cluster);
 	}
 	const size_t smem = (size_t)vp8_pairs_smem_bytes(16, max_mb_cols);
 	switch (mode) {
@@ -964,8 +969,8 @@ int vp8_launch_pairs(int mode, int warps_per_image, const Vp8ImgDesc* descs_dev,
 	const int line_px = 16 * max_mb_cols;
 	cudaStream_t st = (cudaStream_t)stream;
 	if (lockstep == 2) { // the split flavour: fused recon + filter on a cluster only
-		if (mode != VP8_K_RECON_FILTER || warps_per_image != 16 || cluster < 2) return (int)cudaErrorInvalidValue;
-		return launch_split(descs_dev, n_images, line_px, grid_ctas, scratch, cluster, st);
+		if (mode == VP8_K_FILTER || warps_per_image != 16 || cluster < 2) return (int)cudaErrorInvalidValue;
+		return launch_split(mode == VP8_K_RECON_FILTER, descs_dev, n_images, line_px, grid_ctas, scratch, cluster, st);
 	}
 	if (warps_per_image != 8) lockstep = 0;
 	VP8_PAIRS_DISPATCH(launch_pairs_t, descs_dev, n_images, line_px, grid_ctas, smem, scratch, cluster, st)
