@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Randomised soak of the wavefront kernels against the CPU oracle: random batch sizes, frame sizes, content density,
 launch shapes (warps per image, images per CTA, cluster size) and kernel generations, for a given number of seconds.
-Development aid, run under gpurun:  python tools/soak.py [seconds] [seed]"""
+Development aid, run under gpurun:  python tools/soak.py [seconds] [seed] [--clusters]
+--clusters: only the shapes of the cluster kernels (vp8_mb_split / vp8_mb_pairs<16> on 2, 4, 8 CTAs per image): few big frames,
+each oracle frame computed once and decoded under every cluster size and flavour, repeatedly (the hand-over between
+warps / CTAs is timing dependent: the same input many times is the race check)."""
 import sys
 import time
 from pathlib import Path
@@ -60,12 +63,41 @@ def soak(ctx, orc, rng, seconds=None, rounds=None):
     return done, frames_done
 
 
+def soak_clusters(ctx, orc, rng, seconds):
+    t0, done, frames_done = time.time(), 0, 0
+    while time.time() - t0 < seconds:
+        n = int(rng.choice([1, 1, 2, 3, 6]))
+        frames = [fuzz_frame(int(rng.integers(1 << 30)), int(rng.integers(17, 2100)), int(rng.integers(530, 2300)),
+                             density=float(rng.choice([0.0, 0.05, 0.3, 0.9])), amp=int(rng.choice([5, 40, 400, 2500])),
+                             raw=bool(rng.integers(2))) for _ in range(n)]
+        kfs, ds = [f.header() for f in frames], [f.cstruct() for f in frames]
+        want = {flt: [orc.decode_i420(f, flt) for f in frames] for flt in (False, True)}
+        for rep in range(6):
+            for cluster in (2, 4, 8):
+                for split in (False, True):
+                    for flt in (False, True):
+                        ctx.set_cluster(cluster, split)
+                        outs = ctx.decode_i420(kfs, ds, filtered=flt)
+                        cfg = ctx.last_launch_config()
+                        bad = [i for i, (w, o) in enumerate(zip(want[flt], outs)) if not np.array_equal(o, w)]
+                        assert not bad, (f"MISMATCH round {done} rep {rep}: cluster {cluster} split {split} filtered {flt} launch {cfg}: "
+                                         f"frames {bad} of {n}, e.g. {frames[bad[0]].width}x{frames[bad[0]].height}")
+                        frames_done += n
+        done += 1
+    ctx.set_cluster(0, True)
+    return done, frames_done
+
+
 def main():
-    seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
-    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    seconds = float(args[0]) if len(args) > 0 else 60.0
+    rng = np.random.default_rng(int(args[1]) if len(args) > 1 else 1)
     t0 = time.time()
     try:
-        rounds, frames_done = soak(W.Context(0), Oracle(), rng, seconds=seconds)
+        if "--clusters" in sys.argv:
+            rounds, frames_done = soak_clusters(W.Context(0), Oracle(), rng, seconds)
+        else:
+            rounds, frames_done = soak(W.Context(0), Oracle(), rng, seconds=seconds)
     except AssertionError as e:
         print(e)
         return 1
