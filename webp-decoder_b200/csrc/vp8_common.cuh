@@ -219,6 +219,9 @@ __device__ __forceinline__ bool lf_position(int p3, int& p2, int& p1, int& p0, i
 template <int KIND>
 __device__ __forceinline__ void lf_across_columns(uint8_t* q, int lim, int interior, int hev_thr) {
 	uint32_t wp = ld32(q - 4), wq = ld32(q);
+	// p0 == q0 and p1 == q1: every flavour of the filter computes a = 0 and changes nothing, whatever the thresholds say
+	// (simple: f1 = f2 = 0; inner: h = 0 too; macroblock edge: w = 0). Flat areas leave here, two instructions in.
+	if (__byte_perm(wp, 0, 0x4423) == (wq & 0xffffu)) return;
 	int p3 = __byte_perm(wp, 0, 0x4440), p2 = __byte_perm(wp, 0, 0x4441), p1 = __byte_perm(wp, 0, 0x4442), p0 = __byte_perm(wp, 0, 0x4443);
 	int q0 = __byte_perm(wq, 0, 0x4440), q1 = __byte_perm(wq, 0, 0x4441), q2 = __byte_perm(wq, 0, 0x4442), q3 = __byte_perm(wq, 0, 0x4443);
 	if (lf_position<KIND>(p3, p2, p1, p0, q0, q1, q2, q3, lim, interior, hev_thr)) {
@@ -232,7 +235,9 @@ __device__ __forceinline__ void lf_across_columns(uint8_t* q, int lim, int inter
 template <int KIND>
 __device__ __forceinline__ void lf_across_rows(uint8_t* q, int s, int lim, int interior, int hev_thr) {
 	int p3 = 0, q3 = 0;
-	int p2 = q[-3 * s], p1 = q[-2 * s], p0 = q[-s], q0 = q[0], q1 = q[s], q2 = q[2 * s];
+	int p1 = q[-2 * s], p0 = q[-s], q0 = q[0], q1 = q[s];
+	if (p0 == q0 && p1 == q1) return; // a = 0: nothing changes (see lf_across_columns)
+	int p2 = q[-3 * s], q2 = q[2 * s];
 	if (KIND != EDGE_SIMPLE) {
 		p3 = q[-4 * s];
 		q3 = q[3 * s];
