@@ -821,10 +821,26 @@ vp8_mb_lockstep(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px,
 #undef g_hc
 }
 
+// A kernel's dynamic shared memory limit is a property of the FUNCTION, shared by every context and host thread of the
+// process: set to what one launch needs, a second pipeline on the same device that needs less (a narrower frame) could lower it
+// between another thread's set and launch ("invalid argument"). So it is only ever set to the device's opt-in maximum; a request
+// beyond that is refused here.
+template <typename K>
+cudaError_t allow_smem(K k, size_t smem) {
+	static int limit = 0;
+	if (!limit) {
+		int dev = 0, v = 0;
+		if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return cudaErrorUnknown;
+		limit = v;
+	}
+	if (smem > (size_t)limit) return cudaErrorInvalidValue;
+	return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+}
+
 template <int NW, bool RECON, bool FILTER>
 int launch_lockstep_t(const Vp8ImgDesc* descs, int n, int line_px, int grid, int groups, size_t smem, uint8_t* scratch, cudaStream_t st) {
 	auto k = vp8_mb_lockstep<NW, RECON, FILTER>;
-	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = allow_smem(k, smem);
 	if (e != cudaSuccess) return (int)e;
 	k<<<grid, NW * 32 * groups, smem, st>>>(descs, n, line_px, scratch);
 	return (int)cudaGetLastError();
@@ -834,14 +850,14 @@ template <int NW, bool RECON, bool FILTER, bool LS>
 int launch_pairs_t(const Vp8ImgDesc* descs, int n, int line_px, int grid, size_t smem, uint8_t* scratch, int cluster, cudaStream_t st) {
 	if (cluster <= 1) {
 		auto k = vp8_mb_pairs<NW, RECON, FILTER, false, LS>;
-		cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaError_t e = allow_smem(k, smem);
 		if (e != cudaSuccess) return (int)e;
 		k<<<grid, NW * 32, smem, st>>>(descs, n, line_px, scratch);
 		return (int)cudaGetLastError();
 	}
 	if (NW != 16) return (int)cudaErrorInvalidValue; // the cluster flavour is only built for 16 warps per CTA
 	auto k = vp8_mb_pairs<16, RECON, FILTER, true, false>;
-	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = allow_smem(k, smem);
 	if (e != cudaSuccess) return (int)e;
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3(grid);
@@ -865,7 +881,7 @@ size_t split_smem_bytes(int line_px) { return 256 + kBtabWords * 4 + 16 * sizeof
 int launch_split(bool filter, const Vp8ImgDesc* descs, int n, int line_px, int grid, uint8_t* scratch, int cluster, cudaStream_t st) {
 	const size_t smem = split_smem_bytes(line_px);
 	auto k = filter ? vp8_mb_split<true> : vp8_mb_split<false>;
-	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = allow_smem(k, smem);
 	if (e != cudaSuccess) return (int)e;
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3(grid);
@@ -887,7 +903,7 @@ int launch_split(bool filter, const Vp8ImgDesc* descs, int n, int line_px, int g
 template <int NW, bool RECON, bool FILTER, bool LS>
 int occupancy_pairs_t(size_t smem) {
 	auto k = vp8_mb_pairs<NW, RECON, FILTER, false, LS>;
-	if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+	if (allow_smem(k, smem) != cudaSuccess) return 0;
 	int nb = 0;
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, NW * 32, smem) != cudaSuccess) return 0;
 	return nb;
@@ -895,7 +911,7 @@ int occupancy_pairs_t(size_t smem) {
 
 template <typename K>
 int max_clusters_of(K k, size_t smem, int cluster) {
-	if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+	if (allow_smem(k, smem) != cudaSuccess) return 0;
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3(cluster);
 	cfg.blockDim = dim3(16 * 32);
