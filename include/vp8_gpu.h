@@ -138,6 +138,13 @@ int vp8_gpu_filter(vp8_gpu_ctx* ctx, vp8_gpu_batch* b);
 /* m08 on the device: fancy-upsampled RGB24 of the visible frame from the batch's current planes. */
 int vp8_gpu_rgb(vp8_gpu_ctx* ctx, vp8_gpu_batch* b);
 
+/* m09 on the device (after vp8_gpu_rgb): the -png file of every image - signature, IHDR, one IDAT of stored-deflate blocks
+ * over filter-0 scanlines with its Adler-32 and CRC-32, IEND: the bytes reference yuv420_write_png_fd emits
+ * (yuv2rgb_png.c:208-364) - framed in HBM by vp8_png_frame / vp8_png_finish (both checksums are formed in pieces by the
+ * threads that copy the bytes and combined by polynomial arithmetic), so that the host only moves bytes.
+ * EFBIG for an image whose scanlines exceed 0x7FFFFFFF bytes (the reference's own limit). */
+int vp8_gpu_png(vp8_gpu_ctx* ctx, vp8_gpu_batch* b);
+
 enum { VP8_GPU_TIGHT = 0, VP8_GPU_PADDED = 1 };
 
 /* One pass over an uploaded batch: reconstruction, fused with the loop filter when filtered != 0.
@@ -148,8 +155,10 @@ int vp8_gpu_run(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, int filtered, int layout);
  * (Y, U, V tight) resp. the -ppm file ("P6\n<w> <h>\n255\n" + RGB). dst may be pinned or pageable. */
 size_t vp8_gpu_i420_bytes(const vp8_gpu_batch* b);
 size_t vp8_gpu_ppm_bytes(const vp8_gpu_batch* b);
+size_t vp8_gpu_png_bytes(vp8_gpu_batch* b);
 int vp8_gpu_download_i420(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes);
 int vp8_gpu_download_ppm(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes);
+int vp8_gpu_download_png(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes);
 /* Callee-allocated images as the reference returns them (three malloc planes each; yuv420_free). */
 int vp8_gpu_download_images(vp8_gpu_ctx* ctx, vp8_gpu_batch* b, Yuv420Image* out);
 /* Macroblock-aligned planes of frame i (VP8_GPU_PADDED batches), for inspection. */
@@ -167,13 +176,17 @@ int vp8_gpu_decode_i420(vp8_gpu_ctx* ctx, const Vp8KeyFrameHeader* const* kf, co
                         int filtered, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk);
 int vp8_gpu_decode_ppm(vp8_gpu_ctx* ctx, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,
                        uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk);
+int vp8_gpu_decode_png(vp8_gpu_ctx* ctx, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n,
+                       uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk);
+/* Output format of the pipelined calls: what their `ppm` argument selects (any other non-zero value = PPM). */
+enum { VP8_GPU_OUT_I420 = 0, VP8_GPU_OUT_PPM = 1, VP8_GPU_OUT_PNG = 2 };
 size_t vp8_gpu_decode_bytes(const Vp8KeyFrameHeader* const* kf, int n, int ppm);
 
 /* The same pipelined call for frames that are compact already (vp8_parse_webp_compact / vp8_parse_batch_compact,
  * include/vp8_parse.h): nothing is re-scanned or repacked on the host. Frames in pinned memory are read by the copy
  * engine where they are - one transfer per run of frames that sit back to back, which is how vp8_parse_batch_compact
- * lays a batch out - pageable ones are gathered through pinned staging. ppm != 0: -ppm bytes (filtered is implied),
- * else the -yuv / -yuvf bytes. Output layout and capacity as vp8_gpu_decode_i420 / _ppm (vp8_gpu_decode_bytes). */
+ * lays a batch out - pageable ones are gathered through pinned staging. ppm = VP8_GPU_OUT_PPM: -ppm bytes,
+ * VP8_GPU_OUT_PNG: -png bytes (filtered is implied for both), 0: the -yuv / -yuvf bytes. Output layout and capacity as vp8_gpu_decode_i420 / _ppm (vp8_gpu_decode_bytes). */
 int vp8_gpu_decode_compact(vp8_gpu_ctx* ctx, const Vp8CompactFrame* const* frames, int n, int filtered, int ppm, uint8_t* dst,
                            size_t cap, size_t* offsets, size_t* sizes, int chunk);
 
@@ -215,8 +228,9 @@ int vp8_gpu_last_launch_config(const vp8_gpu_ctx* ctx, int* warps_per_image, int
 /* Sum of the device-side durations (CUDA events on the context's stream) of the wavefront launches issued since
  * the previous call, and how many there were. Waits for them to finish. */
 int vp8_gpu_kernel_time(vp8_gpu_ctx* ctx, double* total_ms, int* launches);
-/* Same for the m08 (RGB) launches of vp8_gpu_rgb / vp8_gpu_decode_ppm. */
+/* Same for the m08 (RGB) launches of vp8_gpu_rgb / vp8_gpu_decode_ppm, and for the m09 launch pairs of vp8_gpu_png. */
 int vp8_gpu_rgb_time(vp8_gpu_ctx* ctx, double* total_ms, int* launches);
+int vp8_gpu_png_time(vp8_gpu_ctx* ctx, double* total_ms, int* launches);
 
 /* Host-side per-frame parameter derivation, exported so tests can pin it against the oracle:
  * dq[4][6] = {y1dc,y1ac,uvdc,uvac,y2dc,y2ac} per segment (vp8_recon.c:57-76);

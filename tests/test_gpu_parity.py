@@ -377,6 +377,60 @@ def test_compact_frames_pipelined_decode(lib, gpu_ctx, golden, storage):
     cf.free()
 
 
+def test_png_framed_on_the_device(lib, gpu_ctx, golden, parsed_golden, oracle):
+    """m09 on the GPU (vp8_png_frame / vp8_png_finish): the reference decoder's -png bytes, checksums included, for all 254
+    golden inputs as one mixed-size batch (1x1 .. 960x1162: files of one partial span up to 51 spans), through the staged
+    calls and through every pipelined door; then frame geometries around the segment / scanline / stored-block boundaries
+    against the oracle's writer; then the 1080p / 4K bench inputs (95 / 380 CTAs per file)."""
+    from webp_decoder_b200 import parse as P
+    names = sorted(golden)
+    kfs = [parsed_golden[n][0] for n in names]
+    frs = [parsed_golden[n][1] for n in names]
+    pngs = gpu_ctx.decode_png(kfs, frs)
+    bad = [n for n, p in zip(names, pngs) if sha(p) != golden[n]["png"]]
+    assert not bad, f"-png: {len(bad)} differ, e.g. {bad[:5]}"
+    ms, pairs = gpu_ctx.png_time()
+    assert pairs >= 1 and ms > 0
+    # dense frames, pipelined
+    need = gpu_ctx.decode_bytes(kfs, ppm="png")
+    out = lib.PinnedBuffer(need)
+    out.array[:] = 0x77
+    offs, sizes = gpu_ctx.decode_into(kfs, frs, out.array, ppm="png", chunk=11)
+    bad = [n for n, o, s in zip(names, offs, sizes) if sha(out.array[int(o):int(o) + int(s)]) != golden[n]["png"]]
+    assert not bad, ("decode_png", len(bad), bad[:4])
+    # compact frames and .webp bytes
+    datas = [(GOLDEN / "webp" / n).read_bytes() for n in names]
+    cf = P.parse_batch_compact(datas, threads=4, pinned=True, contiguous=True)
+    for chunk in (9, 0):
+        out.array[:] = 0x55
+        offs, sizes = gpu_ctx.decode_compact_into(cf.frame_list(), out.array, ppm="png", chunk=chunk)
+        bad = [n for n, o, s in zip(names, offs, sizes) if sha(out.array[int(o):int(o) + int(s)]) != golden[n]["png"]]
+        assert not bad, ("compact", chunk, len(bad), bad[:4])
+    cf.free()
+    files = lib.WebpFiles(datas)
+    assert gpu_ctx.decode_webp_bytes(files, ppm="png") == need
+    out.array[:] = 0x33
+    offs, sizes = gpu_ctx.decode_webp_into(files, out.array, ppm="png", chunk=16)
+    bad = [n for n, o, s in zip(names, offs, sizes) if sha(out.array[int(o):int(o) + int(s)]) != golden[n]["png"]]
+    assert not bad, ("webp", len(bad), bad[:4])
+    out.close()
+    # geometries: 3*w+1 around multiples of 16, scanlines longer than a stored block, a block boundary inside a filter byte
+    dims = [(1, 1), (1, 40), (40, 1), (2, 2), (5, 5), (15, 15), (16, 16), (21, 13), (85, 3), (341, 64), (1365, 48), (1366, 49),
+            (129, 129), (1000, 24), (24, 1000), (255, 255), (16383, 4), (7, 9000)]
+    frames = [fuzz_frame(170 + i, w, h, density=0.2 if w * h < 100000 else 0.02) for i, (w, h) in enumerate(dims)]
+    for f, p in zip(frames, gpu_ctx.decode_png([f.header() for f in frames], [f.cstruct() for f in frames])):
+        yuvf = oracle.decode_i420(f, True)
+        assert p == bytes(oracle.png(oracle.rgb(yuvf, f.width, f.height), f.width, f.height)), (f.width, f.height)
+    # bench inputs, each several times in one batch
+    dg = json.loads((ROOT / "bench_data" / "digests.json").read_text())
+    bnames = sorted(dg)
+    pf = P.parse_batch([(ROOT / "bench_data" / n).read_bytes() for n in bnames], pinned=True)
+    order = [k % len(bnames) for k in range(3 * len(bnames))]
+    pngs = gpu_ctx.decode_png([pf.kf_list()[k] for k in order], [pf.frame_list()[k] for k in order])
+    assert [sha(p) for p in pngs] == [dg[bnames[k]]["png"] for k in order]
+    pf.free()
+
+
 @pytest.mark.parametrize("threads,chunk", [(1, 5), (3, 16), (0, 0)])
 def test_webp_bytes_to_pixels_in_one_call(lib, gpu_ctx, golden, threads, chunk):
     """vp8_gpu_decode_webp: .webp bytes in, -yuv/-yuvf/-ppm bytes out; host threads parse chunk k straight into the pinned

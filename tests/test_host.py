@@ -149,6 +149,53 @@ def test_rgb_tile_arithmetic_on_the_host(tmp_path):
     assert out.returncode == 0 and out.stdout.startswith("ok "), out.stdout + out.stderr
 
 
+def test_png_framing_arithmetic_on_the_host(tmp_path):
+    """webp-decoder_b200/csrc/vp8_png.cuh (the arithmetic of the m09 kernels: byte-shifted copy with scanline / stored-block
+    boundaries, Adler-32 from weighted partial sums, CRC-32 pieces combined by multiplication mod the CRC polynomial) also
+    compiles for the host; tests/native/png_check.cpp replays the kernels' whole grid - every CTA, thread, reduction and the
+    finish step - for 74 images against an independent byte-at-a-time writer. One replayed file is then taken apart here
+    with zlib (chunk CRCs, inflate, Adler-32) and compared with the host framing the library exports
+    (vp8_gpu_png_frame, itself pinned by the reference decoder's -png digests)."""
+    import shutil
+    import struct
+    import subprocess
+    import zlib
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "png_check"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-o", str(exe), str(root / "tests" / "native" / "png_check.cpp")], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("ok 74 "), out.stdout + out.stderr
+    w, h = 487, 301  # 3 * w + 1 = 1462; 440062 scanline bytes = 6 full stored blocks + a partial one, 7 spans
+    dump = tmp_path / "replayed.png"
+    assert subprocess.run([str(exe), "dump", str(w), str(h), str(dump)]).returncode == 0
+    png = dump.read_bytes()
+    assert png[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, chunks = 8, []
+    while pos < len(png):
+        n, = struct.unpack(">I", png[pos:pos + 4])
+        kind, data = png[pos + 4:pos + 8], png[pos + 8:pos + 8 + n]
+        crc, = struct.unpack(">I", png[pos + 8 + n:pos + 12 + n])
+        assert zlib.crc32(kind + data) == crc, kind
+        chunks.append((kind, data))
+        pos += 12 + n
+    assert [k for k, _ in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+    assert chunks[0][1] == struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)
+    raw = zlib.decompress(chunks[1][1])  # checks the Adler-32 too
+    lines = np.frombuffer(raw, np.uint8).reshape(h, 3 * w + 1)
+    assert not lines[:, 0].any()
+    import webp_decoder_b200 as lib
+    L = lib.load_library()
+    L.vp8_gpu_png_bound.argtypes, L.vp8_gpu_png_bound.restype = [C.c_uint32, C.c_uint32], C.c_size_t
+    L.vp8_gpu_png_frame.argtypes, L.vp8_gpu_png_frame.restype = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p], C.c_size_t
+    rgb = np.ascontiguousarray(lines[:, 1:])
+    host = np.empty(L.vp8_gpu_png_bound(w, h), np.uint8)
+    n = L.vp8_gpu_png_frame(rgb.ctypes.data, w, h, host.ctypes.data)
+    assert host[:n].tobytes() == png
+
+
 def _dense_to_compact(pf, i):
     """What the compact wire format of parsed frame i must hold, from its dense arrays (numpy restatement of
     include/vp8_parse.h: mask bit b = block b non-zero; 0..15 luma, 16..19 U, 20..23 V, 24 Y2; blocks in bit order)."""

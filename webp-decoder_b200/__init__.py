@@ -29,6 +29,13 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libvp8gpu.so"
 
 TIGHT, PADDED = 0, 1
+OUT_I420, OUT_PPM, OUT_PNG = 0, 1, 2  # what the pipelined calls' `ppm` argument selects ("png" / OUT_PNG: -png files)
+
+
+def _fmt(ppm) -> int:
+    if isinstance(ppm, str):
+        return {"i420": OUT_I420, "ppm": OUT_PPM, "png": OUT_PNG}[ppm]
+    return OUT_PNG if ppm is OUT_PNG or (not isinstance(ppm, bool) and ppm == OUT_PNG) else int(bool(ppm))
 
 EXPORTS = [
     # reference module interfaces
@@ -43,6 +50,7 @@ EXPORTS = [
     "vp8_gpu_last_launch_config", "vp8_gpu_frame_params", "vp8_gpu_kernel_time", "vp8_gpu_rgb_time",
     "vp8_gpu_decode_i420", "vp8_gpu_decode_ppm", "vp8_gpu_decode_bytes", "vp8_gpu_set_kernel",
     "vp8_gpu_png_bound", "vp8_gpu_png_frame", "vp8_gpu_set_transport",
+    "vp8_gpu_png", "vp8_gpu_png_bytes", "vp8_gpu_download_png", "vp8_gpu_decode_png", "vp8_gpu_png_time",
     "vp8_gpu_set_cluster", "vp8_gpu_set_cluster_split", "vp8_gpu_last_split", "vp8_gpu_last_cluster", "vp8_gpu_last_groups", "vp8_gpu_last_segments",
     "vp8_gpu_decode_compact", "vp8_gpu_decode_webp", "vp8_gpu_decode_webp_bytes", "vp8_gpu_last_call_profile", "vp8_gpu_bind_host", "vp8_gpu_last_transport", "vp8_gpu_last_dense_frames",
     # encoder in-loop reconstruction (include/vp8_enc.h)
@@ -101,6 +109,12 @@ def load_library() -> C.CDLL:
     L.vp8_gpu_ppm_bytes.restype = sz
     L.vp8_gpu_download_i420.argtypes = [vp, vp, vp, sz, vp, vp]
     L.vp8_gpu_download_ppm.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.vp8_gpu_png.argtypes = [vp, vp]
+    L.vp8_gpu_png_bytes.argtypes = [vp]
+    L.vp8_gpu_png_bytes.restype = sz
+    L.vp8_gpu_download_png.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.vp8_gpu_decode_png.argtypes = [vp, pp, pp, C.c_int, vp, sz, vp, vp, C.c_int]
+    L.vp8_gpu_png_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.vp8_gpu_download_images.argtypes = [vp, vp, vp]
     L.vp8_gpu_download_padded.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     L.vp8_gpu_batch_size.argtypes = [vp]
@@ -303,6 +317,10 @@ class Context:
     def rgb(self, batch: Batch):
         _check(self._L.vp8_gpu_rgb(self._h, batch._h), "vp8_gpu_rgb")
 
+    def png(self, batch: Batch):
+        """m09 on the device (after rgb): the -png file of every image, framed and checksummed in HBM."""
+        _check(self._L.vp8_gpu_png(self._h, batch._h), "vp8_gpu_png")
+
     # ---- results -----------------------------------------------------------------------------------------
     def _download(self, fn, total_fn, batch: Batch, out: np.ndarray | None):
         total = total_fn(batch._h)
@@ -322,6 +340,10 @@ class Context:
         """Same for the -ppm bytes (header + RGB)."""
         return self._download(self._L.vp8_gpu_download_ppm, self._L.vp8_gpu_ppm_bytes, batch, out)
 
+    def download_png(self, batch: Batch, out: np.ndarray | None = None):
+        """Same for the -png files."""
+        return self._download(self._L.vp8_gpu_download_png, self._L.vp8_gpu_png_bytes, batch, out)
+
     def download_padded(self, batch: Batch, i: int):
         w, h = batch.sizes[i]
         pw, ph = (w + 15) // 16 * 16, (h + 15) // 16 * 16
@@ -334,7 +356,7 @@ class Context:
     def decode_bytes(self, kfs, ppm: bool = False) -> int:
         n = len(kfs)
         kp = (C.c_void_p * n)(*[_addr(k) for k in kfs])
-        return int(self._L.vp8_gpu_decode_bytes(kp, n, int(ppm)))
+        return int(self._L.vp8_gpu_decode_bytes(kp, n, _fmt(ppm)))
 
     def decode_into(self, kfs, frames, out: np.ndarray, filtered: bool = True, ppm: bool = False, chunk: int = 0):
         """vp8_gpu_decode_i420 / vp8_gpu_decode_ppm: upload, kernels and download overlapped chunk by chunk.
@@ -342,7 +364,9 @@ class Context:
         n, kp, fp = self._ptr_arrays(kfs, frames)
         assert out.dtype == np.uint8 and out.flags.c_contiguous
         offs, sizes = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
-        if ppm:
+        if _fmt(ppm) == OUT_PNG:
+            rc = self._L.vp8_gpu_decode_png(self._h, kp, fp, n, out.ctypes.data, out.nbytes, offs.ctypes.data, sizes.ctypes.data, chunk)
+        elif ppm:
             rc = self._L.vp8_gpu_decode_ppm(self._h, kp, fp, n, out.ctypes.data, out.nbytes, offs.ctypes.data, sizes.ctypes.data, chunk)
         else:
             rc = self._L.vp8_gpu_decode_i420(self._h, kp, fp, n, int(bool(filtered)), out.ctypes.data, out.nbytes,
@@ -355,7 +379,7 @@ class Context:
         n = len(frames)
         fp = (C.c_void_p * n)(*[_addr(f) for f in frames])
         offs, sizes = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
-        _check(self._L.vp8_gpu_decode_compact(self._h, fp, n, int(bool(filtered)), int(bool(ppm)), out.ctypes.data, out.nbytes,
+        _check(self._L.vp8_gpu_decode_compact(self._h, fp, n, int(bool(filtered)), _fmt(ppm), out.ctypes.data, out.nbytes,
                                               offs.ctypes.data, sizes.ctypes.data, chunk), "vp8_gpu_decode_compact")
         return offs, sizes
 
@@ -363,12 +387,12 @@ class Context:
         """vp8_gpu_decode_webp: .webp bytes in (a WebpFiles pack), -yuv/-yuvf or -ppm bytes out; host threads parse
         chunk k while the GPU works on the chunks before it."""
         offs, sizes = np.zeros(files.n, np.uint64), np.zeros(files.n, np.uint64)
-        _check(self._L.vp8_gpu_decode_webp(self._h, files.ptrs, files.sizes, files.n, int(bool(filtered)), int(bool(ppm)), out.ctypes.data,
+        _check(self._L.vp8_gpu_decode_webp(self._h, files.ptrs, files.sizes, files.n, int(bool(filtered)), _fmt(ppm), out.ctypes.data,
                                            out.nbytes, offs.ctypes.data, sizes.ctypes.data, chunk), "vp8_gpu_decode_webp")
         return offs, sizes
 
     def decode_webp_bytes(self, files: "WebpFiles", ppm: bool = False) -> int:
-        return int(self._L.vp8_gpu_decode_webp_bytes(files.ptrs, files.sizes, files.n, int(bool(ppm))))
+        return int(self._L.vp8_gpu_decode_webp_bytes(files.ptrs, files.sizes, files.n, _fmt(ppm)))
 
     def last_call_profile(self):
         t, h, w = C.c_double(), C.c_double(), C.c_double()
@@ -401,6 +425,18 @@ class Context:
         finally:
             b.free()
 
+    def decode_png(self, kfs, frames):
+        """List of PNG byte strings, one per frame (what `decoder -png` writes), framed on the device."""
+        b = self.upload(kfs, frames)
+        try:
+            self.run(b, True, TIGHT)
+            self.rgb(b)
+            self.png(b)
+            buf, offs, sizes = self.download_png(b)
+            return [buf[int(o):int(o) + int(s)].tobytes() for o, s in zip(offs, sizes)]
+        finally:
+            b.free()
+
     # ---- counters ----------------------------------------------------------------------------------------
     @property
     def launches(self) -> int:
@@ -424,6 +460,12 @@ class Context:
         """(total_ms, launches) of the m08 RGB launches since the previous call."""
         ms, n = C.c_double(), C.c_int()
         _check(self._L.vp8_gpu_rgb_time(self._h, C.byref(ms), C.byref(n)), "vp8_gpu_rgb_time")
+        return ms.value, n.value
+
+    def png_time(self):
+        """(total_ms, launch pairs) of the m09 launches (vp8_png_frame + vp8_png_finish) since the previous call."""
+        ms, n = C.c_double(), C.c_int()
+        _check(self._L.vp8_gpu_png_time(self._h, C.byref(ms), C.byref(n)), "vp8_gpu_png_time")
         return ms.value, n.value
 
     def last_launch_config(self):

@@ -60,6 +60,17 @@ struct Vp8RgbDesc {
 	uint32_t pad_[2];
 };
 
+// Work item of the PNG framing kernels (vp8_png.cu): one RGB24 image in, the reference's -png file out.
+struct Vp8PngDesc {
+	const uint8_t* rgb; // tight RGB24, 4-byte aligned, readable up to the next multiple of 4 bytes
+	uint8_t* out;       // 16-byte aligned, vp8_png_file_bytes() rounded up to 16 bytes writable
+	uint32_t width, height;
+	uint32_t first_cta; // CTAs of the images before this one
+	uint32_t crc_init;  // the CRC's initial value carried over the main kernel's region (vp8_png_fill_desc)
+	uint8_t head[44];   // the 43 bytes in front of the first stored block (vp8_png_fill_desc)
+	uint32_t pad_;
+};
+
 enum Vp8KernelMode {
 	VP8_K_RECON = 0,        // m06 only: unfiltered pixels out
 	VP8_K_RECON_FILTER = 1, // m06+m07 fused: filtered pixels out, single pass
@@ -89,3 +100,12 @@ int vp8_lockstep_max_groups(int max_mb_cols); // how many groups fit in the shar
 // m08 (vp8_rgb.cu). tiles_per_image: host array, vp8_rgb_tiles() of every image.
 int vp8_launch_rgb(const Vp8RgbDesc* descs_dev, int n_images, const uint32_t* tiles_per_image, void* stream);
 uint32_t vp8_rgb_tiles(uint32_t width, uint32_t height);
+// m09 (vp8_png.cu). Host side: vp8_png_tables() builds the checksum tables (copy vp8_png_tables_bytes() to the device once),
+// vp8_png_fill_desc() completes a descriptor whose width / height are set; first_cta = running sum of vp8_png_ctas().
+int vp8_launch_png(const Vp8PngDesc* descs_dev, int n_images, uint32_t total_ctas, const void* tables_dev, void* accum_dev, void* stream);
+uint32_t vp8_png_ctas(uint32_t width, uint32_t height);
+size_t vp8_png_file_bytes(uint32_t width, uint32_t height);
+size_t vp8_png_accum_bytes(void);
+size_t vp8_png_tables_bytes(void);
+void vp8_png_tables(void* dst);
+void vp8_png_fill_desc(Vp8PngDesc* d, const void* tables);

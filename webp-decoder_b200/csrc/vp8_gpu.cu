@@ -160,6 +160,8 @@ struct vp8_gpu_ctx {
 	// device-side duration of every wavefront launch since the last vp8_gpu_kernel_time() query
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed; // recorded, not yet read
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed_rgb; // same for the m08 launches
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed_png; // same for the m09 launches
+	void* d_png_tables = nullptr;                               // checksum tables of the m09 kernels (first vp8_gpu_png)
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spare;
 	cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr}; // chunk pipeline of vp8_gpu_decode_*
 	cudaEvent_t pipe_ev = nullptr;
@@ -223,6 +225,13 @@ struct vp8_gpu_batch {
 	size_t rgb_bytes = 0;
 	Vp8ImgDesc* d_desc = nullptr;
 	Vp8RgbDesc* d_rgbdesc = nullptr;
+	uint8_t* d_png = nullptr;      // m09: one slot per image (256-byte aligned), the -png file from its first byte
+	size_t png_bytes = 0;
+	std::vector<size_t> png_off;
+	Vp8PngDesc* d_pngdesc = nullptr;
+	void* d_pngacc = nullptr;
+	uint32_t png_ctas = 0;
+	bool pngdesc_up = false, have_png = false;
 	int max_mb_cols = 0;
 	PlaneState state = PLANES_NONE;
 	bool filtered = false, have_rgb = false, have_coeffs = true;
@@ -465,6 +474,9 @@ void batch_destroy(vp8_gpu_ctx* c, vp8_gpu_batch* b, bool known_idle = false) {
 	dev_release(c, b->d_rgb, b->rgb_bytes);
 	dev_release(c, b->d_desc, sizeof(Vp8ImgDesc) * b->n);
 	dev_release(c, b->d_rgbdesc, sizeof(Vp8RgbDesc) * b->n);
+	dev_release(c, b->d_png, b->png_bytes);
+	dev_release(c, b->d_pngdesc, sizeof(Vp8PngDesc) * b->n);
+	dev_release(c, b->d_pngacc, vp8_png_accum_bytes() * b->n);
 	dev_release(c, b->d_scratch, b->scratch_bytes);
 	delete b;
 }
@@ -901,8 +913,10 @@ int write_all(int fd, const void* p, size_t n) {
 	return 0;
 }
 
-// RGB24 of a host I420 image through the device (K3 only).
-int rgb_of_host_image(vp8_gpu_ctx* c, const Yuv420Image* img, std::vector<uint8_t>& rgb) {
+int png_tables_ready(vp8_gpu_ctx* c);
+
+// RGB24 of a host I420 image through the device (m08 kernel only) - or, as_png, the -png file of it (m08 + m09 kernels).
+int rgb_of_host_image(vp8_gpu_ctx* c, const Yuv420Image* img, std::vector<uint8_t>& rgb, bool as_png = false) {
 	const uint32_t w = img->width, h = img->height, cw = (w + 1) / 2, ch = (h + 1) / 2;
 	const size_t ysz = (size_t)w * h, csz = (size_t)cw * ch, total = align_up(ysz) + 2 * align_up(csz);
 	const size_t rgb_bytes = ysz * 3;
@@ -935,7 +949,40 @@ int rgb_of_host_image(vp8_gpu_ctx* c, const Yuv420Image* img, std::vector<uint8_
 		if (lrc) rc = fail(EIO, "rgb launch", (cudaError_t)lrc);
 		else c->launches++;
 	}
-	if (!rc) {
+	if (!rc && as_png) {
+		if ((3 * (uint64_t)w + 1) * h > 0x7FFFFFFFull) rc = fail(EFBIG, "image too large for a single IDAT");
+		const size_t file_len = rc ? 0 : vp8_png_file_bytes(w, h), png_bytes = align_up(file_len), side = 256 + vp8_png_accum_bytes();
+		uint8_t *d_png = nullptr, *d_side = nullptr; // side block: descriptor, then the accumulators
+		if (!rc) rc = png_tables_ready(c);
+		if (!rc && (dev_alloc(c, png_bytes, (void**)&d_png) || dev_alloc(c, side, (void**)&d_side))) rc = -1;
+		if (!rc) {
+			static std::vector<uint8_t> tables;
+			if (tables.empty()) { // callers hold g_default_mu
+				tables.resize(vp8_png_tables_bytes());
+				vp8_png_tables(tables.data());
+			}
+			Vp8PngDesc pd;
+			memset(&pd, 0, sizeof(pd));
+			pd.rgb = d_rgb;
+			pd.out = d_png;
+			pd.width = w;
+			pd.height = h;
+			vp8_png_fill_desc(&pd, tables.data());
+			if (push_table(c, d_side, &pd, sizeof(pd), c->stream)) rc = -1;
+		}
+		if (!rc) {
+			const int lrc = vp8_launch_png((const Vp8PngDesc*)d_side, 1, vp8_png_ctas(w, h), c->d_png_tables, d_side + 256, c->stream);
+			if (lrc) rc = fail(EIO, "png launch", (cudaError_t)lrc);
+			else c->launches += 2;
+		}
+		if (!rc) {
+			rgb.resize(file_len);
+			rc = download(c, c->stream, rgb.data(), d_png, file_len);
+		}
+		cudaStreamSynchronize(c->stream);
+		dev_release(c, d_png, png_bytes);
+		dev_release(c, d_side, side);
+	} else if (!rc) {
 		rgb.resize(rgb_bytes);
 		rc = download(c, c->stream, rgb.data(), d_rgb, rgb_bytes);
 	}
@@ -1209,6 +1256,16 @@ int png_frame(const uint8_t* rgb, uint32_t w, uint32_t h, std::vector<uint8_t>& 
 	return 0;
 }
 
+// Checksum tables of the m09 kernels in device memory, once per context.
+int png_tables_ready(vp8_gpu_ctx* c) {
+	if (c->d_png_tables) return 0;
+	std::vector<uint8_t> t(vp8_png_tables_bytes());
+	vp8_png_tables(t.data());
+	CU(cudaMalloc(&c->d_png_tables, t.size()));
+	CU(cudaMemcpy(c->d_png_tables, t.data(), t.size(), cudaMemcpyHostToDevice));
+	return 0;
+}
+
 } // namespace
 
 // ================================================================================================ C-ABI: batch interface
@@ -1263,7 +1320,8 @@ void vp8_gpu_destroy(vp8_gpu_ctx* c) {
 		if (c->bounce[i]) cudaFreeHost(c->bounce[i]);
 		if (c->bounce_ev[i]) cudaEventDestroy(c->bounce_ev[i]);
 	}
-	for (auto* v : {&c->timed, &c->timed_rgb, &c->spare})
+	if (c->d_png_tables) cudaFree(c->d_png_tables);
+	for (auto* v : {&c->timed, &c->timed_rgb, &c->timed_png, &c->spare})
 		for (auto& ev : *v) {
 			cudaEventDestroy(ev.first);
 			cudaEventDestroy(ev.second);
@@ -1438,12 +1496,14 @@ static int push_rgb_descs(vp8_gpu_ctx* c, vp8_gpu_batch* b, int state) {
 // for. A descriptor table copied on the kernels' own stream is handed to the copy engine only once that event has fired,
 // i.e. behind the arenas of the next chunks the host has queued meanwhile: the first kernels then start 10 ms late
 // (VP8_GPU_TRACE=2 timeline, profiles/README.md r2).
-static int push_tables_ahead(vp8_gpu_ctx* c, vp8_gpu_batch* b, int filtered, bool want_ppm) {
+static int push_png_descs(vp8_gpu_ctx* c, vp8_gpu_batch* b);
+static int push_tables_ahead(vp8_gpu_ctx* c, vp8_gpu_batch* b, int filtered, int format) {
 	if (ensure_planes(c, b, VP8_GPU_TIGHT)) return -1;
 	bool any = false;
 	for (auto& m : b->meta) any |= m.any_filter;
 	if (push_descs(c, b, (filtered && any) ? VP8_K_RECON_FILTER : VP8_K_RECON, VP8_GPU_TIGHT)) return -1;
-	return want_ppm ? push_rgb_descs(c, b, PLANES_TIGHT) : 0;
+	if (format != VP8_GPU_OUT_I420 && push_rgb_descs(c, b, PLANES_TIGHT)) return -1;
+	return format == VP8_GPU_OUT_PNG ? push_png_descs(c, b) : 0;
 }
 
 int vp8_gpu_rgb(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
@@ -1472,6 +1532,115 @@ int vp8_gpu_rgb(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
 	if (rc) return fail(EIO, "rgb launch", (cudaError_t)rc);
 	c->launches += (b->n + 65534) / 65535;
 	b->have_rgb = true;
+	b->have_png = false;
+	return 0;
+}
+
+// m09 on the device (vp8_png.cu): slot layout, work items and accumulators of the batch, sent on the batch's stream.
+static size_t png_slot_bytes(size_t w, size_t h) { return align_up(vp8_png_file_bytes((uint32_t)w, (uint32_t)h)); }
+static int png_layout(vp8_gpu_batch* b) {
+	if (!b->png_off.empty()) return 0;
+	size_t off = 0;
+	uint64_t ctas = 0;
+	b->png_off.resize(b->n);
+	for (int i = 0; i < b->n; i++) {
+		const FrameMeta& m = b->meta[i];
+		if ((3 * (uint64_t)m.width + 1) * m.height > 0x7FFFFFFFull) {
+			b->png_off.clear();
+			return fail(EFBIG, "image too large for a single IDAT");
+		}
+		b->png_off[i] = off;
+		off += png_slot_bytes(m.width, m.height);
+		ctas += vp8_png_ctas(m.width, m.height);
+	}
+	if (ctas > 0x7FFFFFFFull) {
+		b->png_off.clear();
+		return fail(EFBIG, "batch too large for one PNG launch");
+	}
+	b->png_bytes = off;
+	b->png_ctas = (uint32_t)ctas;
+	return 0;
+}
+static int push_png_descs(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
+	if (png_layout(b)) return -1;
+	if (png_tables_ready(c)) return -1;
+	if (!b->d_rgb && dev_alloc(c, b->rgb_bytes, (void**)&b->d_rgb)) return -1;
+	if (!b->d_png && dev_alloc(c, b->png_bytes, (void**)&b->d_png)) return -1;
+	if (!b->d_pngdesc && dev_alloc(c, sizeof(Vp8PngDesc) * b->n, (void**)&b->d_pngdesc)) return -1;
+	if (!b->d_pngacc && dev_alloc(c, vp8_png_accum_bytes() * b->n, &b->d_pngacc)) return -1;
+	if (b->pngdesc_up) return 0;
+	static std::once_flag once;
+	static std::vector<uint8_t> host_tables;
+	std::call_once(once, [] {
+		host_tables.resize(vp8_png_tables_bytes());
+		vp8_png_tables(host_tables.data());
+	});
+	std::vector<Vp8PngDesc> h(b->n);
+	uint32_t first = 0;
+	for (int i = 0; i < b->n; i++) {
+		const FrameMeta& m = b->meta[i];
+		Vp8PngDesc& d = h[i];
+		memset(&d, 0, sizeof(d));
+		d.rgb = b->d_rgb + m.rgb_off + kPpmSlot;
+		d.out = b->d_png + b->png_off[i];
+		d.width = m.width;
+		d.height = m.height;
+		d.first_cta = first;
+		first += vp8_png_ctas(m.width, m.height);
+		// same picture size as the one before: same head and initial-value term
+		if (i && h[i - 1].width == d.width && h[i - 1].height == d.height) {
+			memcpy(d.head, h[i - 1].head, sizeof(d.head));
+			d.crc_init = h[i - 1].crc_init;
+		} else {
+			vp8_png_fill_desc(&d, host_tables.data());
+		}
+	}
+	if (push_table(c, b->d_pngdesc, h.data(), sizeof(Vp8PngDesc) * b->n, b->stream)) return -1;
+	b->pngdesc_up = true;
+	return 0;
+}
+
+int vp8_gpu_png(vp8_gpu_ctx* c, vp8_gpu_batch* b) {
+	if (!c || !b) return fail(EINVAL, "bad arguments");
+	if (!b->have_rgb) return fail(EINVAL, "run vp8_gpu_rgb first");
+	CU(cudaSetDevice(c->device));
+	if (push_png_descs(c, b)) return -1;
+	std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+	if (!c->spare.empty()) {
+		ev = c->spare.back();
+		c->spare.pop_back();
+	} else {
+		CU(cudaEventCreate(&ev.first));
+		CU(cudaEventCreate(&ev.second));
+	}
+	CU(cudaEventRecord(ev.first, b->stream));
+	const int rc = vp8_launch_png(b->d_pngdesc, b->n, b->png_ctas, c->d_png_tables, b->d_pngacc, b->stream);
+	CU(cudaEventRecord(ev.second, b->stream));
+	c->timed_png.push_back(ev);
+	if (c->timed_png.size() > 4096) {
+		c->spare.push_back(c->timed_png.front());
+		c->timed_png.erase(c->timed_png.begin());
+	}
+	if (rc) return fail(EIO, "png launch", (cudaError_t)rc);
+	c->launches += 2;
+	b->have_png = true;
+	return 0;
+}
+
+size_t vp8_gpu_png_bytes(vp8_gpu_batch* b) { return b && !png_layout(b) ? b->png_bytes : 0; }
+
+int vp8_gpu_download_png(vp8_gpu_ctx* c, vp8_gpu_batch* b, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes) {
+	if (!c || !b || !dst) return fail(EINVAL, "bad arguments");
+	if (!b->have_png) return fail(EINVAL, "run vp8_gpu_png first");
+	if (cap < b->png_bytes) return fail(EINVAL, "destination too small");
+	CU(cudaSetDevice(c->device));
+	const FrameMeta& last = b->meta.back();
+	const size_t used = b->png_off.back() + vp8_png_file_bytes(last.width, last.height);
+	if (download(c, b->stream, dst, b->d_png, used)) return -1;
+	for (int i = 0; i < b->n; i++) {
+		if (offsets) offsets[i] = b->png_off[i];
+		if (sizes) sizes[i] = vp8_png_file_bytes(b->meta[i].width, b->meta[i].height);
+	}
 	return 0;
 }
 
@@ -2022,15 +2191,26 @@ int batch_create_webp(vp8_gpu_ctx* c, const uint8_t* const* files, const size_t*
 // whether everything queued on the upload stream so far has already left the host.
 using ChunkMaker = std::function<int(int, int, int, cudaStream_t, bool, vp8_gpu_batch**)>;
 
-static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const ChunkMaker& make_chunk, int filtered, bool want_ppm,
+static int out_format(int ppm) { return ppm == VP8_GPU_OUT_PNG ? VP8_GPU_OUT_PNG : ppm ? VP8_GPU_OUT_PPM : VP8_GPU_OUT_I420; }
+static size_t out_slot_bytes(size_t w, size_t h, int format) {
+	return format == VP8_GPU_OUT_PNG   ? png_slot_bytes(w, h)
+	       : format == VP8_GPU_OUT_PPM ? align_up(kPpmSlot + w * h * 3)
+	                                   : align_up(w * h + 2 * ((w + 1) / 2) * ((h + 1) / 2));
+}
+
+static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const ChunkMaker& make_chunk, int filtered, int format,
                             uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk, bool ramp = true) {
+	const bool want_ppm = format == VP8_GPU_OUT_PPM, want_png = format == VP8_GPU_OUT_PNG;
+	if (want_png)
+		for (int i = 0; i < n; i++)
+			if ((3 * (uint64_t)geom[i].width + 1) * geom[i].height > 0x7FFFFFFFull) return fail(EFBIG, "image too large for a single IDAT");
 	CU(cudaSetDevice(c->device));
 	if (chunk <= 0) chunk = 64;
 	// global layout
 	std::vector<size_t> off(n + 1, 0);
 	for (int i = 0; i < n; i++) {
 		const size_t w = geom[i].width, h = geom[i].height;
-		off[i + 1] = off[i] + (want_ppm ? align_up(kPpmSlot + w * h * 3) : align_up(w * h + 2 * ((w + 1) / 2) * ((h + 1) / 2)));
+		off[i + 1] = off[i] + out_slot_bytes(w, h, format);
 	}
 	if (cap < off[n]) return fail(EINVAL, "destination too small");
 	for (auto& p : c->pipe)
@@ -2104,7 +2284,7 @@ static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const 
 		if (rc) break;
 		ch.b = b;
 		b->stream = s_up;
-		rc = push_tables_ahead(c, b, filtered, want_ppm);
+		rc = push_tables_ahead(c, b, filtered, format);
 		if (rc) break;
 		mark(s_up);
 		if (cudaEventRecord(ch.up, s_up) != cudaSuccess || cudaStreamWaitEvent(s_run, ch.up, 0) != cudaSuccess) {
@@ -2113,7 +2293,8 @@ static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const 
 		}
 		b->stream = s_run; // kernels (and the descriptor upload) of this chunk
 		rc = vp8_gpu_run(c, b, filtered, VP8_GPU_TIGHT);
-		if (!rc && want_ppm) rc = vp8_gpu_rgb(c, b);
+		if (!rc && (want_ppm || want_png)) rc = vp8_gpu_rgb(c, b);
+		if (!rc && want_png) rc = vp8_gpu_png(c, b);
 		if (rc) break;
 		mark(s_run);
 		if (cudaEventRecord(ev_kernel, s_run) != cudaSuccess || cudaStreamWaitEvent(s_down, ev_kernel, 0) != cudaSuccess) {
@@ -2121,7 +2302,10 @@ static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const 
 			break;
 		}
 		const FrameMeta& last = b->meta.back();
-		if (want_ppm) {
+		if (want_png) {
+			const size_t used = b->png_off.back() + vp8_png_file_bytes(last.width, last.height);
+			rc = download(c, s_down, dst + off[first], b->d_png, used, false);
+		} else if (want_ppm) {
 			const size_t used = last.rgb_off + kPpmSlot + (size_t)last.width * last.height * 3;
 			rc = download(c, s_down, dst + off[first], b->d_rgb, used, false);
 		} else {
@@ -2171,6 +2355,9 @@ static int decode_pipelined(vp8_gpu_ctx* c, const FrameGeom* geom, int n, const 
 			memcpy(dst + off[i] + kPpmSlot - hl, hdr, hl);
 			if (offsets) offsets[i] = off[i] + kPpmSlot - hl;
 			if (sizes) sizes[i] = hl + w * h * 3;
+		} else if (want_png) {
+			if (offsets) offsets[i] = off[i];
+			if (sizes) sizes[i] = vp8_png_file_bytes((uint32_t)w, (uint32_t)h);
 		} else {
 			if (offsets) offsets[i] = off[i];
 			if (sizes) sizes[i] = w * h + 2 * ((w + 1) / 2) * ((h + 1) / 2);
@@ -2229,7 +2416,7 @@ static int in_processing_order(std::vector<FrameGeom>& g, int n, size_t* offsets
 // and link is behind - was measured too: 109-197 ms; dense chunks slow the compaction threads down, both pull on the same
 // host memory.)
 static int decode_dense(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n, int filtered,
-                        bool want_ppm, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk) {
+                        int format, uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk) {
 	if (!c || !kf || !frames || !dst || n <= 0) return fail(EINVAL, "bad arguments");
 	std::vector<FrameGeom> g(n);
 	for (int i = 0; i < n; i++) {
@@ -2250,18 +2437,23 @@ static int decode_dense(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, cons
 			    return compact ? batch_create_compact(c, kfp.data() + first, frp.data() + first, cnt, slot, s_up, out)
 			                   : batch_create(c, kfp.data() + first, frp.data() + first, cnt, true, out, s_up, true);
 		    },
-		    filtered, want_ppm, dst, cap, op, sp, chunk);
+		    filtered, format, dst, cap, op, sp, chunk);
 	});
 }
 
 int vp8_gpu_decode_i420(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n, int filtered,
                         uint8_t* dst, size_t cap, size_t* offsets, size_t* sizes, int chunk) {
-	return decode_dense(c, kf, frames, n, filtered, false, dst, cap, offsets, sizes, chunk);
+	return decode_dense(c, kf, frames, n, filtered, VP8_GPU_OUT_I420, dst, cap, offsets, sizes, chunk);
 }
 
 int vp8_gpu_decode_ppm(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n, uint8_t* dst,
                        size_t cap, size_t* offsets, size_t* sizes, int chunk) {
-	return decode_dense(c, kf, frames, n, 1, true, dst, cap, offsets, sizes, chunk);
+	return decode_dense(c, kf, frames, n, 1, VP8_GPU_OUT_PPM, dst, cap, offsets, sizes, chunk);
+}
+
+int vp8_gpu_decode_png(vp8_gpu_ctx* c, const Vp8KeyFrameHeader* const* kf, const Vp8DecodedFrame* const* frames, int n, uint8_t* dst,
+                       size_t cap, size_t* offsets, size_t* sizes, int chunk) {
+	return decode_dense(c, kf, frames, n, 1, VP8_GPU_OUT_PNG, dst, cap, offsets, sizes, chunk);
 }
 
 int vp8_gpu_decode_compact(vp8_gpu_ctx* c, const Vp8CompactFrame* const* frames, int n, int filtered, int ppm, uint8_t* dst, size_t cap,
@@ -2280,7 +2472,7 @@ int vp8_gpu_decode_compact(vp8_gpu_ctx* c, const Vp8CompactFrame* const* frames,
 		    [&](int first, int cnt, int slot, cudaStream_t s_up, bool, vp8_gpu_batch** out) {
 			    return batch_create_precompact(c, frp.data() + first, cnt, slot, s_up, out);
 		    },
-		    ppm ? 1 : filtered, ppm != 0, dst, cap, op, sp, chunk);
+		    ppm ? 1 : filtered, out_format(ppm), dst, cap, op, sp, chunk);
 	});
 }
 
@@ -2302,7 +2494,7 @@ int vp8_gpu_decode_webp(vp8_gpu_ctx* c, const uint8_t* const* files, const size_
 		    [&](int first, int cnt, int slot, cudaStream_t s_up, bool, vp8_gpu_batch** out) {
 			    return batch_create_webp(c, fp.data() + first, fs.data() + first, gp + first, cnt, slot, s_up, out);
 		    },
-		    ppm ? 1 : filtered, ppm != 0, dst, cap, op, sp, chunk, /*ramp*/ false);
+		    ppm ? 1 : filtered, out_format(ppm), dst, cap, op, sp, chunk, /*ramp*/ false);
 	});
 }
 
@@ -2311,7 +2503,8 @@ size_t vp8_gpu_decode_webp_bytes(const uint8_t* const* files, const size_t* file
 	for (int i = 0; files && file_sizes && i < n; i++) {
 		uint32_t w = 0, h = 0;
 		if (vp8_parse_webp_size(files[i], file_sizes[i], &w, &h)) return 0;
-		total += ppm ? align_up(kPpmSlot + (size_t)w * h * 3) : align_up((size_t)w * h + 2 * (size_t)((w + 1) / 2) * ((h + 1) / 2));
+		if (ppm == VP8_GPU_OUT_PNG && !((3 * (uint64_t)w + 1) * h <= 0x7FFFFFFFull)) return 0;
+		total += out_slot_bytes(w, h, out_format(ppm));
 	}
 	return total;
 }
@@ -2397,7 +2590,8 @@ size_t vp8_gpu_decode_bytes(const Vp8KeyFrameHeader* const* kf, int n, int ppm) 
 	size_t total = 0;
 	for (int i = 0; kf && i < n; i++) {
 		const size_t w = kf[i]->width, h = kf[i]->height;
-		total += ppm ? align_up(kPpmSlot + w * h * 3) : align_up(w * h + 2 * ((w + 1) / 2) * ((h + 1) / 2));
+		if (ppm == VP8_GPU_OUT_PNG && !((3 * (uint64_t)w + 1) * h <= 0x7FFFFFFFull)) return 0;
+		total += out_slot_bytes(w, h, out_format(ppm));
 	}
 	return total;
 }
@@ -2448,6 +2642,7 @@ static int drain_timed(vp8_gpu_ctx* c, std::vector<std::pair<cudaEvent_t, cudaEv
 
 int vp8_gpu_kernel_time(vp8_gpu_ctx* c, double* total_ms, int* launches) { return c ? drain_timed(c, c->timed, total_ms, launches) : fail(EINVAL, "null context"); }
 int vp8_gpu_rgb_time(vp8_gpu_ctx* c, double* total_ms, int* launches) { return c ? drain_timed(c, c->timed_rgb, total_ms, launches) : fail(EINVAL, "null context"); }
+int vp8_gpu_png_time(vp8_gpu_ctx* c, double* total_ms, int* launches) { return c ? drain_timed(c, c->timed_png, total_ms, launches) : fail(EINVAL, "null context"); }
 
 // ================================================================================================ C-ABI: reference module interfaces
 
@@ -2568,7 +2763,7 @@ int vp8_loopfilter_apply_keyframe(Yuv420Image* img, const Vp8DecodedFrame* decod
 	return 0;
 }
 
-static int rgb_for_writer(int fd, const Yuv420Image* img, std::vector<uint8_t>& rgb) {
+static int rgb_for_writer(int fd, const Yuv420Image* img, std::vector<uint8_t>& rgb, bool as_png = false) {
 	if (fd < 0 || !img || !img->y || !img->u || !img->v || img->width == 0 || img->height == 0) {
 		errno = EINVAL;
 		return -1;
@@ -2576,7 +2771,7 @@ static int rgb_for_writer(int fd, const Yuv420Image* img, std::vector<uint8_t>& 
 	std::lock_guard<std::mutex> lock(g_default_mu);
 	vp8_gpu_ctx* c = default_ctx();
 	if (!c) return -1;
-	return rgb_of_host_image(c, img, rgb);
+	return rgb_of_host_image(c, img, rgb, as_png);
 }
 
 int yuv420_write_ppm_fd(int fd, const Yuv420Image* img) {
@@ -2589,9 +2784,8 @@ int yuv420_write_ppm_fd(int fd, const Yuv420Image* img) {
 }
 
 int yuv420_write_png_fd(int fd, const Yuv420Image* img) {
-	std::vector<uint8_t> rgb, png;
-	if (rgb_for_writer(fd, img, rgb)) return -1;
-	if (png_frame(rgb.data(), img->width, img->height, png)) return -1;
+	std::vector<uint8_t> png; // framed on the device: vp8_png_frame / vp8_png_finish behind the RGB kernel
+	if (rgb_for_writer(fd, img, png, true)) return -1;
 	return write_all(fd, png.data(), png.size());
 }
 

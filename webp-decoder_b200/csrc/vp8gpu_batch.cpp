@@ -126,7 +126,7 @@ static int run_share(int device, int slot, int n_devices, std::vector<Job*>& job
 	const int m = (int)frp.size();
 	if (m) {
 		// ---- one pipelined GPU call
-		const bool rgb = mode == "-ppm" || mode == "-png";
+		const int rgb = mode == "-png" ? VP8_GPU_OUT_PNG : mode == "-ppm" ? VP8_GPU_OUT_PPM : VP8_GPU_OUT_I420; // -png: framed on the device
 		const size_t cap = vp8_gpu_decode_bytes(kfp.data(), m, rgb);
 		uint8_t* out = (uint8_t*)vp8_gpu_host_alloc(cap);
 		std::vector<size_t> offs(m), sizes(m);
@@ -137,16 +137,7 @@ static int run_share(int device, int slot, int n_devices, std::vector<Job*>& job
 			// ---- write results
 			for (int k = 0; k < m; k++) {
 				const std::string base = out_dir + "/" + stem_of(dec[k]->path);
-				bool ok;
-				if (mode == "-png") { // the PNG container is framed on the host around the RGB bytes (the PPM payload)
-					const uint32_t w = kfp[k]->width, h = kfp[k]->height;
-					const uint8_t* rgbp = out + offs[k] + (sizes[k] - (size_t)w * h * 3);
-					std::vector<uint8_t> png(vp8_gpu_png_bound(w, h));
-					const size_t len = vp8_gpu_png_frame(rgbp, w, h, png.data());
-					ok = len && write_file(base + ".png", png.data(), len);
-				} else {
-					ok = write_file(base + (mode == "-ppm" ? ".ppm" : ".i420"), out + offs[k], sizes[k]);
-				}
+				const bool ok = write_file(base + (mode == "-png" ? ".png" : mode == "-ppm" ? ".ppm" : ".i420"), out + offs[k], sizes[k]);
 				if (!ok) {
 					complain("error: %s: write failed\n", base.c_str());
 					failed++;
