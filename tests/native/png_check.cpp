@@ -112,6 +112,19 @@ int main(int argc, char** argv) {
 		fclose(f);
 		return 0;
 	}
+	// the reciprocal division behind the scanline index, at both ends of its range
+	for (uint32_t w : {1u, 2u, 5u, 21u, 85u, 341u, 1365u, 1920u, 5461u, 16383u}) {
+		Geom g = geom(w, 1);
+		for (int i = 0; i < 200000; i++) {
+			const uint32_t r = i < 1000 ? (uint32_t)i : i < 2000 ? 0x7FFFFFFFu - (uint32_t)(i - 1000) : i < 3000 ? g.line * (uint32_t)(i - 2000) : (rnd() >> 1);
+			uint32_t rem;
+			const uint32_t q = div_line(g, r, rem);
+			if (q != r / g.line || rem != r % g.line) {
+				printf("div_line(%u, line %u) = %u rem %u\n", r, g.line, q, rem);
+				return 1;
+			}
+		}
+	}
 	// widths around the segment / line / block geometry, the smallest images, a file of many spans
 	static const uint32_t sizes[][2] = {{1, 1},    {1, 2},    {2, 1},     {3, 3},    {5, 1},     {4, 7},     {5, 5},   {16, 16},  {21, 13},
 	                                    {85, 3},   {129, 129}, {256, 255}, {341, 64}, {1000, 7},  {21845, 1}, {21845, 2}, {21846, 3}, {7, 9000},

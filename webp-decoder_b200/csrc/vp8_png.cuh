@@ -50,6 +50,7 @@ struct Geom {
 	uint32_t adler_at; // file offset of the Adler-32 = 37 + zsize
 	uint32_t crc_end;  // adler_at rounded down to 16: the main kernel's CRC covers [37, crc_end)
 	uint32_t file_len; // 57 + zsize
+	uint32_t line_inv; // ceil(2^32 / line): scanline position -> line by one multiplication (div_line)
 };
 
 PNG_HD Geom geom(uint32_t w, uint32_t h) {
@@ -64,7 +65,20 @@ PNG_HD Geom geom(uint32_t w, uint32_t h) {
 	g.adler_at = 37 + g.zsize;
 	g.crc_end = g.adler_at & ~15u;
 	g.file_len = 57 + g.zsize;
+	g.line_inv = 0xFFFFFFFFu / g.line + 1;
 	return g;
+}
+// r / line and r % line for r < 2^31: the estimate umulhi(r, ceil(2^32 / line)) is the quotient or one more.
+PNG_HD uint32_t div_line(const Geom& g, uint32_t r, uint32_t& rem) {
+#if defined(__CUDA_ARCH__)
+	uint32_t q = __umulhi(r, g.line_inv);
+#else
+	uint32_t q = (uint32_t)(((uint64_t)r * g.line_inv) >> 32);
+#endif
+	int32_t m = (int32_t)(r - q * g.line);
+	if (m < 0) m += (int32_t)g.line, q--;
+	rem = (uint32_t)m;
+	return q;
 }
 PNG_HD bool geom_ok(uint64_t w, uint64_t h) { return w && h && (3 * w + 1) * h <= 0x7FFFFFFFull; }
 PNG_HD uint32_t ctas_of(const Geom& g) { return (g.file_len + kSpan - 1) / kSpan; }
@@ -179,8 +193,7 @@ PNG_HD Walker walker_at(const Geom& g, uint32_t f) {
 		wk.k = z / kStoredZ;
 		wk.o = z - wk.k * kStoredZ;
 		const uint32_t r = wk.k * kStored + (wk.o > 5 ? wk.o - 5 : 0); // scanline position of the next scanline byte
-		wk.rowi = r / g.line;
-		wk.col = r - wk.rowi * g.line;
+		wk.rowi = div_line(g, r, wk.col);
 	}
 	return wk;
 }
@@ -207,18 +220,36 @@ PNG_HD uint32_t walker_next(const Geom& g, const uint8_t* head, const uint8_t* r
 	return v;
 }
 
-// Is the 16-byte segment at file offset f (a multiple of 16) a plain copy of 16 RGB bytes of one line inside one stored block?
-// If so: src = their offset in the RGB image, r0 = scanline position of the first.
-PNG_HD bool seg_is_plain(const Geom& g, uint32_t f, size_t& src, uint32_t& r0) {
-	if (f < 48) return false;
+// Is the 16-byte segment at file offset f (a multiple of 16) made of 16 scanline bytes of one stored block, at most one of them
+// a filter byte? The RGB image is tight, so those are consecutive RGB bytes with (perhaps) one zero put in between: src = offset
+// of the first RGB byte in the image, zero_at = where the filter byte goes (16 = nowhere; bytes behind it come from one RGB byte
+// earlier), r0 = scanline position of the segment's first byte.
+PNG_HD bool seg_is_copy(const Geom& g, uint32_t f, size_t& src, uint32_t& r0, uint32_t& zero_at) {
+	if (f < 48 || g.line < kSeg) return false;
 	const uint32_t z = f - kHead, k = z / kStoredZ, o = z - k * kStoredZ;
 	if (o < 5 || o + kSeg > kStoredZ) return false;
 	r0 = k * kStored + o - 5;
 	if (r0 + kSeg > g.raw) return false;
-	const uint32_t rowi = r0 / g.line, col = r0 - rowi * g.line;
-	if (col == 0 || col + kSeg > g.line) return false;
-	src = (size_t)rowi * g.row + col - 1;
+	uint32_t col;
+	const uint32_t rowi = div_line(g, r0, col);
+	const uint32_t s0 = rowi * g.row + (col ? col - 1 : 0);
+	if (s0 + kSeg > g.row * g.h) return false; // the last bytes of the image go the slow way (16 RGB bytes are read regardless)
+	src = s0;
+	zero_at = col ? g.line - col : 0;
+	if (zero_at > kSeg) zero_at = kSeg;
 	return true;
+}
+// 16 bytes s[] (little-endian words) with a zero byte put in at position at (0..15): bytes behind it move up by one, the last
+// one drops out.
+PNG_HD void insert_zero(uint32_t s[4], uint32_t at) {
+	const uint32_t t0 = s[0] << 8, t1 = (s[1] << 8) | (s[0] >> 24), t2 = (s[2] << 8) | (s[1] >> 24), t3 = (s[3] << 8) | (s[2] >> 24);
+	const uint32_t t[4] = {t0, t1, t2, t3};
+	for (int i = 0; i < 4; i++) {
+		const int d = (int)at - 4 * i; // position of the zero relative to this word
+		const uint32_t lo = d <= 0 ? 0u : d >= 4 ? 0xFFFFFFFFu : (1u << (8 * d)) - 1u;         // bytes in front of it: as they are
+		const uint32_t hi = d < 0 ? 0xFFFFFFFFu : d >= 3 ? 0u : ~((1u << (8 * d + 8)) - 1u);   // bytes behind it: moved up
+		s[i] = (s[i] & lo) | (t[i] & hi);
+	}
 }
 
 PNG_HD uint32_t dot4(uint32_t bytes, uint32_t weights, uint32_t acc) {
@@ -252,8 +283,8 @@ struct ThreadAcc {
 PNG_HD void segment(const Geom& g, const Tables* t, const uint8_t* head, const uint8_t* rgb, uint32_t f, int seg_index, uint32_t o[4],
                     ThreadAcc& acc) {
 	size_t src;
-	uint32_t r0;
-	if (seg_is_plain(g, f, src, r0)) {
+	uint32_t r0, zero_at;
+	if (seg_is_copy(g, f, src, r0, zero_at)) {
 		const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(rgb + (src & ~(size_t)3));
 		const uint32_t sh = (uint32_t)(src & 3) * 8;
 		const uint32_t w0 = wsrc[0], w1 = wsrc[1], w2 = wsrc[2], w3 = wsrc[3];
@@ -266,6 +297,7 @@ PNG_HD void segment(const Geom& g, const Tables* t, const uint8_t* head, const u
 		} else {
 			o[0] = w0, o[1] = w1, o[2] = w2, o[3] = w3;
 		}
+		if (zero_at < kSeg) insert_zero(o, zero_at); // a scanline ends inside the segment
 		seg_adler(g, o, r0, acc.a, acc.b);
 	} else {
 		Walker wk = walker_at(g, f);
