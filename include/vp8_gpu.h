@@ -75,7 +75,7 @@ const char* vp8_gpu_last_error(void);
 int vp8_gpu_set_tuning(vp8_gpu_ctx* ctx, int warps_per_image, int images_per_sm);
 
 /* Which schedule the wavefront kernel runs big batches in: 3 (default) = several images per SM run vp8_mb_lockstep (one
- * CTA per SM carries up to 7 images and all its warps meet at a barrier every third macroblock step, which keeps them
+ * CTA per SM carries up to 7 images and all its warps meet at a barrier every second macroblock step, which keeps them
  * on the same instruction-cache lines), 2 = vp8_mb_pairs (one CTA per image) whatever the batch size. Both are bit-exact;
  * the environment variable VP8_GPU_KERNEL presets it. */
 int vp8_gpu_set_kernel(vp8_gpu_ctx* ctx, int version);

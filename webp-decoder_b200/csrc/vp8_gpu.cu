@@ -146,7 +146,7 @@ struct vp8_gpu_ctx {
 	int last_cluster = 1;
 	bool last_split = false;
 	int kernel_version = 3; // 2: vp8_mb_pairs for every batch size, 3: big batches run vp8_mb_lockstep (several images
-	                        // per CTA, barrier every third step)
+	                        // per CTA, barrier every second step)
 	bool lockstep_small = true; // kernel 3: 8-warp CTAs also walk their steps in lockstep (VP8_GPU_LOCKSTEP_SMALL=0: no)
 	mutable std::unordered_map<uint64_t, int> cluster_fit; // clusters_resident()
 	bool split = true;          // cluster launches of the fused mode run vp8_mb_split: a reconstruction and a filter warp per row pair (VP8_GPU_SPLIT)

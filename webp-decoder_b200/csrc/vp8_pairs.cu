@@ -625,9 +625,9 @@ vp8_mb_split(const Vp8ImgDesc* __restrict__ descs, int n_images, int line_px, ui
 // (ctl[0]); when all NW have, the group's first warp loads the next descriptor and publishes it (ctl[1]).
 constexpr int kLockMaxGroups = 7;
 #ifndef VP8P_LOCK_BARRIER_EVERY
-#define VP8P_LOCK_BARRIER_EVERY 3
+#define VP8P_LOCK_BARRIER_EVERY 2 // build switch for the A/B runs (tools/ab_bench.sh)
 #endif
-constexpr int kLockBarrierEvery = VP8P_LOCK_BARRIER_EVERY; // the lockstep kernel's warps meet every N-th step (round 2 kernel, ms per 1024 x 1080p: 1 -> 12.87, 2 -> 12.45, 3 -> 12.21, 4 -> 12.39)
+constexpr int kLockBarrierEvery = VP8P_LOCK_BARRIER_EVERY; // the lockstep kernel's warps meet every N-th step. ms per 1024 x 1080p: round-2 step 1 -> 12.87, 2 -> 12.45, 3 -> 12.21, 4 -> 12.39; with the loop filter's early exit (lighter, less even steps) 2 -> 11.78, 3 -> 12.03, 4 -> 12.53, 5 -> 12.39
 
 // Per-image values every warp of a group needs but only now and then: kept in shared memory, not in registers.
 struct LockImage {
