@@ -841,6 +841,9 @@ int launch_wavefront(vp8_gpu_ctx* c, vp8_gpu_batch* b, int kernel_mode, int layo
 	size_t need = 0;
 	for (auto& sg : segs) need = std::max(need, vp8_pairs_scratch_bytes(sg.plan.slots(), b->max_mb_cols)); // launches run one after the other
 	if (b->scratch_bytes < need) {
+		// an earlier launch on this batch (staged calls: recon, then the stand-alone filter in another shape) may still be using
+		// the smaller scratch: it goes back to the block cache, from where any stream may take it, only once that launch is done
+		if (b->d_scratch) CU(cudaStreamSynchronize(b->stream ? b->stream : c->stream));
 		dev_release(c, b->d_scratch, b->scratch_bytes);
 		b->d_scratch = nullptr;
 		b->scratch_bytes = 0;
