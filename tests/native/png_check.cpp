@@ -128,7 +128,7 @@ int main(int argc, char** argv) {
 	// widths around the segment / line / block geometry, the smallest images, a file of many spans
 	static const uint32_t sizes[][2] = {{1, 1},    {1, 2},    {2, 1},     {3, 3},    {5, 1},     {4, 7},     {5, 5},   {16, 16},  {21, 13},
 	                                    {85, 3},   {129, 129}, {256, 255}, {341, 64}, {1000, 7},  {21845, 1}, {21845, 2}, {21846, 3}, {7, 9000},
-	                                    {1365, 48}, {1366, 49}, {640, 480}, {1000, 700}, {1920, 1080}, {16383, 5}, {3, 16383}};
+	                                    {1365, 48}, {1366, 49}, {640, 480}, {1000, 700}, {1920, 1080}, {3840, 2160}, {16383, 5}, {3, 16383}};
 	long images = 0, bytes = 0;
 	for (auto& wh : sizes)
 		for (int flavour = 0; flavour < 3; flavour++) {

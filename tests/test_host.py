@@ -153,7 +153,7 @@ def test_png_framing_arithmetic_on_the_host(tmp_path):
     """webp-decoder_b200/csrc/vp8_png.cuh (the arithmetic of the m09 kernels: byte-shifted copy with scanline / stored-block
     boundaries, Adler-32 from weighted partial sums, CRC-32 pieces combined by multiplication mod the CRC polynomial) also
     compiles for the host; tests/native/png_check.cpp replays the kernels' whole grid - every CTA, thread, reduction and the
-    finish step - for 74 images against an independent byte-at-a-time writer. One replayed file is then taken apart here
+    finish step - for 76 images against an independent byte-at-a-time writer. One replayed file is then taken apart here
     with zlib (chunk CRCs, inflate, Adler-32) and compared with the host framing the library exports
     (vp8_gpu_png_frame, itself pinned by the reference decoder's -png digests)."""
     import shutil
@@ -167,7 +167,7 @@ def test_png_framing_arithmetic_on_the_host(tmp_path):
     exe = tmp_path / "png_check"
     subprocess.run([gxx, "-O2", "-std=c++17", "-o", str(exe), str(root / "tests" / "native" / "png_check.cpp")], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert out.returncode == 0 and out.stdout.startswith("ok 74 "), out.stdout + out.stderr
+    assert out.returncode == 0 and out.stdout.startswith("ok 76 "), out.stdout + out.stderr
     w, h = 487, 301  # 3 * w + 1 = 1462; 440062 scanline bytes = 6 full stored blocks + a partial one, 7 spans
     dump = tmp_path / "replayed.png"
     assert subprocess.run([str(exe), "dump", str(w), str(h), str(dump)]).returncode == 0
