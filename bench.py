@@ -393,7 +393,12 @@ def gpu_arm(args):
     # ---- (3) BASELINE configs 3-5 in small (outside the headline's timed regions)
     configs = None
     if not args.no_configs:
-        configs = other_configs(ctx, W, P, S, torch, dist, world, rank, local, stream, job_max, sync_all, ppm_done=ppm, args=args)
+        try:
+            configs = other_configs(ctx, W, P, S, torch, dist, world, rank, local, stream, job_max, sync_all, ppm_done=ppm, args=args)
+        except Exception as e:  # the headline above is measured already: a failing side leg is reported, not allowed to swallow the line
+            import traceback
+            traceback.print_exc()
+            configs = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         peak, peak_src = measured_peak()
