@@ -212,9 +212,11 @@ int vp8_gpu_last_call_profile(const vp8_gpu_ctx* ctx, double* total_ms, double* 
  * could not be read (nothing is changed then), -1 on error. */
 int vp8_gpu_bind_host(vp8_gpu_ctx* ctx, int index, int share);
 
-/* m09 framing of an RGB24 image (what vp8_gpu_download_ppm / vp8_gpu_decode_ppm return behind the PPM header): the exact
- * bytes reference yuv420_write_png_fd emits (yuv2rgb_png.c:208-364). out must hold vp8_gpu_png_bound bytes; returns the
- * length, 0 on error. Host-side: stored deflate, CRC-32 by carry-less multiplication (PCLMULQDQ) and AVX2 Adler-32 where the
+/* m09 framing of an RGB24 image that is in HOST memory already (what vp8_gpu_download_ppm / vp8_gpu_decode_ppm return behind
+ * the PPM header): the exact bytes reference yuv420_write_png_fd emits (yuv2rgb_png.c:208-364). out must hold
+ * vp8_gpu_png_bound bytes; returns the length, 0 on error. Not what the -png paths of this library run - those frame the files
+ * on the device (vp8_gpu_png, vp8_gpu_decode_png, VP8_GPU_OUT_PNG, yuv420_write_png_fd) - but a utility for callers that hold
+ * RGB on the host, and the second opinion the tests compare the device framing with. Host-side: stored deflate, CRC-32 by carry-less multiplication (PCLMULQDQ) and AVX2 Adler-32 where the
  * CPU has them and they reproduce the slice-by-8 / scalar versions on a test pattern at start-up, those versions otherwise. */
 size_t vp8_gpu_png_bound(uint32_t width, uint32_t height);
 size_t vp8_gpu_png_frame(const uint8_t* rgb, uint32_t width, uint32_t height, uint8_t* out);
